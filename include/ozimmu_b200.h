@@ -1,0 +1,155 @@
+/*
+ * ozimmu_b200.h -- C-ABI of the B200-native Ozaki-scheme DGEMM (drop-in for enp1s0/ozIMMU).
+ *
+ * Plain C: pointers, sizes and ints only.  `stream` arguments are a cudaStream_t passed as
+ * void*.  Every function returns 0 on success; kernel launchers return the cudaError_t
+ * value otherwise, host-API functions return 1 for an invalid argument (as the reference
+ * does) or a negative number for a CUDA / internal failure.  Nothing here throws, nothing
+ * synchronises the device unless stated.
+ *
+ * Two layers live in the one shared library (ozimmu_b200/lib/libozimmu.so):
+ *
+ *  1. ozk_*   -- the kernel ABI: thin launchers over the hand-written sm_100a kernels
+ *                (ozimmu_b200/csrc/split.cu, gemm_fused.cu).  Raw device pointers.
+ *  2. ozimmu_* -- the host API: a C spelling of the reference's public C++ interface
+ *                (reference include/ozimmu/ozimmu.hpp:47-100).  The same library also
+ *                exports that C++ interface itself (namespace mtk::ozimmu, declared in
+ *                include/ozimmu/ozimmu.hpp of this repo) and the cuBLAS interposers
+ *                (cublasDgemm_v2, cublasGemmEx, ... -- reference src/cublas.cu:103-513),
+ *                so LD_PRELOAD=libozimmu.so behaves like the reference's libozimmu.so.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference tree).
+ */
+#ifndef OZIMMU_B200_H
+#define OZIMMU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------
+ * Enumerations (values identical to reference include/ozimmu/ozimmu.hpp:12-45)
+ * ------------------------------------------------------------------------------------- */
+enum { OZIMMU_OP_N = 0, OZIMMU_OP_T = 1 };                      /* operation_t   :12 */
+enum {                                                          /* compute_mode_t :14-37 */
+  OZIMMU_SGEMM = 0,
+  OZIMMU_DGEMM = 1,
+  OZIMMU_FP64_INT8_3 = 2, /* fp64_int8_S == S - 1 for S = 3..18 */
+  OZIMMU_FP64_INT8_18 = 17,
+  OZIMMU_FP64_INT8_AUTO = 18
+};
+enum { OZIMMU_MALLOC_SYNC = 0, OZIMMU_MALLOC_ASYNC = 1 };       /* malloc_mode_t :41 */
+enum { OZIMMU_REAL = 0, OZIMMU_COMPLX = 1 };                    /* element_kind_t :43-46 */
+
+typedef struct ozimmu_handle_s *ozimmu_handle_t;                /* mtk::ozimmu::handle_t :9-11 */
+
+/* ---------------------------------------------------------------------------------------
+ * 1. Kernel ABI (device pointers; asynchronous on `stream`)
+ * ------------------------------------------------------------------------------------- */
+
+/* reference src/split.cu:520-536 get_bits_per_int8 */
+uint32_t ozk_bits_per_int8(uint32_t k);
+
+/* Row pitch (bytes == elements) of one int8 slice row for inner length k: k rounded up to a
+ * multiple of 16 (TMA global strides must be 16-byte multiples).  The reference pads to 4
+ * (src/utils.hpp:30-39); the padding is zero in both, so products are identical. */
+size_t ozk_slice_pitch(size_t k);
+
+/* reference src/split.cu:193-283 (split_int8_kernel + split_int8_A/split_int8):
+ * per-"row" max exponent scan and FP64 -> num_split x int8 mantissa split.
+ *   in        : rows x len view of op(X).  col_major != 0: element (r,c) = in[c*ld + r]
+ *               (op_n A / op_t B), else in[r*ld + c] (op_t A / op_n B).
+ *   out       : [num_split][rows][pitch] int8, K contiguous, bytes len..pitch-1 zero.
+ *   max_exp   : [rows] doubles, 2 * 2^(emax-1023) (reference :191,202-204,234-241).
+ *   scratch   : [rows] uint32 device scratch (only used when col_major != 0).
+ */
+int ozk_split_int8(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, size_t rows,
+                   size_t len, const double *in, size_t ld, int col_major, unsigned num_split,
+                   unsigned bits_per_int8, void *stream);
+
+/* reference src/gemm.cu:266-334 (matmul_core -> cublasGemmEx int8) + :77-102
+ * (accumulate_in_f64) + :104-122 (init_accumulator_buffer) + :124-158 (axby), fused:
+ * for every (i,j) of the reference pair order (src/config.cu:85-92) an exact
+ * int8 x int8 -> int32 product on tcgen05 tensor cores, accumulated per element in FP64 in
+ * the reference's op order, then scaled by 2^-44 * amax[r] * bmax[c] and written as
+ * C = alpha*x (+ beta*C).  C is column-major with leading dimension ldc; alpha/beta by value.
+ */
+int ozk_gemm_i8_fused(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
+                      size_t pitch, const double *amax, const double *bmax, unsigned num_split,
+                      unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
+                      void *stream);
+
+/* Degenerate k == 0 product: C = beta * C (C not read when beta == 0; reference
+ * src/gemm.cu:143-147 applied to an all-zero accumulator). */
+int ozk_scale_c(size_t m, size_t n, double beta, double *c, size_t ldc, void *stream);
+
+/* Test/tuning hook: force the thread-block-cluster shape (cm x cn CTAs sharing TMA-multicast
+ * operand tiles) of the fused kernel; (0,0) restores the built-in heuristic. */
+int ozk_set_cluster_shape(int cm, int cn);
+
+/* Debug/verification launcher: the raw int32 product of ONE slice pair (1-based ids), written
+ * column-major with ld = m -- what the reference's cublasGemmEx call produces
+ * (src/gemm.cu:315-329).  Same tcgen05 main loop as ozk_gemm_i8_fused. */
+int ozk_gemm_i8_pair(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
+                     size_t pitch, unsigned num_split, unsigned a_id, unsigned b_id, int32_t *c_i32,
+                     void *stream);
+
+/* reference src/split.cu:302-380 (init counter + calculate_mantissa_loss_kernel):
+ * adds, for num_split = 3..18, sum over elements of max(0, (emax+1-e)+53 - num_split*bits)
+ * into counters[16] (device, uint64).  Does not zero the counters. */
+int ozk_mantissa_loss(unsigned long long *counters16, uint32_t *scratch, size_t rows, size_t len,
+                      const double *in, size_t ld, int col_major, unsigned bits_per_int8,
+                      void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * 2. Host API (C spelling of reference include/ozimmu/ozimmu.hpp)
+ * ------------------------------------------------------------------------------------- */
+int ozimmu_create(ozimmu_handle_t *handle, int malloc_mode);                     /* :47  */
+int ozimmu_destroy(ozimmu_handle_t handle);                                      /* :48  */
+int ozimmu_set_cuda_stream(ozimmu_handle_t handle, void *stream);                /* :49-50 */
+int ozimmu_enable_profiling(ozimmu_handle_t handle);                             /* :52  */
+int ozimmu_disable_profiling(ozimmu_handle_t handle);                            /* :53  */
+int ozimmu_print_profiler_result(ozimmu_handle_t handle, const char *tag, int csv); /* :54-55 */
+int ozimmu_clear_profiler_result(ozimmu_handle_t handle);                        /* :56  */
+int ozimmu_set_auto_mantissa_loss_threshold(ozimmu_handle_t handle, double t);   /* :58-59 */
+double ozimmu_get_auto_mantissa_loss_threshold(ozimmu_handle_t handle);          /* :60  */
+
+/* :68-74 -- returns the new size in bytes if the workspace grew, else 0 */
+size_t ozimmu_reallocate_working_memory(ozimmu_handle_t handle, int op_a, int op_b, size_t m,
+                                        size_t n, size_t k, int element_kind, int compute_mode);
+size_t ozimmu_reallocate_working_memory_bytes(ozimmu_handle_t handle, size_t size_in_byte);
+
+/* :76-83 -- alpha/beta are HOST pointers (double for real, double[2] for complex); a/b/c are
+ * device pointers; BLAS column-major. 0 ok, 1 invalid argument, <0 CUDA failure. */
+int ozimmu_gemm(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                const void *alpha, const void *a, size_t lda, const void *b, size_t ldb,
+                const void *beta, void *c, size_t ldc, int compute_mode, int element_kind);
+
+/* :85-94 -- returns the selected compute mode (OZIMMU_FP64_INT8_3.. or OZIMMU_DGEMM);
+ * negative on failure.  counters16 (host, optional) receives the 16 loss totals. */
+int ozimmu_auto_mode_select(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n,
+                            size_t k, const void *a, size_t lda, const void *b, size_t ldb,
+                            int element_kind, double mantissa_loss_threshold,
+                            unsigned long long *counters16);
+
+const char *ozimmu_get_compute_mode_name_str(int compute_mode);                  /* :96  */
+uint32_t ozimmu_get_bits_per_int8(uint32_t k);                                   /* :102 */
+
+/* Same as ozimmu_gemm but a/b/c are HOST buffers (pinned for full speed): stages H2D copies,
+ * split, products and the D2H copy of C on internal streams and returns when C is complete.
+ * This is the end-to-end entry `bench.py` times as "e2e". */
+int ozimmu_gemm_host(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                     const double *alpha, const double *a, size_t lda, const double *b, size_t ldb,
+                     const double *beta, double *c, size_t ldc, int compute_mode);
+
+/* Number of kernels this library launched since load (bench.py's gpu_launches). */
+unsigned long long ozimmu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OZIMMU_B200_H */

@@ -1,0 +1,464 @@
+// api.cu -- the public interface: namespace mtk::ozimmu (source-compatible with reference
+// include/ozimmu/ozimmu.hpp:47-100) and its plain-C spelling (include/ozimmu_b200.h).
+//
+// Host orchestration of one DGEMM (replaces reference src/gemm.cu:344-410 gemm_int8<double> and
+// :524-653 mtk::ozimmu::gemm, src/handle.cu, src/split.cu:454-518 auto_mode_select):
+//
+//   stream:      [wait prev]  split(A) -------------+
+//   aux stream:  [fork]       split(B) --[join]------> fused tcgen05 product+accumulate+finalize
+//
+// No device-wide synchronisation, no per-call allocation once the workspace has grown, two
+// (row-contiguous operand) or three launches per operand-free call instead of the reference's
+// 2*P(s)+4.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "host.hpp"
+#include "oz_common.cuh"
+#include "ozimmu_b200.h"
+
+using namespace mtk::ozimmu;
+namespace H = oz::host;
+
+void oz::host::ensure_streams(mtk::ozimmu::handle *h) {
+  if (h->aux_stream) return;
+  OZ_CUDA_CHECK(cudaGetDevice(&h->device));
+  OZ_CUDA_CHECK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+  OZ_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  OZ_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  OZ_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+}
+
+namespace {
+using oz::host::ensure_streams;
+
+// reference src/utils.hpp:143-156 check_gemm_shape
+int check_shape(operation_t op, std::size_t rows, std::size_t cols, std::size_t ld, const char *name) {
+  const std::size_t need = (op == op_n) ? rows : cols;
+  if (need > ld) {
+    H::log_error(std::string("The leading dimension of ") + name + " (" + std::to_string(ld) +
+                 ") must be larger or equal to the number of " + (op == op_n ? "rows" : "cols") + " (" +
+                 std::to_string(need) + ")");
+    return 1;
+  }
+  return 0;
+}
+
+// reference src/utils.hpp:158-168 check_address_alignment
+int check_alignment(const void *p, std::size_t size, const char *name) {
+  if (reinterpret_cast<std::uintptr_t>(p) % size) {
+    H::log_error(std::string("Invalid address alignment for matrix ") + name);
+    return 1;
+  }
+  return 0;
+}
+
+cublasHandle_t private_cublas(handle_t h) {
+  if (h->cublas_handle == nullptr) {
+    using Fn = cublasStatus_t (*)(cublasHandle_t *);
+    auto fn = reinterpret_cast<Fn>(H::real_cublas_symbol("cublasCreate_v2"));
+    if (fn == nullptr || fn(&h->cublas_handle) != CUBLAS_STATUS_SUCCESS)
+      throw std::runtime_error("ozIMMU: cuBLAS is not available for the dgemm passthrough");
+  }
+  using SetStream = cublasStatus_t (*)(cublasHandle_t, cudaStream_t);
+  auto set_stream = reinterpret_cast<SetStream>(H::real_cublas_symbol("cublasSetStream_v2"));
+  if (set_stream) set_stream(h->cublas_handle, h->cuda_stream);
+  return h->cublas_handle;
+}
+
+// Order this call after the previous user of the shared workspace if that one ran on another stream.
+void wait_previous(handle_t h, cudaStream_t s) {
+  if (h->has_pending && h->last_stream != s) OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_done, 0));
+}
+void mark_done(handle_t h, cudaStream_t s) {
+  OZ_CUDA_CHECK(cudaEventRecord(h->ev_done, s));
+  h->has_pending = true;
+  h->last_stream = s;
+}
+
+// reference src/gemm.cu:344-410 gemm_int8<double>
+void gemm_int8_real(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n,
+                    std::size_t k, double alpha, const double *a, std::size_t lda, const double *b,
+                    std::size_t ldb, double beta, double *c, std::size_t ldc, unsigned num_split) {
+  if (m == 0 || n == 0) return;
+  if (k == 0) {
+    OZ_KERNEL_CHECK(ozk_scale_c(m, n, beta, c, ldc, h->cuda_stream));
+    return;
+  }
+  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
+  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split);
+  reallocate_working_memory(h, w.total);
+  ensure_streams(h);
+  char *ws = static_cast<char *>(h->working_memory_ptr);
+  double *amax = reinterpret_cast<double *>(ws + w.off_amax);
+  double *bmax = reinterpret_cast<double *>(ws + w.off_bmax);
+  auto *scr_a = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_a);
+  auto *scr_b = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_b);
+  auto *a_sl = reinterpret_cast<std::int8_t *>(ws + w.off_a_slices);
+  auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
+  cudaStream_t s = h->cuda_stream;
+  wait_previous(h, s);
+
+  // "rows" of the split are rows of op(A) and columns of op(B) (reference src/split.cu:266-283):
+  //   op_n A (m x k, col-major)  -> row r strided by lda  -> col_major
+  //   op_n B (k x n, col-major)  -> column j contiguous   -> !col_major
+  const int a_col_major = (op_a == op_n), b_col_major = (op_b != op_n);
+  const bool overlap = !h->profiler.enabled;
+  if (overlap) {
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    OZ_KERNEL_CHECK(ozk_split_int8(a_sl, w.pitch, amax, scr_a, m, k, a, lda, a_col_major, num_split, bits, s));
+    OZ_KERNEL_CHECK(ozk_split_int8(b_sl, w.pitch, bmax, scr_b, n, k, b, ldb, b_col_major, num_split, bits,
+                                   h->aux_stream));
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, h->aux_stream));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
+  } else {
+    h->profiler.start("split_A", s);
+    OZ_KERNEL_CHECK(ozk_split_int8(a_sl, w.pitch, amax, scr_a, m, k, a, lda, a_col_major, num_split, bits, s));
+    h->profiler.stop("split_A", s);
+    h->profiler.start("split_B", s);
+    OZ_KERNEL_CHECK(ozk_split_int8(b_sl, w.pitch, bmax, scr_b, n, k, b, ldb, b_col_major, num_split, bits, s));
+    h->profiler.stop("split_B", s);
+  }
+  h->profiler.start("int8tc_accumulate_fused", s);
+  OZ_KERNEL_CHECK(ozk_gemm_i8_fused(m, n, k, a_sl, b_sl, w.pitch, amax, bmax, num_split, bits, alpha, beta, c,
+                                    ldc, s));
+  h->profiler.stop("int8tc_accumulate_fused", s);
+  mark_done(h, s);
+}
+
+template <class F>
+int guarded(F &&f) {
+  try {
+    return f();
+  } catch (const std::exception &e) {
+    H::log_error(e.what());
+    return -1;
+  }
+}
+
+}  // namespace
+
+// ===============================================================================================
+// namespace mtk::ozimmu
+// ===============================================================================================
+int mtk::ozimmu::create(handle_t *handle, const malloc_mode_t mm) {
+  H::log_info("Initializing ozIMMU handle");
+  auto h = (*handle = new mtk::ozimmu::handle);
+  h->malloc_mode = mm;
+  OZ_CUDA_CHECK(cudaMalloc(&h->d_mantissa_loss_counter_ptr,
+                           sizeof(unsigned long long) * handle::mantissa_loss_counter_length));
+  OZ_CUDA_CHECK(cudaMallocHost(&h->h_mantissa_loss_counter_ptr,
+                               sizeof(unsigned long long) * handle::mantissa_loss_counter_length));
+  // reference src/handle.cu:25-30 (defaults 1024; README says 128 -- SURVEY App. B.3)
+  h->intercept_threshold_m = std::stoul(H::env_or("OZIMMU_INTERCEPT_THRESHOLD_M", "1024"));
+  h->intercept_threshold_n = std::stoul(H::env_or("OZIMMU_INTERCEPT_THRESHOLD_N", "1024"));
+  h->intercept_threshold_k = std::stoul(H::env_or("OZIMMU_INTERCEPT_THRESHOLD_K", "1024"));
+  return 0;
+}
+
+int mtk::ozimmu::destroy(handle_t h) {
+  if (h == nullptr) return 0;
+  H::log_info("Destroying ozIMMU handle");
+  cudaDeviceSynchronize();
+  if (h->cublas_handle) {
+    using Fn = cublasStatus_t (*)(cublasHandle_t);
+    if (auto fn = reinterpret_cast<Fn>(H::real_cublas_symbol("cublasDestroy_v2"))) fn(h->cublas_handle);
+  }
+  cudaFree(h->working_memory_ptr);
+  cudaFree(h->d_mantissa_loss_counter_ptr);
+  cudaFreeHost(h->h_mantissa_loss_counter_ptr);
+  cudaFree(h->stage_a);
+  cudaFree(h->stage_b);
+  cudaFree(h->stage_c);
+  for (cudaStream_t s : {h->aux_stream, h->h2d_stream, h->d2h_stream, h->compute_stream})
+    if (s) cudaStreamDestroy(s);
+  for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_done, h->ev_a_in})
+    if (e) cudaEventDestroy(e);
+  for (int i = 0; i < handle::kMaxPanels; i++) {
+    if (h->ev_panel_in[i]) cudaEventDestroy(h->ev_panel_in[i]);
+    if (h->ev_panel_out[i]) cudaEventDestroy(h->ev_panel_out[i]);
+  }
+  delete h;
+  return 0;
+}
+
+void mtk::ozimmu::set_cuda_stream(handle_t handle, const cudaStream_t cuda_stream) {
+  handle->cuda_stream = cuda_stream;
+}
+
+void mtk::ozimmu::enable_profiling(handle_t handle) { handle->profiler.enabled = true; }
+void mtk::ozimmu::disable_profiling(handle_t handle) { handle->profiler.enabled = false; }
+void mtk::ozimmu::print_profiler_result(handle_t handle, const std::string tag, const bool csv) {
+  handle->profiler.print(tag, csv);
+}
+void mtk::ozimmu::clear_profiler_result(handle_t handle) { handle->profiler.clear(); }
+
+void mtk::ozimmu::set_auto_mantissa_loss_threashold(handle_t handle, const double threshold) {
+  handle->avg_mantissa_loss_threshold = threshold;
+}
+double mtk::ozimmu::get_auto_mantissa_loss_threashold(handle_t handle) {
+  return handle->avg_mantissa_loss_threshold;
+}
+
+// reference src/handle.cu:63-93 (grow-only)
+std::size_t mtk::ozimmu::reallocate_working_memory(handle_t h, const std::size_t size_in_byte) {
+  if (size_in_byte <= h->current_working_memory_size) return 0;
+  H::log_info("Reallocated memory : " + std::to_string(size_in_byte) + " B");
+  if (h->working_memory_ptr != nullptr) {
+    if (h->malloc_mode == malloc_sync) {
+      OZ_CUDA_CHECK(cudaDeviceSynchronize());
+      OZ_CUDA_CHECK(cudaFree(h->working_memory_ptr));
+    } else {
+      // the old block may still be in use by work queued on the previous stream
+      if (h->has_pending) OZ_CUDA_CHECK(cudaStreamWaitEvent(h->cuda_stream, h->ev_done, 0));
+      OZ_CUDA_CHECK(cudaFreeAsync(h->working_memory_ptr, h->cuda_stream));
+    }
+    h->working_memory_ptr = nullptr;
+  }
+  h->current_working_memory_size = 0;
+  if (h->malloc_mode == malloc_sync) {
+    OZ_CUDA_CHECK(cudaMalloc(&h->working_memory_ptr, size_in_byte));
+  } else {
+    OZ_CUDA_CHECK(cudaMallocAsync(&h->working_memory_ptr, size_in_byte, h->cuda_stream));
+  }
+  h->current_working_memory_size = size_in_byte;
+  return size_in_byte;
+}
+
+// reference src/handle.cu:95-144 -- sized for this library's layout (no FP64/int32 m*n buffers)
+std::size_t mtk::ozimmu::reallocate_working_memory(handle_t h, const gemm_list_t gemm_list) {
+  std::size_t need = 0;
+  for (const auto &g : gemm_list) {
+    const std::size_t m = std::get<2>(g), n = std::get<3>(g), k = std::get<4>(g);
+    const element_kind_t kind = std::get<5>(g);
+    const compute_mode_t mode = std::get<6>(g);
+    unsigned s = 0;
+    if (H::is_int8_mode(mode)) s = H::num_split_of(mode);
+    else if (mode == fp64_int8_auto) s = 18;
+    if (s == 0) continue;
+    std::size_t bytes = H::workspace_layout(m, n, k, s).total;
+    if (kind == complx) bytes *= 2;
+    need = std::max(need, bytes);
+  }
+  return reallocate_working_memory(h, need);
+}
+
+std::string mtk::ozimmu::get_compute_mode_name_str(const compute_mode_t mode) {
+  if (mode == sgemm) return "sgemm";
+  if (mode == dgemm) return "dgemm";
+  if (mode == fp64_int8_auto) return "fp64_int8_auto";
+  if (H::is_int8_mode(mode)) return "fp64_int8_" + std::to_string(H::num_split_of(mode));
+  throw std::runtime_error("ozIMMU: unknown compute mode " + std::to_string(static_cast<int>(mode)));
+}
+
+// reference src/handle.cu:194-225
+data_t mtk::ozimmu::get_output_type(const compute_mode_t mode) {
+  if (mode == sgemm) return fp32;
+  if (mode == dgemm || mode == fp64_int8_auto || H::is_int8_mode(mode)) return fp64;
+  throw std::runtime_error("ozIMMU: unknown compute mode " + std::to_string(static_cast<int>(mode)));
+}
+
+// reference src/handle.cu:227-244
+std::size_t mtk::ozimmu::get_data_size_in_byte(const data_t d) {
+  switch (d) {
+    case fp64: return 8;
+    case fp32: return 4;
+    case fp16: return 2;
+    case int8: return 1;
+    case none: return 0;
+    default: throw std::runtime_error("ozIMMU: data type has no size");
+  }
+}
+
+std::uint32_t mtk::ozimmu::get_bits_per_int8(const std::uint32_t k) { return ozk_bits_per_int8(k); }
+
+// reference src/split.cu:454-518
+compute_mode_t mtk::ozimmu::auto_mode_select(handle_t h, const operation_t op_A, const operation_t op_B,
+                                             const std::size_t m, const std::size_t n, const std::size_t k,
+                                             const void *const a_ptr, const std::size_t lda,
+                                             const void *const b_ptr, const std::size_t ldb,
+                                             const element_kind_t element_kind,
+                                             const double mantissa_loss_threshold) {
+  if (element_kind != real) throw std::runtime_error("ozIMMU: complex auto mode is not implemented");
+  constexpr int N = handle::mantissa_loss_counter_length;
+  for (int i = 0; i < N; i++) h->last_loss_counters[i] = 0;
+  if (m == 0 || n == 0 || k == 0) return fp64_int8_3;
+  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
+  const std::size_t scr_bytes = sizeof(std::uint32_t) * std::max(m, n);
+  reallocate_working_memory(h, scr_bytes);
+  ensure_streams(h);
+  cudaStream_t s = h->cuda_stream;
+  wait_previous(h, s);
+  auto *scr = static_cast<std::uint32_t *>(h->working_memory_ptr);
+  OZ_CUDA_CHECK(cudaMemsetAsync(h->d_mantissa_loss_counter_ptr, 0, sizeof(unsigned long long) * N, s));
+  OZ_KERNEL_CHECK(ozk_mantissa_loss(h->d_mantissa_loss_counter_ptr, scr, m, k, static_cast<const double *>(a_ptr),
+                                    lda, op_A == op_n, bits, s));
+  OZ_KERNEL_CHECK(ozk_mantissa_loss(h->d_mantissa_loss_counter_ptr, scr, n, k, static_cast<const double *>(b_ptr),
+                                    ldb, op_B != op_n, bits, s));
+  OZ_CUDA_CHECK(cudaMemcpyAsync(h->h_mantissa_loss_counter_ptr, h->d_mantissa_loss_counter_ptr,
+                                sizeof(unsigned long long) * N, cudaMemcpyDeviceToHost, s));
+  mark_done(h, s);
+  OZ_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int i = 0; i < N; i++) h->last_loss_counters[i] = h->h_mantissa_loss_counter_ptr[i];
+  // reference src/split.cu:484-493: first split count whose average loss is within the threshold
+  const double denom = static_cast<double>(m * k + k * n);
+  for (int i = 0; i < N; i++)
+    if (static_cast<double>(h->last_loss_counters[i]) / denom <= mantissa_loss_threshold)
+      return H::mode_of_num_split(static_cast<unsigned>(i) + 3u);
+  return dgemm;
+}
+
+int mtk::ozimmu::gemm(handle_t h, const operation_t op_A, const operation_t op_B, const std::size_t m,
+                      const std::size_t n, const std::size_t k, const void *alpha, const void *const a_ptr,
+                      const std::size_t lda, const void *const b_ptr, const std::size_t ldb, const void *beta,
+                      void *const c_ptr, std::size_t ldc, const compute_mode_t compute_mode,
+                      const element_kind_t element_kind) {
+  int arg_error = 0;
+  arg_error |= check_shape(op_A, m, k, lda, "A");
+  arg_error |= check_shape(op_B, k, n, ldb, "B");
+  arg_error |= check_shape(op_n, m, n, ldc, "C");
+  const std::size_t esz = element_kind == real ? sizeof(double) : 2 * sizeof(double);
+  arg_error |= check_alignment(a_ptr, esz, "A");
+  arg_error |= check_alignment(b_ptr, esz, "B");
+  arg_error |= check_alignment(c_ptr, esz, "C");
+  if (arg_error) return 1;
+
+  if (H::is_int8_mode(compute_mode)) {
+    if (element_kind != real) throw std::runtime_error("ozIMMU: the complex int8 path is not implemented");
+    gemm_int8_real(h, op_A, op_B, m, n, k, *static_cast<const double *>(alpha), static_cast<const double *>(a_ptr),
+                   lda, static_cast<const double *>(b_ptr), ldb, *static_cast<const double *>(beta),
+                   static_cast<double *>(c_ptr), ldc, H::num_split_of(compute_mode));
+    return 0;
+  }
+  if (compute_mode == fp64_int8_auto) {
+    const compute_mode_t chosen = auto_mode_select(h, op_A, op_B, m, n, k, a_ptr, lda, b_ptr, ldb, element_kind,
+                                                   h->avg_mantissa_loss_threshold);
+    H::log_info("AUTO selected mode = " + get_compute_mode_name_str(chosen) +
+                ", threshold average mantissa loss = " + std::to_string(h->avg_mantissa_loss_threshold));
+    return gemm(h, op_A, op_B, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc, chosen, element_kind);
+  }
+  if (compute_mode == dgemm) {
+    using Fn = cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void *,
+                                  const void *, cudaDataType_t, int, const void *, cudaDataType_t, int, const void *,
+                                  void *, cudaDataType_t, int, cublasComputeType_t, cublasGemmAlgo_t);
+    auto fn = reinterpret_cast<Fn>(H::real_cublas_symbol("cublasGemmEx"));
+    if (fn == nullptr) throw std::runtime_error("ozIMMU: cublasGemmEx is not available for the dgemm passthrough");
+    const cudaDataType_t dt = element_kind == real ? CUDA_R_64F : CUDA_C_64F;
+    const cublasStatus_t st =
+        fn(private_cublas(h), op_A == op_n ? CUBLAS_OP_N : CUBLAS_OP_T, op_B == op_n ? CUBLAS_OP_N : CUBLAS_OP_T,
+           static_cast<int>(m), static_cast<int>(n), static_cast<int>(k), alpha, a_ptr, dt, static_cast<int>(lda),
+           b_ptr, dt, static_cast<int>(ldb), beta, c_ptr, dt, static_cast<int>(ldc), CUBLAS_COMPUTE_64F,
+           CUBLAS_GEMM_DEFAULT);
+    if (st != CUBLAS_STATUS_SUCCESS)
+      throw std::runtime_error("ozIMMU: cublasGemmEx passthrough failed with status " + std::to_string(st));
+    return 0;
+  }
+  throw std::runtime_error("ozIMMU: compute mode " + get_compute_mode_name_str(compute_mode) +
+                           " is not implemented");
+}
+
+// ===============================================================================================
+// C spelling
+// ===============================================================================================
+extern "C" {
+
+int ozimmu_create(ozimmu_handle_t *handle, int malloc_mode) {
+  return guarded([&] {
+    return create(reinterpret_cast<handle_t *>(handle), static_cast<malloc_mode_t>(malloc_mode));
+  });
+}
+int ozimmu_destroy(ozimmu_handle_t handle) {
+  return guarded([&] { return destroy(reinterpret_cast<handle_t>(handle)); });
+}
+int ozimmu_set_cuda_stream(ozimmu_handle_t handle, void *stream) {
+  set_cuda_stream(reinterpret_cast<handle_t>(handle), static_cast<cudaStream_t>(stream));
+  return 0;
+}
+int ozimmu_enable_profiling(ozimmu_handle_t handle) {
+  enable_profiling(reinterpret_cast<handle_t>(handle));
+  return 0;
+}
+int ozimmu_disable_profiling(ozimmu_handle_t handle) {
+  disable_profiling(reinterpret_cast<handle_t>(handle));
+  return 0;
+}
+int ozimmu_print_profiler_result(ozimmu_handle_t handle, const char *tag, int csv) {
+  print_profiler_result(reinterpret_cast<handle_t>(handle), tag ? tag : "", csv != 0);
+  return 0;
+}
+int ozimmu_clear_profiler_result(ozimmu_handle_t handle) {
+  clear_profiler_result(reinterpret_cast<handle_t>(handle));
+  return 0;
+}
+int ozimmu_set_auto_mantissa_loss_threshold(ozimmu_handle_t handle, double t) {
+  set_auto_mantissa_loss_threashold(reinterpret_cast<handle_t>(handle), t);
+  return 0;
+}
+double ozimmu_get_auto_mantissa_loss_threshold(ozimmu_handle_t handle) {
+  return get_auto_mantissa_loss_threashold(reinterpret_cast<handle_t>(handle));
+}
+
+size_t ozimmu_reallocate_working_memory(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                                        int element_kind, int compute_mode) {
+  size_t r = 0;
+  guarded([&] {
+    r = reallocate_working_memory(
+        reinterpret_cast<handle_t>(handle),
+        gemm_list_t{{static_cast<operation_t>(op_a), static_cast<operation_t>(op_b), m, n, k,
+                     static_cast<element_kind_t>(element_kind), static_cast<compute_mode_t>(compute_mode)}});
+    return 0;
+  });
+  return r;
+}
+size_t ozimmu_reallocate_working_memory_bytes(ozimmu_handle_t handle, size_t size_in_byte) {
+  size_t r = 0;
+  guarded([&] {
+    r = reallocate_working_memory(reinterpret_cast<handle_t>(handle), size_in_byte);
+    return 0;
+  });
+  return r;
+}
+
+int ozimmu_gemm(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k, const void *alpha,
+                const void *a, size_t lda, const void *b, size_t ldb, const void *beta, void *c, size_t ldc,
+                int compute_mode, int element_kind) {
+  if (handle == nullptr || alpha == nullptr || beta == nullptr || compute_mode < 0 ||
+      compute_mode > OZIMMU_FP64_INT8_AUTO || (element_kind != OZIMMU_REAL && element_kind != OZIMMU_COMPLX))
+    return 1;
+  return guarded([&] {
+    return gemm(reinterpret_cast<handle_t>(handle), static_cast<operation_t>(op_a != 0),
+                static_cast<operation_t>(op_b != 0), m, n, k, alpha, a, lda, b, ldb, beta, c, ldc,
+                static_cast<compute_mode_t>(compute_mode), static_cast<element_kind_t>(element_kind));
+  });
+}
+
+int ozimmu_auto_mode_select(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                            const void *a, size_t lda, const void *b, size_t ldb, int element_kind,
+                            double mantissa_loss_threshold, unsigned long long *counters16) {
+  if (handle == nullptr) return -1;
+  return guarded([&] {
+    auto h = reinterpret_cast<handle_t>(handle);
+    const compute_mode_t mode =
+        auto_mode_select(h, static_cast<operation_t>(op_a != 0), static_cast<operation_t>(op_b != 0), m, n, k, a,
+                         lda, b, ldb, static_cast<element_kind_t>(element_kind), mantissa_loss_threshold);
+    if (counters16)
+      std::memcpy(counters16, h->last_loss_counters, sizeof(unsigned long long) * handle::mantissa_loss_counter_length);
+    return static_cast<int>(mode);
+  });
+}
+
+const char *ozimmu_get_compute_mode_name_str(int compute_mode) {
+  static thread_local std::string name;
+  try {
+    name = get_compute_mode_name_str(static_cast<compute_mode_t>(compute_mode));
+  } catch (const std::exception &) {
+    return nullptr;
+  }
+  return name.c_str();
+}
+
+uint32_t ozimmu_get_bits_per_int8(uint32_t k) { return ozk_bits_per_int8(k); }
+
+}  // extern "C"

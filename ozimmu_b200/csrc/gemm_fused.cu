@@ -1,0 +1,486 @@
+// gemm_fused.cu -- the hot path: s(s+1)/2 exact int8 x int8 -> int32 slice products on tcgen05
+// tensor cores, each folded into a per-element FP64 accumulator in the reference's exact op
+// order, then the exponent rescale and alpha/beta -- ONE persistent kernel.
+//
+// Replaces, fused: reference src/gemm.cu:266-334 (matmul_core -> cublasGemmEx int8, 45 library
+// GEMMs at s=9), :77-102 (accumulate_in_f64, one 20 B/element HBM pass per product), :104-122
+// (init_accumulator_buffer) and :124-158 (axby).  Arithmetic per output element follows SURVEY
+// App. A.4/A.5 exactly (same FMA sequence => bit-identical C).
+//
+// Design (B200 / sm_100a):
+//  * Persistent CTAs, one per SM.  Each CTA owns a 128x128 tile of C for the whole pair list, so
+//    the FP64 accumulator never leaves the SM: it lives in the registers of 8 epilogue warps
+//    (256 threads x 64 doubles).  HBM sees the int8 slices (mostly from L2) and C exactly once.
+//  * Warp roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one thread), warp 2 = TMEM
+//    allocator, warps 4-11 = epilogue.  setmaxnreg moves registers from warps 0-3 to the epilogue.
+//  * Operands: K-major int8 slices [slice][row][pitch]; TMA (3-D tensor map: k, row, slice) stages
+//    128x128-byte tiles with the 128-byte swizzle into a 6-deep SMEM ring; UMMA M=128,N=128,K=32
+//    kind::i8 accumulates a full-K product into one of 4 TMEM buffers (128 columns each), so the
+//    MMA pipe runs up to 3 products ahead of the epilogue.
+//  * Optional thread-block clusters (CM x CN CTAs): the A tile is TMA-multicast across the CN CTAs
+//    that share a row block and the B tile across the CM CTAs that share a column block, cutting
+//    L2->SMEM traffic per SM from 128 to 128*(1/CN+1/CM)/2 bytes per MMA-cycle.
+//  * Epilogue per product: tcgen05.ld 64 int32 columns of the thread's row, release the TMEM
+//    buffer, acc = fma((double)p, 2^(32-rshift), acc).  After the last pair:
+//    x = acc*2^-44*amax[r]*bmax[c]; C = alpha*x (+ beta*C), coalesced along rows of column-major C.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "oz_common.cuh"
+#include "ozimmu_b200.h"
+#include "ptx.cuh"
+
+namespace oz {
+namespace {
+
+constexpr uint32_t BM = 128, BN = 128, BK = 128;  // tile (BK in bytes == int8 elements)
+constexpr uint32_t kStages = 6;
+constexpr uint32_t kAccBufs = 4;                  // TMEM accumulator ring (4 x 128 columns = 512)
+constexpr uint32_t kThreads = 384;
+constexpr uint32_t kEpiWarps = 8;
+constexpr uint32_t kStageBytes = (BM + BN) * BK;  // 32 KB
+constexpr uint32_t kBarBytes = 8 * (2 * kStages + 2 * kAccBufs) + 16;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment
+constexpr uint32_t kUmmaK = 32;
+
+struct FusedParams {
+  uint32_t m, n;
+  uint32_t k_blocks;           // ceil(pitch / BK)
+  uint32_t num_split;
+  int32_t bits;                // L = bits per int8 slice
+  uint32_t single_a, single_b; // != 0: raw mode, only this (1-based) pair, int32 output
+  uint32_t super_m, super_n;   // cluster-tile grid
+  uint32_t group_m;            // rasterisation band height in cluster tiles
+  double alpha, beta;
+  double *c;
+  unsigned long long ldc;
+  const double *amax;
+  const double *bmax;
+  int32_t *c_i32;
+};
+
+// reference src/config.cu:85-92: for sum = 2..s+1, for j = 1..sum-1: (A_id=j, B_id=sum-j)
+struct PairIter {
+  uint32_t s, sum, a;
+  bool single, done;
+  __device__ PairIter(const FusedParams &p) {
+    s = p.num_split;
+    single = p.single_a != 0;
+    done = false;
+    if (single) {
+      sum = p.single_a + p.single_b;
+      a = p.single_a;
+    } else {
+      sum = 2;
+      a = 1;
+    }
+  }
+  __device__ bool valid() const { return !done; }
+  __device__ uint32_t a_id() const { return a; }
+  __device__ uint32_t b_id() const { return sum - a; }
+  __device__ void next() {
+    if (single) {
+      done = true;
+      return;
+    }
+    a++;
+    if (a >= sum || a > s) {
+      sum++;
+      a = (sum - 1 > s) ? sum - s : 1;  // keep B_id = sum - a <= s (never hit for sum <= s+1)
+    }
+    if (sum > s + 1) done = true;
+  }
+  // 2^(32 - rshift), rshift = L*(A_id+B_id-2) - 2*(7-L)   (reference src/gemm.cu:394-401, :96-99)
+  __device__ double scale(int32_t L) const {
+    const int32_t e = 32 - (L * static_cast<int32_t>(sum - 2) - 2 * (7 - L));
+    return __longlong_as_double(static_cast<long long>(static_cast<uint64_t>(1023 + e) << 52));
+  }
+};
+
+__device__ __forceinline__ void super_tile_coords(const FusedParams &p, uint32_t st, uint32_t &sm,
+                                                  uint32_t &sn) {
+  const uint32_t group_size = p.group_m * p.super_n;
+  const uint32_t g = st / group_size;
+  const uint32_t first = g * p.group_m;
+  const uint32_t rows = min(p.super_m - first, p.group_m);
+  const uint32_t r = st - g * group_size;
+  sm = first + r % rows;
+  sn = r / rows;
+}
+
+template <uint32_t CM, uint32_t CN>
+__global__ void __launch_bounds__(kThreads, 1)
+oz_gemm_fused_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                     const __grid_constant__ CUtensorMap tmap_b, const FusedParams p) {
+  constexpr uint32_t CSZ = CM * CN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * kStages + b); };
+  auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * kStages + kAccBufs + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kAccBufs);
+  volatile uint32_t *tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t crank = (CSZ > 1) ? ptx::cluster_ctarank() : 0u;
+  const uint32_t cm = crank % CM, cn = crank / CM;
+  const uint32_t cluster_id = blockIdx.x / CSZ;
+  const uint32_t num_clusters = gridDim.x / CSZ;
+  const uint32_t num_super = p.super_m * p.super_n;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < kStages; s++) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), CM + CN - 1);
+    }
+    for (uint32_t b = 0; b < kAccBufs; b++) {
+      ptx::mbar_init(tfull_bar(b), 1);
+      ptx::mbar_init(tempty_bar(b), kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  if (CSZ > 1) {
+    ptx::cluster_arrive();
+    ptx::cluster_wait();
+  } else {
+    __syncthreads();
+  }
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    ptx::reg_dealloc<56>();
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      uint16_t mask_a = 0, mask_b = 0;
+      for (uint32_t j = 0; j < CN; j++) mask_a |= static_cast<uint16_t>(1u << (cm + CM * j));
+      for (uint32_t i = 0; i < CM; i++) mask_b |= static_cast<uint16_t>(1u << (i + CM * cn));
+      uint32_t ks = 0;
+      for (uint32_t st = cluster_id; st < num_super; st += num_clusters) {
+        uint32_t sm, sn;
+        super_tile_coords(p, st, sm, sn);
+        const int row_a = static_cast<int>((sm * CM + cm) * BM + cn * (BM / CN));
+        const int row_b = static_cast<int>((sn * CN + cn) * BN + cm * (BN / CM));
+        for (PairIter it(p); it.valid(); it.next()) {
+          const int sa = static_cast<int>(it.a_id() - 1), sb = static_cast<int>(it.b_id() - 1);
+          for (uint32_t kb = 0; kb < p.k_blocks; kb++, ks++) {
+            const uint32_t stage = ks % kStages, ph = (ks / kStages) & 1u;
+            ptx::mbar_wait(empty_bar(stage), ph ^ 1u);
+            ptx::mbar_expect_tx(full_bar(stage), kStageBytes);
+            const uint32_t a_dst = smem_base + stage * kStageBytes + cn * (BM / CN) * BK;
+            const uint32_t b_dst = smem_base + stage * kStageBytes + BM * BK + cm * (BN / CM) * BK;
+            if (CN > 1) {
+              ptx::tma_load_3d_mc(a_dst, &tmap_a, full_bar(stage), static_cast<int>(kb * BK), row_a, sa, mask_a);
+            } else {
+              ptx::tma_load_3d(a_dst, &tmap_a, full_bar(stage), static_cast<int>(kb * BK), row_a, sa);
+            }
+            if (CM > 1) {
+              ptx::tma_load_3d_mc(b_dst, &tmap_b, full_bar(stage), static_cast<int>(kb * BK), row_b, sb, mask_b);
+            } else {
+              ptx::tma_load_3d(b_dst, &tmap_b, full_bar(stage), static_cast<int>(kb * BK), row_b, sb);
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = ptx::make_i8_idesc(BM, BN);
+      uint16_t mask_e = 0;
+      for (uint32_t j = 0; j < CN; j++) mask_e |= static_cast<uint16_t>(1u << (cm + CM * j));
+      for (uint32_t i = 0; i < CM; i++) mask_e |= static_cast<uint16_t>(1u << (i + CM * cn));
+      uint32_t ks = 0, pc = 0;
+      for (uint32_t st = cluster_id; st < num_super; st += num_clusters) {
+        for (PairIter it(p); it.valid(); it.next(), pc++) {
+          const uint32_t buf = pc % kAccBufs, bph = (pc / kAccBufs) & 1u;
+          ptx::mbar_wait(tempty_bar(buf), bph ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          for (uint32_t kb = 0; kb < p.k_blocks; kb++, ks++) {
+            const uint32_t stage = ks % kStages, ph = (ks / kStages) & 1u;
+            ptx::mbar_wait(full_bar(stage), ph);
+            ptx::tc_fence_after();
+            const uint32_t a_smem = smem_base + stage * kStageBytes;
+            const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_smem);
+            const uint64_t b_desc = ptx::make_sw128_kmajor_desc(a_smem + BM * BK);
+#pragma unroll
+            for (uint32_t kk = 0; kk < BK / kUmmaK; kk++) {
+              // advance kUmmaK bytes along K inside the 128-byte swizzle atom: +32 B => +2 (16-B units)
+              ptx::mma_i8_ss(d_tmem, a_desc + kk * (kUmmaK >> 4), b_desc + kk * (kUmmaK >> 4), idesc,
+                             (kb | kk) != 0 ? 1u : 0u);
+            }
+            if (CSZ > 1) {
+              ptx::tc_commit_mc(empty_bar(stage), mask_e);
+            } else {
+              ptx::tc_commit(empty_bar(stage));
+            }
+          }
+          ptx::tc_commit(tfull_bar(buf));
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps, FP64 accumulators in registers =====================
+    ptx::reg_alloc<224>();
+    const uint32_t q = warp & 3u;            // TMEM lane quarter this warp may touch
+    const uint32_t half = (warp - 4u) >> 2;  // which 64-column half of the tile
+    const bool raw = p.single_a != 0;
+    uint32_t pc = 0;
+    for (uint32_t st = cluster_id; st < num_super; st += num_clusters) {
+      uint32_t sm, sn;
+      super_tile_coords(p, st, sm, sn);
+      const uint32_t row = (sm * CM + cm) * BM + q * 32u + lane;
+      const uint32_t col0 = (sn * CN + cn) * BN + half * 64u;
+      double acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; j++) acc[j] = 0.0;
+      for (PairIter it(p); it.valid(); it.next(), pc++) {
+        const uint32_t buf = pc % kAccBufs, bph = (pc / kAccBufs) & 1u;
+        ptx::mbar_wait(tfull_bar(buf), bph);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * BN + half * 64u;
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; c++) ptx::tmem_ld_x16(taddr + c * 16, v[c]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+        if (!raw) {
+          const double scale = it.scale(p.bits);
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              acc[c * 16 + j] = __fma_rn(__int2double_rn(static_cast<int32_t>(v[c][j])), scale, acc[c * 16 + j]);
+        } else if (row < p.m) {
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const uint32_t col = col0 + c * 16 + j;
+              if (col < p.n) p.c_i32[static_cast<size_t>(col) * p.m + row] = static_cast<int32_t>(v[c][j]);
+            }
+        }
+      }
+      if (!raw && row < p.m) {
+        // reference src/gemm.cu:124-148: x = acc / 2^44 * amax[mi] * bmax[ni]
+        const double am = p.amax[row];
+        double *crow = p.c + row;
+#pragma unroll
+        for (int j = 0; j < 64; j++) {
+          const uint32_t col = col0 + j;
+          if (col < p.n) {
+            double x = __dmul_rn(acc[j], 0x1p-44);
+            x = __dmul_rn(x, am);
+            x = __dmul_rn(x, __ldg(p.bmax + col));
+            double *dst = crow + static_cast<size_t>(col) * p.ldc;
+            if (p.beta != 0) {
+              *dst = __fma_rn(p.alpha, x, __dmul_rn(p.beta, *dst));
+            } else {
+              *dst = __dmul_rn(p.alpha, x);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  if (CSZ > 1) {
+    ptx::cluster_arrive();
+    ptx::cluster_wait();
+  } else {
+    __syncthreads();
+  }
+  if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// k == 0: every product is empty, C = beta * C (beta == 0: C is not read, reference src/gemm.cu:143-147)
+__global__ void __launch_bounds__(256)
+oz_scale_c_kernel(double *__restrict__ c, const size_t ldc, const uint32_t m, const uint32_t n, const double beta) {
+  const uint32_t r = blockIdx.x * 256 + threadIdx.x, col = blockIdx.y;
+  if (r >= m || col >= n) return;
+  double *p = c + static_cast<size_t>(col) * ldc + r;
+  *p = (beta != 0) ? __dmul_rn(beta, *p) : 0.0;
+}
+
+// ---- host side --------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// slices: [num_split][rows][pitch] int8 -> 3-D map (k, row, slice), box (128, box_rows, 1), SW128
+int make_slice_tmap(CUtensorMap *map, const int8_t *base, size_t rows, size_t pitch,
+                    unsigned num_split, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return static_cast<int>(cudaErrorNotSupported);
+  cuuint64_t dims[3] = {pitch, rows, num_split};
+  cuuint64_t strides[2] = {pitch, static_cast<cuuint64_t>(rows) * pitch};
+  cuuint32_t box[3] = {BK, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(cudaErrorInvalidValue);
+}
+
+int g_cluster_override = 0;  // 0 = heuristic; else CM*10+CN (test hook, see ozk_set_cluster_shape)
+
+template <uint32_t CM, uint32_t CN>
+int launch_fused(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_slices, size_t pitch,
+                 cudaStream_t stream) {
+  FusedParams p = p0;
+  CUtensorMap ta, tb;
+  int rc = make_slice_tmap(&ta, a_slices, p.m, pitch, p.num_split, BM / CN);
+  if (rc) return rc;
+  rc = make_slice_tmap(&tb, b_slices, p.n, pitch, p.num_split, BN / CM);
+  if (rc) return rc;
+  const uint32_t tiles_m = ceil_div_u32(p.m, BM), tiles_n = ceil_div_u32(p.n, BN);
+  p.super_m = ceil_div_u32(tiles_m, CM);
+  p.super_n = ceil_div_u32(tiles_n, CN);
+  p.group_m = (12 / CM) > 0 ? 12 / CM : 1;
+
+  auto kern = oz_gemm_fused_kernel<CM, CN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    OZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_done = true;
+  }
+  int dev = 0, sms = 0;
+  OZ_CUDA_TRY(cudaGetDevice(&dev));
+  OZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  uint32_t max_clusters = static_cast<uint32_t>(sms) / (CM * CN);
+  if (CM * CN > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CM * CN;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int cached_max = -1;
+    if (cached_max < 0) {
+      cfg.gridDim = dim3(static_cast<unsigned>(sms) / (CM * CN) * (CM * CN));
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) cached_max = nc;
+      else cached_max = static_cast<int>(max_clusters);
+    }
+    max_clusters = static_cast<uint32_t>(cached_max);
+  }
+  const uint32_t num_super = p.super_m * p.super_n;
+  const uint32_t clusters = num_super < max_clusters ? num_super : max_clusters;
+  if (clusters == 0) return 0;
+  cfg.gridDim = dim3(clusters * CM * CN);
+  OZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  count_launch(1);
+  return 0;
+}
+
+int dispatch_fused(const FusedParams &p, const int8_t *a_slices, const int8_t *b_slices, size_t pitch,
+                   cudaStream_t stream) {
+  int shape = g_cluster_override;
+  if (shape == 0) shape = 11;
+  switch (shape) {
+    case 11: return launch_fused<1, 1>(p, a_slices, b_slices, pitch, stream);
+    case 21: return launch_fused<2, 1>(p, a_slices, b_slices, pitch, stream);
+    case 12: return launch_fused<1, 2>(p, a_slices, b_slices, pitch, stream);
+    case 22: return launch_fused<2, 2>(p, a_slices, b_slices, pitch, stream);
+    default: return static_cast<int>(cudaErrorInvalidValue);
+  }
+}
+
+bool valid_common(size_t m, size_t n, size_t k, size_t pitch, unsigned num_split, unsigned bits) {
+  return m > 0 && n > 0 && k > 0 && m < (1ull << 31) && n < (1ull << 31) && pitch % 16 == 0 &&
+         pitch >= k && pitch < (1ull << 31) && num_split >= 1 && num_split <= 18 && bits >= 1 && bits <= 7;
+}
+
+}  // namespace
+}  // namespace oz
+
+// Test/tuning hook: force the cluster shape of the fused kernel (0 = default heuristic).
+extern "C" int ozk_set_cluster_shape(int cm, int cn) {
+  oz::g_cluster_override = (cm <= 0 || cn <= 0) ? 0 : cm * 10 + cn;
+  return 0;
+}
+
+extern "C" int ozk_gemm_i8_fused(size_t m, size_t n, size_t k, const int8_t *a_slices,
+                                 const int8_t *b_slices, size_t pitch, const double *amax,
+                                 const double *bmax, unsigned num_split, unsigned bits_per_int8,
+                                 double alpha, double beta, double *c, size_t ldc, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m)
+    return static_cast<int>(cudaErrorInvalidValue);
+  oz::FusedParams p{};
+  p.m = static_cast<uint32_t>(m);
+  p.n = static_cast<uint32_t>(n);
+  p.k_blocks = oz::ceil_div_u32(static_cast<uint32_t>(pitch), oz::BK);
+  p.num_split = num_split;
+  p.bits = static_cast<int32_t>(bits_per_int8);
+  p.alpha = alpha;
+  p.beta = beta;
+  p.c = c;
+  p.ldc = ldc;
+  p.amax = amax;
+  p.bmax = bmax;
+  return oz::dispatch_fused(p, a_slices, b_slices, pitch, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ozk_scale_c(size_t m, size_t n, double beta, double *c, size_t ldc, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  if (ldc < m || m >= (1ull << 31) || n >= 65536ull * 32768ull) return static_cast<int>(cudaErrorInvalidValue);
+  for (size_t j0 = 0; j0 < n; j0 += 65535) {
+    const unsigned nj = static_cast<unsigned>(n - j0 < 65535 ? n - j0 : 65535);
+    dim3 grid(static_cast<unsigned>((m + 255) / 256), nj);
+    oz::oz_scale_c_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(c + j0 * ldc, ldc, static_cast<uint32_t>(m),
+                                                                              nj, beta);
+    oz::count_launch(1);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ozk_gemm_i8_pair(size_t m, size_t n, size_t k, const int8_t *a_slices,
+                                const int8_t *b_slices, size_t pitch, unsigned num_split,
+                                unsigned a_id, unsigned b_id, int32_t *c_i32, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  if (!oz::valid_common(m, n, k, pitch, num_split, 7) || a_id < 1 || b_id < 1 || a_id > num_split ||
+      b_id > num_split)
+    return static_cast<int>(cudaErrorInvalidValue);
+  oz::FusedParams p{};
+  p.m = static_cast<uint32_t>(m);
+  p.n = static_cast<uint32_t>(n);
+  p.k_blocks = oz::ceil_div_u32(static_cast<uint32_t>(pitch), oz::BK);
+  p.num_split = num_split;
+  p.bits = 7;
+  p.single_a = a_id;
+  p.single_b = b_id;
+  p.c_i32 = c_i32;
+  return oz::dispatch_fused(p, a_slices, b_slices, pitch, static_cast<cudaStream_t>(stream));
+}

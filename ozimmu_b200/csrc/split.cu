@@ -1,0 +1,350 @@
+// split.cu -- per-row max-exponent scan, FP64 -> s x int8 mantissa split, mantissa-loss totals.
+//
+// Replaces reference src/split.cu:14-67 (get_exp_max_element), :155-185 (cut_int8_core),
+// :193-283 (split_int8_kernel + host wrappers) and :302-380 (mantissa-loss kernels).
+// Arithmetic follows SURVEY App. A.2/A.3/A.6 bit for bit; the data movement is new:
+//
+//  * "rows contiguous" inputs (op_t A, op_n B): one CTA per row, the row is read from HBM
+//    once into shared memory (bank-swizzled), the max exponent is a warp-shuffle reduction,
+//    and every thread then emits 16 consecutive K elements as one 16-byte store per slice.
+//  * "rows strided" inputs (op_n A, op_t B; column-major source): threads are mapped to
+//    rows so that global loads stay coalesced along the contiguous dimension; the row max
+//    is an atomicMax over the integer exponent field, and the split kernel has every thread
+//    gather 16 K-consecutive elements of its row (each a coalesced column segment across the
+//    warp) so it can also emit one 16-byte store per slice -- no shared-memory transpose.
+//  * no device synchronisation (the reference calls cudaDeviceSynchronize per split,
+//    src/split.cu:261).
+//
+// Output layout: out[slice][row][pitch] int8, K contiguous, pitch = k rounded up to 16,
+// padding bytes zero -- the K-major layout the tcgen05 kernel's TMA descriptors expect.
+#include "oz_common.cuh"
+#include "ozimmu_b200.h"
+
+namespace oz {
+namespace {
+
+constexpr int kSplitThreads = 256;
+constexpr int kMaxCachedLen = 24 * 1024;  // doubles per row kept in SMEM (192 KB)
+
+__device__ __forceinline__ uint32_t exp_field(double x) {
+  return static_cast<uint32_t>((static_cast<uint64_t>(__double_as_longlong(x)) >> 52) & 0x7FFu);
+}
+
+// reference src/split.cu:191,202-204: max_exp = 2 * asdouble(max exponent field)
+__device__ __forceinline__ double max_exp_from_field(uint32_t e) {
+  return __dmul_rn(__longlong_as_double(static_cast<long long>(static_cast<uint64_t>(e) << 52)), 2.0);
+}
+
+// reference src/split.cu:155-185 for 16 K-consecutive elements of one row.
+// w[t][q] receives bytes 4q..4q+3 of slice t.
+template <int S>
+__device__ __forceinline__ void cut16(const double (&v)[16], const uint64_t max_exp_bits,
+                                      const unsigned L, uint32_t (&w)[S][4]) {
+#pragma unroll
+  for (int t = 0; t < S; t++) {
+    w[t][0] = w[t][1] = w[t][2] = w[t][3] = 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const double a = v[j];
+    const uint64_t bits = static_cast<uint64_t>(__double_as_longlong(a));
+    const uint64_t ea = bits & kExpMask;
+    const bool positive = a > 0;
+    // 53-bit significand, MSB at bit 127 of a 128-bit word (hi:lo); no implicit bit for subnormals
+    uint64_t hi = ((bits & kMantMask) | (ea ? (1ull << 52) : 0ull)) << 11;
+    uint64_t lo = 0;
+    const uint64_t off = (max_exp_bits - ea) >> 52;
+    if (off >= 128) {
+      hi = 0;
+    } else if (off >= 64) {
+      lo = hi >> (off - 64);
+      hi = 0;
+    } else if (off > 0) {
+      lo = hi << (64 - off);
+      hi >>= off;
+    }
+#pragma unroll
+    for (int t = 0; t < S; t++) {
+      const int32_t top = static_cast<int32_t>(hi >> (64 - L));
+      const int32_t sv = positive ? top : -top;
+      w[t][j >> 2] |= (static_cast<uint32_t>(sv) & 0xFFu) << (8 * (j & 3));
+      hi = (hi << L) | (lo >> (64 - L));
+      lo <<= L;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t block_max_u32(uint32_t v, uint32_t *s_red) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = (threadIdx.x < kSplitThreads / 32) ? s_red[threadIdx.x] : 0u;
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) s_red[0] = v;
+  }
+  __syncthreads();
+  return s_red[0];
+}
+
+// SMEM position of row element i: 16-element groups, in-group index XOR-swizzled by the
+// group id so that "thread t reads element j of group t" is bank-conflict free.
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return (i & ~15u) | ((i ^ (i >> 4)) & 15u); }
+
+// ---------------------------------------------------------------------------------------------
+// Rows contiguous in memory: one CTA per row.
+// ---------------------------------------------------------------------------------------------
+template <int S, bool CACHED>
+__global__ void __launch_bounds__(kSplitThreads)
+split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
+                  const size_t rows, const uint32_t len, const double *__restrict__ in,
+                  const size_t ld, const unsigned L) {
+  extern __shared__ double s_row[];
+  __shared__ uint32_t s_red[kSplitThreads / 32];
+  const size_t row = blockIdx.x;
+  const double *__restrict__ src = in + row * ld;
+
+  uint32_t e = 0;
+  for (uint32_t i = threadIdx.x; i < len; i += kSplitThreads) {
+    const double x = __ldg(src + i);
+    if (CACHED) s_row[swz(i)] = x;
+    e = max(e, exp_field(x));
+  }
+  e = block_max_u32(e, s_red);  // also orders the s_row writes before the reads below
+  const double mx = max_exp_from_field(e);
+  const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
+  if (threadIdx.x == 0) max_exp[row] = mx;
+
+  const size_t slice_stride = rows * pitch;
+  int8_t *__restrict__ dst = out + row * pitch;
+  const uint32_t ngroups = static_cast<uint32_t>(pitch / 16);
+  for (uint32_t g = threadIdx.x; g < ngroups; g += kSplitThreads) {
+    double v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const uint32_t i = g * 16 + j;
+      if (CACHED) {
+        v[j] = (i < len) ? s_row[(g * 16) | ((j ^ g) & 15u)] : 0.0;
+      } else {
+        v[j] = (i < len) ? __ldg(src + i) : 0.0;
+      }
+    }
+    uint32_t w[S][4];
+    cut16<S>(v, mx_bits, L, w);
+#pragma unroll
+    for (int t = 0; t < S; t++) {
+      uint4 q = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+      // elements >= len are exact zeros => their slice bytes are already 0
+      *reinterpret_cast<uint4 *>(dst + t * slice_stride + g * 16) = q;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rows strided (column-major source): thread <-> row so loads coalesce along rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int kColChunk = 64;  // columns per CTA in the row-max pass
+
+__global__ void __launch_bounds__(256)
+rowmax_cols_kernel(uint32_t *__restrict__ emax, const size_t rows, const uint32_t len,
+                   const double *__restrict__ in, const size_t ld) {
+  const size_t r = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (r >= rows) return;
+  const uint32_t c0 = blockIdx.y * kColChunk;
+  const uint32_t c1 = min(len, c0 + kColChunk);
+  uint32_t e = 0;
+#pragma unroll 8
+  for (uint32_t c = c0; c < c1; c++) e = max(e, exp_field(__ldg(in + static_cast<size_t>(c) * ld + r)));
+  atomicMax(emax + r, e);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256)
+split_cols_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
+                  const uint32_t *__restrict__ emax, const size_t rows, const uint32_t len,
+                  const double *__restrict__ in, const size_t ld, const unsigned L) {
+  const size_t r = static_cast<size_t>(blockIdx.x) * 64 + (threadIdx.x & 63);
+  const uint32_t cbase = blockIdx.y * 64 + (threadIdx.x >> 6) * 16;
+  if (r >= rows || cbase >= pitch) return;
+  const double mx = max_exp_from_field(emax[r]);
+  const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
+  if (blockIdx.y == 0 && threadIdx.x < 64) max_exp[r] = mx;
+
+  double v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const uint32_t c = cbase + j;
+    v[j] = (c < len) ? __ldg(in + static_cast<size_t>(c) * ld + r) : 0.0;
+  }
+  uint32_t w[S][4];
+  cut16<S>(v, mx_bits, L, w);
+  const size_t slice_stride = rows * pitch;
+  int8_t *__restrict__ dst = out + r * pitch + cbase;
+#pragma unroll
+  for (int t = 0; t < S; t++) {
+    *reinterpret_cast<uint4 *>(dst + t * slice_stride) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mantissa-loss totals (auto mode).  reference src/split.cu:317-380, intended semantics
+// (SURVEY App. A.6): zeros contribute nothing, 16 counters for num_split = 3..18.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void loss_accumulate(uint32_t (&cnt)[16], const double x,
+                                                const uint64_t mx_exp_bits, const bool mx_zero,
+                                                const unsigned L) {
+  if (x == 0 || mx_zero) return;
+  const uint32_t req = static_cast<uint32_t>(
+      ((mx_exp_bits - (static_cast<uint64_t>(__double_as_longlong(x)) & kExpMask)) >> 52) + 53);
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    const uint32_t space = (s + 3) * L;
+    cnt[s] += (space < req) ? (req - space) : 0u;
+  }
+}
+
+__device__ __forceinline__ void loss_block_reduce(uint32_t (&cnt)[16], unsigned long long *out) {
+  __shared__ unsigned long long s_cnt[16];
+  if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0ull;
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    uint32_t v = cnt[s];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[s], static_cast<unsigned long long>(v));
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 && s_cnt[threadIdx.x]) atomicAdd(out + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(kSplitThreads)
+loss_rows_kernel(unsigned long long *__restrict__ counters, const uint32_t len,
+                 const double *__restrict__ in, const size_t ld, const unsigned L) {
+  __shared__ uint32_t s_red[kSplitThreads / 32];
+  const double *__restrict__ src = in + static_cast<size_t>(blockIdx.x) * ld;
+  uint32_t e = 0;
+  for (uint32_t i = threadIdx.x; i < len; i += kSplitThreads) e = max(e, exp_field(__ldg(src + i)));
+  e = block_max_u32(e, s_red);
+  const double mx = max_exp_from_field(e);
+  const uint64_t mx_exp_bits = static_cast<uint64_t>(__double_as_longlong(mx)) & kExpMask;
+  uint32_t cnt[16];
+#pragma unroll
+  for (int s = 0; s < 16; s++) cnt[s] = 0;
+  for (uint32_t i = threadIdx.x; i < len; i += kSplitThreads)
+    loss_accumulate(cnt, __ldg(src + i), mx_exp_bits, mx == 0, L);
+  loss_block_reduce(cnt, counters);
+}
+
+__global__ void __launch_bounds__(256)
+loss_cols_kernel(unsigned long long *__restrict__ counters, const uint32_t *__restrict__ emax,
+                 const size_t rows, const uint32_t len, const double *__restrict__ in,
+                 const size_t ld, const unsigned L) {
+  const size_t r = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  uint32_t cnt[16];
+#pragma unroll
+  for (int s = 0; s < 16; s++) cnt[s] = 0;
+  if (r < rows) {
+    const double mx = max_exp_from_field(emax[r]);
+    const uint64_t mx_exp_bits = static_cast<uint64_t>(__double_as_longlong(mx)) & kExpMask;
+    const uint32_t c0 = blockIdx.y * kColChunk;
+    const uint32_t c1 = min(len, c0 + kColChunk);
+#pragma unroll 4
+    for (uint32_t c = c0; c < c1; c++)
+      loss_accumulate(cnt, __ldg(in + static_cast<size_t>(c) * ld + r), mx_exp_bits, mx == 0, L);
+  }
+  loss_block_reduce(cnt, counters);
+}
+
+template <int S>
+int launch_split(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, size_t rows,
+                 size_t len, const double *in, size_t ld, int col_major, unsigned L,
+                 cudaStream_t stream) {
+  if (col_major) {
+    OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), stream));
+    dim3 g1(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk));
+    rowmax_cols_kernel<<<g1, 256, 0, stream>>>(scratch, rows, static_cast<uint32_t>(len), in, ld);
+    dim3 g2(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((pitch + 63) / 64));
+    split_cols_kernel<S><<<g2, 256, 0, stream>>>(out, pitch, max_exp, scratch, rows,
+                                                 static_cast<uint32_t>(len), in, ld, L);
+    count_launch(2);
+  } else {
+    if (len <= static_cast<size_t>(kMaxCachedLen)) {
+      const size_t smem = ((len + 15) / 16 * 16) * sizeof(double);
+      if (smem > 48 * 1024) {
+        OZ_CUDA_TRY(cudaFuncSetAttribute(split_rows_kernel<S, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      }
+      split_rows_kernel<S, true><<<static_cast<unsigned>(rows), kSplitThreads, smem, stream>>>(
+          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L);
+    } else {
+      split_rows_kernel<S, false><<<static_cast<unsigned>(rows), kSplitThreads, 0, stream>>>(
+          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L);
+    }
+    count_launch(1);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+}  // namespace oz
+
+extern "C" uint32_t ozk_bits_per_int8(uint32_t k) {
+  if (k == 0) return 0;
+  uint32_t lg = 0;
+  while (lg < 31 && (1u << (lg + 1)) <= k) lg++;
+  if ((1u << lg) != k) lg++;
+  const uint32_t v = (31 - lg) / 2;
+  return v < 7 ? v : 7;
+}
+
+extern "C" size_t ozk_slice_pitch(size_t k) { return oz::slice_pitch(k); }
+
+extern "C" int ozk_split_int8(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch,
+                              size_t rows, size_t len, const double *in, size_t ld, int col_major,
+                              unsigned num_split, unsigned bits_per_int8, void *stream) {
+  if (rows == 0 || len == 0) return 0;
+  if (pitch % 16 != 0 || pitch < len || bits_per_int8 == 0 || bits_per_int8 > 7 ||
+      len > 0xFFFFFFF0ull || rows > 0x7FFFFFFFull || (col_major && scratch == nullptr))
+    return static_cast<int>(cudaErrorInvalidValue);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define OZ_SPLIT_CASE(S)                                                                       \
+  case S:                                                                                      \
+    return oz::launch_split<S>(out, pitch, max_exp, scratch, rows, len, in, ld, col_major,     \
+                               bits_per_int8, s);
+  switch (num_split) {
+    OZ_SPLIT_CASE(3) OZ_SPLIT_CASE(4) OZ_SPLIT_CASE(5) OZ_SPLIT_CASE(6) OZ_SPLIT_CASE(7)
+    OZ_SPLIT_CASE(8) OZ_SPLIT_CASE(9) OZ_SPLIT_CASE(10) OZ_SPLIT_CASE(11) OZ_SPLIT_CASE(12)
+    OZ_SPLIT_CASE(13) OZ_SPLIT_CASE(14) OZ_SPLIT_CASE(15) OZ_SPLIT_CASE(16) OZ_SPLIT_CASE(17)
+    OZ_SPLIT_CASE(18)
+    default:
+      return static_cast<int>(cudaErrorInvalidValue);
+  }
+#undef OZ_SPLIT_CASE
+}
+
+extern "C" int ozk_mantissa_loss(unsigned long long *counters16, uint32_t *scratch, size_t rows,
+                                 size_t len, const double *in, size_t ld, int col_major,
+                                 unsigned bits_per_int8, void *stream) {
+  if (rows == 0 || len == 0) return 0;
+  if (len > 0xFFFFFFF0ull || rows > 0x7FFFFFFFull || (col_major && scratch == nullptr))
+    return static_cast<int>(cudaErrorInvalidValue);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  using namespace oz;
+  if (col_major) {
+    OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), s));
+    dim3 g(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk));
+    rowmax_cols_kernel<<<g, 256, 0, s>>>(scratch, rows, static_cast<uint32_t>(len), in, ld);
+    loss_cols_kernel<<<g, 256, 0, s>>>(counters16, scratch, rows, static_cast<uint32_t>(len), in, ld,
+                                       bits_per_int8);
+    count_launch(2);
+  } else {
+    loss_rows_kernel<<<static_cast<unsigned>(rows), kSplitThreads, 0, s>>>(
+        counters16, static_cast<uint32_t>(len), in, ld, bits_per_int8);
+    count_launch(1);
+  }
+  return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,115 @@
+"""-m gpu: auto mode (mantissa-loss totals + selection) against oracle and reference, the dgemm
+passthrough, and the LD_PRELOAD drop-in (cublasDgemm interception under an unmodified torch)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib
+import ozimmu_b200 as oz
+from gpu_util import Reference, bits, to_dev
+
+pytestmark = pytest.mark.gpu
+ROOT = oracle_lib.ROOT
+
+
+@pytest.mark.parametrize("op_a,op_b", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("phi", [0.0, 1.0, 4.0])
+def test_auto_counters_and_selection_vs_oracle(handle, op_a, op_b, phi):
+    m, n, k = 96, 80, 160
+    a = oracle_lib.gen_matrix(f"exp_rand-{phi}", m * k, 1)
+    b = oracle_lib.gen_matrix(f"exp_rand-{phi}", k * n, 2)
+    lda = m if op_a == 0 else k
+    ldb = k if op_b == 0 else n
+    da, db = to_dev(a), to_dev(b)
+    for thr in (0.0, 0.5, 1.5, 8.0):
+        want_s, want_cnt = oracle_lib.oracle_auto_select(op_a, op_b, m, n, k, a, lda, b, ldb, thr)
+        cnt = []
+        mode = oz.auto_mode_select(handle, op_a, op_b, m, n, k, da, lda, db, ldb, oz.real, thr, cnt)
+        assert cnt == [int(v) for v in want_cnt]
+        assert mode == (oz.fp64_int8(want_s) if want_s else oz.compute_mode_t.dgemm)
+
+
+def test_auto_vs_reference_counters(handle):
+    """Reference counters are only defined for fp64_int8_3..10 (8 counters) and for
+    inputs without exact zeros with k % 32 == 0 (App. B.2)."""
+    if oracle_lib.reference() is None:
+        pytest.skip("oracle/_ref/libozref.so not built")
+    ref = Reference()
+    try:
+        m = n = k = 1024
+        for phi in (0.0, 1.0, 2.0):
+            a = to_dev(oracle_lib.gen_matrix(f"exp_rand-{phi}", m * k, 3))
+            b = to_dev(oracle_lib.gen_matrix(f"exp_rand-{phi}", k * n, 4))
+            for thr in (0.0, 1.0, 4.0):
+                ref_mode, ref_cnt = ref.auto_mode_select(0, 0, m, n, k, a, m, b, k, thr)
+                cnt = []
+                mode = oz.auto_mode_select(handle, 0, 0, m, n, k, a, m, b, k, oz.real, thr, cnt)
+                assert cnt[:8] == ref_cnt
+                if oz.compute_mode_t.fp64_int8_3 <= ref_mode <= oz.compute_mode_t.fp64_int8_10:
+                    assert int(mode) == ref_mode
+    finally:
+        ref.close()
+
+
+def test_auto_mode_gemm_runs_selected_mode(handle):
+    m, n, k = 300, 200, 500
+    a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 5))
+    b = to_dev(oracle_lib.gen_matrix("exp_rand-1", k * n, 6))
+    oz.set_auto_mantissa_loss_threashold(handle, 1.0)
+    assert oz.get_auto_mantissa_loss_threashold(handle) == 1.0
+    mode = oz.auto_mode_select(handle, 0, 0, m, n, k, a, m, b, k, oz.real, 1.0)
+    c_auto = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+    c_fix = torch.zeros_like(c_auto)
+    assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c_auto, m, oz.compute_mode_t.fp64_int8_auto) == 0
+    assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c_fix, m, mode) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(c_auto.view(torch.int64), c_fix.view(torch.int64))
+
+
+def test_dgemm_passthrough(handle):
+    m, n, k = 200, 150, 100
+    a = torch.randn(k, m, dtype=torch.float64, device="cuda")  # column-major m x k
+    b = torch.randn(n, k, dtype=torch.float64, device="cuda")  # column-major k x n
+    c = torch.zeros(n, m, dtype=torch.float64, device="cuda")
+    assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c, m, oz.compute_mode_t.dgemm) == 0
+    torch.cuda.synchronize()
+    assert torch.allclose(c, b @ a, rtol=1e-12, atol=1e-12)
+
+
+DROPIN = r"""
+import os, torch
+torch.manual_seed(0)
+n = 1536
+a = torch.rand(n, n, dtype=torch.float64, device="cuda")
+b = torch.rand(n, n, dtype=torch.float64, device="cuda")
+c = a @ b
+torch.cuda.synchronize()
+torch.save({"a": a.cpu(), "b": b.cpu(), "c": c.cpu()}, os.environ["OZ_DROPIN_OUT"])
+"""
+
+
+def test_ld_preload_dropin(tmp_path, handle):
+    """An unmodified PyTorch program under LD_PRELOAD=libozimmu.so OZIMMU_COMPUTE_MODE=fp64_int8_9:
+    its float64 matmul (cublasDgemm / cublasGemmEx) must be served by the Ozaki path, i.e. be
+    bit-identical to a direct ozimmu_gemm call on the same operands, and must log the interception."""
+    out = tmp_path / "dropin.pt"
+    env = dict(os.environ, LD_PRELOAD=str(oz.LIB_PATH), OZIMMU_COMPUTE_MODE="fp64_int8_9", OZIMMU_INFO="1",
+               OZIMMU_ENABLE_CULIP_PROFILING="1", OZ_DROPIN_OUT=str(out))
+    p = subprocess.run([sys.executable, "-c", DROPIN], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "[CULiP Result][Dfp64_int8_9-" in p.stdout, p.stdout[-2000:]
+    d = torch.load(out)
+    n = d["a"].shape[0]
+    # torch row-major C = A @ B  <=>  column-major C^T = B^T A^T: cuBLAS is called with (B, A)
+    a, b = d["a"].cuda(), d["b"].cuda()
+    c = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    assert oz.gemm(handle, 0, 0, n, n, n, 1.0, b, n, a, n, 0.0, c, n, oz.fp64_int8(9)) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(c), bits(d["c"]))
+    # and it is an accurate DGEMM
+    ref = d["a"] @ d["b"]
+    assert (torch.linalg.norm(d["c"] - ref) / torch.linalg.norm(ref)).item() < 1e-15

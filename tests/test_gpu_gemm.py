@@ -1,0 +1,218 @@
+"""-m gpu: whole-path parity of ozimmu_gemm (C-ABI) against (1) the CPU oracle at small sizes,
+(2) the unmodified reference (oracle/_ref/libozref.so) on the reference's own ci_test grid
+(reference test/main_test.cu:703-744) and at the BASELINE sizes, bit-for-bit on the FP64 output."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib
+import ozimmu_b200 as oz
+from gpu_util import Reference, bits, to_dev, ulp_distance
+
+pytestmark = pytest.mark.gpu
+
+
+def stored_shape(op, rows, cols, ld_extra):
+    """column-major storage of op(X) (rows x cols): -> (ld, number of stored columns)"""
+    r, c = (rows, cols) if op == 0 else (cols, rows)
+    return r + ld_extra, c
+
+
+def make_case(op_a, op_b, m, n, k, kind, seed, ld_extra=0):
+    lda, ca = stored_shape(op_a, m, k, ld_extra)
+    ldb, cb = stored_shape(op_b, k, n, ld_extra)
+    ldc = m + ld_extra
+    a = oracle_lib.gen_matrix(kind, lda * ca, seed)
+    b = oracle_lib.gen_matrix(kind, ldb * cb, seed + 1)
+    c = oracle_lib.gen_matrix("normal01", ldc * n, seed + 2)
+    return a, lda, b, ldb, c, ldc
+
+
+@pytest.mark.parametrize("op_a,op_b", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k,num_split,kind,alpha,beta,ld_extra", [
+    (64, 48, 100, 9, "urand01", 1.0, 0.0, 0),
+    (130, 70, 257, 13, "exp_rand-2", -1.5, 0.75, 3),
+    (33, 200, 16, 3, "normal01", 2.0, 0.0, 1),
+    (129, 131, 300, 18, "mixed", 1.0, -1.0, 0),
+    (1, 1, 1, 9, "urand01", 1.0, 0.0, 0),
+])
+def test_gemm_matches_oracle(handle, op_a, op_b, m, n, k, num_split, kind, alpha, beta, ld_extra):
+    a, lda, b, ldb, c, ldc = make_case(op_a, op_b, m, n, k, kind, seed=m + n + k, ld_extra=ld_extra)
+    want = oracle_lib.oracle_gemm(op_a, op_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, num_split)
+    da, db, dc = to_dev(a), to_dev(b), to_dev(c)
+    rc = oz.gemm(handle, op_a, op_b, m, n, k, alpha, da, lda, db, ldb, beta, dc, ldc, oz.fp64_int8(num_split))
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = dc.cpu().numpy()
+    assert np.array_equal(bits(got), bits(want)), f"max ulp distance {ulp_distance(got, want)}"
+
+
+def test_gemm_k_zero_and_empty(handle):
+    m, n = 40, 24
+    c = oracle_lib.gen_matrix("normal01", m * n, 5)
+    dc = to_dev(c)
+    da = torch.zeros(1, dtype=torch.float64, device="cuda")
+    assert oz.gemm(handle, 0, 0, m, n, 0, 1.0, da, m, da, 1, 2.0, dc, m, oz.fp64_int8(9)) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(dc.cpu().numpy(), 2.0 * c)
+    assert oz.gemm(handle, 0, 0, 0, n, 8, 1.0, da, 1, da, 8, 0.0, dc, 1, oz.fp64_int8(9)) == 0
+
+
+def test_gemm_invalid_arguments(handle):
+    x = torch.zeros(64 * 64, dtype=torch.float64, device="cuda")
+    # lda < m  -> 1 (reference src/gemm.cu:535-556)
+    assert oz.gemm(handle, 0, 0, 64, 64, 64, 1.0, x, 32, x, 64, 0.0, x, 64, oz.fp64_int8(9)) == 1
+    # misaligned pointer -> 1
+    assert oz.gemm(handle, 0, 0, 8, 8, 8, 1.0, x.data_ptr() + 4, 8, x, 8, 0.0, x, 8, oz.fp64_int8(9)) == 1
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if oracle_lib.reference() is None:
+        pytest.skip("oracle/_ref/libozref.so not built")
+    r = Reference()
+    yield r
+    r.close()
+
+
+def run_both(ref, handle, op_a, op_b, m, n, k, num_split, kind, alpha=1.0, beta=0.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ra, ca = (m, k) if op_a == 0 else (k, m)
+    rb, cb = (k, n) if op_b == 0 else (n, k)
+
+    def gen(count):
+        if kind == "urand01":
+            return 1.0 - torch.rand(count, dtype=torch.float64, device="cuda", generator=g)
+        if kind == "normal01":
+            return torch.randn(count, dtype=torch.float64, device="cuda", generator=g)
+        phi = float(kind.split("-", 1)[1])
+        return (torch.rand(count, dtype=torch.float64, device="cuda", generator=g) - 0.5) * torch.exp(
+            phi * torch.randn(count, dtype=torch.float64, device="cuda", generator=g))
+
+    a, b = gen(ra * ca), gen(rb * cb)
+    c0 = torch.randn(m * n, dtype=torch.float64, device="cuda", generator=g)
+    c_ref, c_new = c0.clone(), c0.clone()
+    mode = oz.fp64_int8(num_split)
+    ref.gemm(op_a, op_b, m, n, k, alpha, a, ra, b, rb, beta, c_ref, m, mode)
+    assert oz.gemm(handle, op_a, op_b, m, n, k, alpha, a, ra, b, rb, beta, c_new, m, mode) == 0
+    torch.cuda.synchronize()
+    return a, b, c_ref, c_new
+
+
+# the reference's own CI grid: all op combos x {1023,1024,1025}^3 (sampled) x modes 8..16
+CI_SIZES = [(1023, 1023, 1023), (1024, 1024, 1024), (1025, 1025, 1025), (1023, 1025, 1024), (1025, 1024, 1023)]
+
+
+@pytest.mark.parametrize("op_a,op_b", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", CI_SIZES)
+def test_ci_grid_bit_exact_vs_reference(ref, handle, op_a, op_b, m, n, k):
+    for num_split in (8, 12, 16):
+        _, _, c_ref, c_new = run_both(ref, handle, op_a, op_b, m, n, k, num_split, "urand01", seed=num_split)
+        assert torch.equal(c_ref.view(torch.int64), c_new.view(torch.int64)), \
+            f"s={num_split}: max ulp distance {ulp_distance(c_ref, c_new)}"
+
+
+@pytest.mark.parametrize("num_split", list(range(3, 19)))
+def test_every_mode_bit_exact_vs_reference(ref, handle, num_split):
+    _, _, c_ref, c_new = run_both(ref, handle, 0, 0, 1024, 768, 1536, num_split, "exp_rand-1", alpha=-0.5, beta=1.25,
+                                  seed=100 + num_split)
+    assert torch.equal(c_ref.view(torch.int64), c_new.view(torch.int64)), \
+        f"max ulp distance {ulp_distance(c_ref, c_new)}"
+
+
+@pytest.mark.parametrize("kind", ["urand01", "normal01", "exp_rand-1"])
+def test_config2_4096_bit_exact_and_accurate(ref, handle, kind):
+    """BASELINE config 2: 4096^3 fp64_int8_9.  Parity: bit-exact vs the reference.  Accuracy: the
+    reference CI gate (relative residual < 1e-15 on urand01, test/main_test.cu:744) measured against
+    cuBLAS DGEMM."""
+    n = 4096
+    a, b, c_ref, c_new = run_both(ref, handle, 0, 0, n, n, n, 9, kind, seed=7)
+    assert torch.equal(c_ref.view(torch.int64), c_new.view(torch.int64)), \
+        f"max ulp distance {ulp_distance(c_ref, c_new)}"
+    # column-major A (n x n, ld n) is the row-major transpose: C^T = B^T A^T
+    c_blas = (b.view(n, n) @ a.view(n, n)).reshape(-1)
+    resid = (torch.linalg.vector_norm(c_new - c_blas) / torch.linalg.vector_norm(c_blas)).item()
+    if kind == "urand01":
+        assert resid < 1e-15
+    else:
+        assert resid < 1e-12
+
+
+def test_headline_8192_bit_exact_vs_reference(ref, handle):
+    """BASELINE headline size: 8192^3 fp64_int8_9, bit-for-bit against the reference."""
+    n = 8192
+    _, _, c_ref, c_new = run_both(ref, handle, 0, 0, n, n, n, 9, "urand01", seed=11)
+    assert torch.equal(c_ref.view(torch.int64), c_new.view(torch.int64)), \
+        f"max ulp distance {ulp_distance(c_ref, c_new)}"
+
+
+@pytest.mark.parametrize("shape", [(2, 1), (1, 2), (2, 2)])
+def test_cluster_shapes_same_bits(handle, shape):
+    m, n, k = 1000, 900, 2050
+    a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 1))
+    b = to_dev(oracle_lib.gen_matrix("exp_rand-1", k * n, 2))
+    c0 = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+    c1 = torch.zeros_like(c0)
+    oz.lib().ozk_set_cluster_shape(1, 1)
+    assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c0, m, oz.fp64_int8(9)) == 0
+    oz.lib().ozk_set_cluster_shape(*shape)
+    try:
+        assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c1, m, oz.fp64_int8(9)) == 0
+        torch.cuda.synchronize()
+    finally:
+        oz.lib().ozk_set_cluster_shape(0, 0)
+    assert torch.equal(c0.view(torch.int64), c1.view(torch.int64))
+
+
+def test_linearity_property_full_size(handle):
+    """Size-independent property at a BASELINE size: scaling A by a power of two scales C exactly
+    (the split is exponent-aligned per row, so 2^p * A has the same slices)."""
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(n * n, dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn(n * n, dtype=torch.float64, device="cuda", generator=g)
+    c1 = torch.empty(n * n, dtype=torch.float64, device="cuda")
+    c2 = torch.empty_like(c1)
+    assert oz.gemm(handle, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c1, n, oz.fp64_int8(9)) == 0
+    assert oz.gemm(handle, 0, 0, n, n, n, 1.0, a * 1024.0, n, b, n, 0.0, c2, n, oz.fp64_int8(9)) == 0
+    torch.cuda.synchronize()
+    assert torch.equal((c1 * 1024.0).view(torch.int64), c2.view(torch.int64))
+
+
+def test_gemm_host_equals_device_path(handle):
+    m, n, k = 1500, 4500, 1100  # 2-3 column panels, ragged
+    a = oracle_lib.gen_matrix("exp_rand-1", m * k, 21)
+    b = oracle_lib.gen_matrix("exp_rand-1", k * n, 22)
+    c = oracle_lib.gen_matrix("normal01", m * n, 23)
+    for (op_a, op_b) in [(0, 0), (1, 1)]:
+        lda = m if op_a == 0 else k
+        ldb = k if op_b == 0 else n
+        dc = to_dev(c)
+        assert oz.gemm(handle, op_a, op_b, m, n, k, 1.5, to_dev(a), lda, to_dev(b), ldb, -0.5, dc, m, oz.fp64_int8(9)) == 0
+        torch.cuda.synchronize()
+        ha = torch.from_numpy(a).pin_memory()
+        hb = torch.from_numpy(b).pin_memory()
+        hc = torch.from_numpy(c.copy()).pin_memory()
+        assert oz.gemm_host(handle, op_a, op_b, m, n, k, 1.5, ha, lda, hb, ldb, -0.5, hc, m, oz.fp64_int8(9)) == 0
+        assert np.array_equal(bits(hc.numpy()), bits(dc))
+        # pageable numpy operands too
+        hc2 = c.copy()
+        assert oz.gemm_host(handle, op_a, op_b, m, n, k, 1.5, a, lda, b, ldb, -0.5, hc2, m, oz.fp64_int8(9)) == 0
+        assert np.array_equal(bits(hc2), bits(dc))
+
+
+def test_stream_and_reuse(handle):
+    """Calls on a user stream, workspace growth between calls, back-to-back reuse."""
+    s = torch.cuda.Stream()
+    oz.set_cuda_stream(handle, s)
+    outs = []
+    with torch.cuda.stream(s):
+        for (m, n, k) in [(256, 256, 256), (700, 300, 900), (256, 256, 256)]:
+            a = to_dev(oracle_lib.gen_matrix("urand01", m * k, 1))
+            b = to_dev(oracle_lib.gen_matrix("urand01", k * n, 2))
+            c = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+            assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c, m, oz.fp64_int8(9)) == 0
+            outs.append(c)
+    s.synchronize()
+    oz.set_cuda_stream(handle, None)
+    assert torch.equal(outs[0].view(torch.int64), outs[2].view(torch.int64))
