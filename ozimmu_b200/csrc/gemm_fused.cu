@@ -23,6 +23,8 @@
 //  * Epilogue per product: tcgen05.ld 64 int32 columns of the thread's row, release the TMEM
 //    buffer, acc = fma((double)p, 2^(32-rshift), acc).  After the last pair:
 //    x = acc*2^-44*amax[r]*bmax[c]; C = alpha*x (+ beta*C), coalesced along rows of column-major C.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -57,6 +59,11 @@ struct FusedParams {
   const double *amax;
   const double *bmax;
   int32_t *c_i32;
+  // pair kernel tuning (see launch_pair): L2 prefetch lead in k-blocks; soft lockstep between CTA pairs
+  uint32_t prefetch_ahead;
+  uint32_t *sync_ctr;          // one arrival counter per kSyncEvery k-steps, zeroed before launch (or null)
+  uint32_t sync_window;        // a pair starts sync interval j only after interval j - window is complete
+  uint32_t sync_len;           // counters available
 };
 
 // reference src/config.cu:85-92: for sum = 2..s+1, for j = 1..sum-1: (A_id=j, B_id=sum-j)
@@ -305,6 +312,299 @@ oz_gemm_fused_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+// =================================================================================================
+// CTA-pair kernel (the default): tcgen05.mma.cta_group::2, UMMA M=256 x N=BN x K=32.
+//
+// Why: with one CTA per 128x128 tile every MMA-cycle moves 256 B through shared memory (TMA writes
+// + tensor-core reads of (128+128) x 32 B per 64 cycles) against a 128 B/clk port, which pins the
+// tensor pipe at 50 % (ncu profiles/r1_fused_1cta.txt).  A CTA pair shares B: each CTA stages its own
+// 128 rows of A and only BN/2 rows of B, and reads the same -- (128 + BN/2) x 64 B per BN/2 cycles:
+// 192 B/clk at BN=128, 149 B/clk at BN=192.  BN=192 is the widest tile whose FP64 accumulators
+// (128 x 192 per CTA = 192 registers per epilogue thread) still fit the register file.
+//
+// Per CTA: 128 x BN outputs, FP64 accumulators in the registers of 8 epilogue warps, int32 products
+// in kAccBufs TMEM buffers.  Leader CTA (cluster rank 0) issues all MMAs; both CTAs run a TMA
+// producer (completing on the LEADER's full barrier) and an epilogue (arriving on the LEADER's
+// tmem-empty barrier); tcgen05.commit multicasts "stage free" / "product ready" to both CTAs.
+// =================================================================================================
+constexpr uint32_t kSyncEvery = 16;      // k-steps per soft-lockstep interval of the pair kernel
+
+// Position in one CTA's operand stream of the pair kernel: (tile, slice pair, k-block), in issue order.
+template <uint32_t BN_>
+struct KCursor {
+  const FusedParams &p;
+  uint32_t t, step, num_tiles, kb, rank;
+  PairIter it;
+  int row_a, row_b;
+  __device__ KCursor(const FusedParams &p_, uint32_t first, uint32_t step_, uint32_t num_tiles_, uint32_t rank_)
+      : p(p_), t(first), step(step_), num_tiles(num_tiles_), kb(0), rank(rank_), it(p_) {
+    set_rows();
+  }
+  __device__ void set_rows() {
+    if (t >= num_tiles) return;
+    uint32_t tm, tn;
+    super_tile_coords(p, t, tm, tn);
+    row_a = static_cast<int>(tm * 2 * BM + rank * BM);
+    row_b = static_cast<int>(tn * BN_ + rank * (BN_ / 2));
+  }
+  __device__ bool valid() const { return t < num_tiles; }
+  __device__ int k0() const { return static_cast<int>(kb * BK); }
+  __device__ int sa() const { return static_cast<int>(it.a_id() - 1); }
+  __device__ int sb() const { return static_cast<int>(it.b_id() - 1); }
+  __device__ void next() {
+    if (++kb < p.k_blocks) return;
+    kb = 0;
+    it.next();
+    if (it.valid()) return;
+    it = PairIter(p);
+    t += step;
+    set_rows();
+  }
+  __device__ void prefetch(const CUtensorMap *ta, const CUtensorMap *tb) const {
+    ptx::tma_prefetch_l2_3d(ta, k0(), row_a, sa());
+    ptx::tma_prefetch_l2_3d(tb, k0(), row_b, sb());
+  }
+};
+
+template <uint32_t BN_>
+struct PairCfg {
+  static constexpr uint32_t kBN = BN_;
+  static constexpr uint32_t kStageBytes = (BM + BN_ / 2) * BK;       // per CTA
+  static constexpr uint32_t kStages = (BN_ == 128) ? 8 : 7;
+  static constexpr uint32_t kAccBufs = (BN_ == 128) ? 4 : 2;
+  static constexpr uint32_t kBufStride = (BN_ == 128) ? 128 : 256;   // TMEM columns between buffers
+  static constexpr uint32_t kBarBytes = 8 * (2 * kStages + 2 * kAccBufs) + 16;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr uint32_t kColsPerThread = BN_ / 2;                // epilogue: 2 column halves
+  static constexpr uint32_t kRegsOther = (BN_ == 128) ? 56 : 40;
+  static constexpr uint32_t kRegsEpi = (BN_ == 128) ? 224 : 232;
+};
+
+template <uint32_t BN_>
+__global__ void __launch_bounds__(kThreads, 1)
+oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const FusedParams p) {
+  using Cfg = PairCfg<BN_>;
+  constexpr uint32_t kStagesP = Cfg::kStages, kBufs = Cfg::kAccBufs, kCols = Cfg::kColsPerThread;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStagesP * Cfg::kStageBytes;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (kStagesP + s); };
+  auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * kStagesP + b); };
+  auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * kStagesP + kBufs + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStagesP + 2 * kBufs);
+  volatile uint32_t *tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  // warp-uniform by construction (shfl from lane 0), so that the single-warp role loops below stay
+  // on the uniform datapath: tcgen05.mma / TMA operands must be uniform registers, and values
+  // produced under lane-divergent control flow force a per-instruction ELECT/R2UR waterfall.
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0);  // 0 = leader
+  const uint32_t pair_id = blockIdx.x >> 1;
+  const uint32_t num_pairs = gridDim.x >> 1;
+  const uint32_t num_tiles = p.super_m * p.super_n;  // super_m: 256-row tiles, super_n: BN-column tiles
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < kStagesP; s++) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (uint32_t b = 0; b < kBufs; b++) {
+      ptx::mbar_init(tfull_bar(b), 1);
+      ptx::mbar_init(tempty_bar(b), 2 * kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 2) ptx::tmem_alloc_2sm<512>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+
+  if (warp < 4) {
+    ptx::reg_dealloc<Cfg::kRegsOther>();
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs; whole warp loops, one lane issues) ==========
+      // A second cursor runs kPrefetchAhead k-blocks ahead of the ring and pulls the boxes into L2
+      // (cp.async.bulk.prefetch): a slice panel is re-read once per pair that uses it and rarely
+      // survives in L2 between uses, so without this the ring (7 stages ~ 1.6 us) eats HBM latency.
+      const bool issuer = ptx::elect_one();
+      uint32_t stage = 0, ph = 0;
+      KCursor<BN_> ahead(p, pair_id, num_pairs, num_tiles, rank);
+      for (uint32_t i = 0; i < p.prefetch_ahead && ahead.valid(); i++, ahead.next()) {
+        if (issuer) ahead.prefetch(&tmap_a, &tmap_b);
+      }
+      // Soft lockstep: the CTA pairs of one wave share slice panels through L2 only while they stay
+      // within a few k-steps of each other; left alone they drift apart by whole products and every
+      // panel is re-fetched from HBM (ncu: 103 GB of DRAM reads for a 1.2 GB working set at 8192^3).
+      // Leaders count arrivals per kSyncEvery-step interval and do not start interval j before all
+      // pairs have started interval j - window.  It is a performance hint only: the wait is bounded
+      // and abandoned for the rest of the kernel on the first timeout.
+      const uint32_t steps_per_tile = (p.single_a != 0 ? 1u : p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
+      const uint32_t tiles_max = (num_tiles + num_pairs - 1) / num_pairs;
+      const uint32_t pairs_last = num_tiles - (tiles_max - 1) * num_pairs;  // pairs that own tiles_max tiles
+      bool lockstep = p.sync_ctr != nullptr && rank == 0;
+      uint32_t g = 0;
+      for (KCursor<BN_> cur(p, pair_id, num_pairs, num_tiles, rank); cur.valid(); cur.next(), g++) {
+        if (lockstep && (g % kSyncEvery) == 0) {
+          const uint32_t j = g / kSyncEvery;
+          if (j >= p.sync_len) {
+            lockstep = false;
+          } else {
+            uint32_t ok = 1;
+            if (issuer) {
+              atomicAdd(p.sync_ctr + j, 1u);
+              if (j >= p.sync_window) {
+                const uint32_t jw = j - p.sync_window;
+                const uint32_t want = (static_cast<uint64_t>(jw) * kSyncEvery < static_cast<uint64_t>(tiles_max - 1) * steps_per_tile)
+                                          ? num_pairs : pairs_last;
+                const long long t0 = clock64();
+                while (ptx::ld_relaxed_gpu(p.sync_ctr + jw) < want) {
+                  if (clock64() - t0 > 400000) { ok = 0; break; }
+                }
+              }
+            }
+            ok = __shfl_sync(0xffffffffu, ok, __ffs(__ballot_sync(0xffffffffu, issuer)) - 1);
+            if (!ok) lockstep = false;
+          }
+        }
+        ptx::mbar_wait(empty_bar(stage), ph ^ 1u);
+        const uint32_t leader_full = ptx::mapa(full_bar(stage), 0);
+        const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+        if (issuer) {
+          if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          ptx::tma_load_3d_2sm(a_dst, &tmap_a, leader_full, cur.k0(), cur.row_a, cur.sa());
+          ptx::tma_load_3d_2sm(a_dst + BM * BK, &tmap_b, leader_full, cur.k0(), cur.row_b, cur.sb());
+          if (ahead.valid()) ahead.prefetch(&tmap_a, &tmap_b);
+        }
+        if (ahead.valid()) ahead.next();
+        if (++stage == kStagesP) { stage = 0; ph ^= 1u; }
+      }
+    } else if (warp == 1 && rank == 0) {
+      // ===================== MMA issuer (leader CTA; whole warp loops, one lane issues) ============
+      constexpr uint32_t idesc = ptx::make_i8_idesc(2 * BM, BN_);
+      const bool issuer = ptx::elect_one();
+      uint32_t stage = 0, ph = 0, buf = 0, bph = 0;
+      for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
+        for (PairIter it(p); it.valid(); it.next()) {
+          ptx::mbar_wait_cluster(tempty_bar(buf), bph ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * Cfg::kBufStride;
+          for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
+            ptx::mbar_wait_cluster(full_bar(stage), ph);
+            ptx::tc_fence_after();
+            const uint32_t a_smem = smem_base + stage * Cfg::kStageBytes;
+            const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_smem);
+            const uint64_t b_desc = ptx::make_sw128_kmajor_desc(a_smem + BM * BK);
+            if (issuer) {
+#pragma unroll
+              for (uint32_t kk = 0; kk < BK / kUmmaK; kk++)
+                ptx::mma_i8_ss_2sm(d_tmem, a_desc + kk * (kUmmaK >> 4), b_desc + kk * (kUmmaK >> 4), idesc,
+                                   (kb | kk) != 0 ? 1u : 0u);
+              ptx::tc_commit_2sm_mc(empty_bar(stage), 0x3);
+            }
+            __syncwarp();
+            if (++stage == kStagesP) { stage = 0; ph ^= 1u; }
+          }
+          if (issuer) ptx::tc_commit_2sm_mc(tfull_bar(buf), 0x3);
+          __syncwarp();
+          if (++buf == kBufs) { buf = 0; bph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): 8 warps, FP64 accumulators in registers ==========
+    ptx::reg_alloc<Cfg::kRegsEpi>();
+    const uint32_t q = warp & 3u;            // TMEM lane quarter this warp may touch
+    const uint32_t half = (warp - 4u) >> 2;  // which column half of the tile
+    const bool raw = p.single_a != 0;
+    uint32_t pc = 0;
+    for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
+      uint32_t tm, tn;
+      super_tile_coords(p, t, tm, tn);
+      const uint32_t row = tm * 2 * BM + rank * BM + q * 32u + lane;
+      const uint32_t col0 = tn * BN_ + half * kCols;
+      double acc[kCols];
+#pragma unroll
+      for (uint32_t j = 0; j < kCols; j++) acc[j] = 0.0;
+      for (PairIter it(p); it.valid(); it.next(), pc++) {
+        const uint32_t buf = pc % kBufs, bph = (pc / kBufs) & 1u;
+        ptx::mbar_wait(tfull_bar(buf), bph);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * Cfg::kBufStride + half * kCols;
+        const double scale = it.scale(p.bits);
+#pragma unroll
+        for (uint32_t c = 0; c < kCols / 16; c++) {
+          uint32_t v[16];
+          ptx::tmem_ld_x16(taddr + c * 16, v);
+          ptx::tmem_ld_wait();
+          if (!raw) {
+            // (double)p without I2F.F64 (a quarter-rate conversion, 15/clk/SM measured, that would
+            // make the epilogue as slow as the MMAs): 2^52 + 2^31 + p is the bit pattern
+            // {0x43300000, p ^ 0x80000000}; subtracting 2^52 + 2^31 is exact.
+#pragma unroll
+            for (uint32_t g = 0; g < 16; g += 8) {
+              double d[8];
+#pragma unroll
+              for (uint32_t j = 0; j < 8; j++)
+                d[j] = __dadd_rn(__hiloint2double(0x43300000, static_cast<int>(v[g + j] ^ 0x80000000u)),
+                                 -4503601774854144.0);
+#pragma unroll
+              for (uint32_t j = 0; j < 8; j++)
+                acc[c * 16 + g + j] = __fma_rn(d[j], scale, acc[c * 16 + g + j]);
+            }
+          } else if (row < p.m) {
+#pragma unroll
+            for (uint32_t j = 0; j < 16; j++) {
+              const uint32_t col = col0 + c * 16 + j;
+              if (col < p.n) p.c_i32[static_cast<size_t>(col) * p.m + row] = static_cast<int32_t>(v[j]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) ptx::mbar_arrive(tempty_bar(buf));
+          else ptx::mbar_arrive_remote(ptx::mapa(tempty_bar(buf), 0));
+        }
+      }
+      if (!raw && row < p.m) {
+        // reference src/gemm.cu:124-148: x = acc / 2^44 * amax[mi] * bmax[ni]
+        const double am = p.amax[row];
+        double *crow = p.c + row;
+#pragma unroll
+        for (uint32_t j = 0; j < kCols; j++) {
+          const uint32_t col = col0 + j;
+          if (col < p.n) {
+            double x = __dmul_rn(acc[j], 0x1p-44);
+            x = __dmul_rn(x, am);
+            x = __dmul_rn(x, __ldg(p.bmax + col));
+            double *dst = crow + static_cast<size_t>(col) * p.ldc;
+            if (p.beta != 0) {
+              *dst = __fma_rn(p.alpha, x, __dmul_rn(p.beta, *dst));
+            } else {
+              *dst = __dmul_rn(p.alpha, x);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (warp == 2) ptx::tmem_dealloc_2sm<512>(tmem_base);
+}
+
 // k == 0: every product is empty, C = beta * C (beta == 0: C is not read, reference src/gemm.cu:143-147)
 __global__ void __launch_bounds__(256)
 oz_scale_c_kernel(double *__restrict__ c, const size_t ldc, const uint32_t m, const uint32_t n, const double beta) {
@@ -347,7 +647,9 @@ int make_slice_tmap(CUtensorMap *map, const int8_t *base, size_t rows, size_t pi
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(cudaErrorInvalidValue);
 }
 
-int g_cluster_override = 0;  // 0 = heuristic; else CM*10+CN (test hook, see ozk_set_cluster_shape)
+// 0 = default (CTA-pair kernel, BN=192); 128/192 = CTA-pair kernel with that BN; CM*10+CN = the
+// single-CTA kernel with a CM x CN multicast cluster (test/tuning hook, see ozk_set_cluster_shape)
+int g_cluster_override = 0;
 
 template <uint32_t CM, uint32_t CN>
 int launch_fused(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_slices, size_t pitch,
@@ -404,11 +706,122 @@ int launch_fused(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_
   return 0;
 }
 
+
+// ---- pair-kernel tuning knobs (read once; OZIMMU_B200_PREFETCH / OZIMMU_B200_LOCKSTEP override) ----
+struct PairTuning {
+  uint32_t prefetch_ahead;  // k-blocks of L2 prefetch lead (0 = off)
+  uint32_t sync_window;     // soft-lockstep window in kSyncEvery-step intervals (0 = off)
+};
+const PairTuning &pair_tuning() {
+  static const PairTuning t = [] {
+    PairTuning v{16, 2};
+    if (const char *e = std::getenv("OZIMMU_B200_PREFETCH")) v.prefetch_ahead = static_cast<uint32_t>(std::atoi(e));
+    if (const char *e = std::getenv("OZIMMU_B200_LOCKSTEP")) v.sync_window = static_cast<uint32_t>(std::atoi(e));
+    if (v.prefetch_ahead > 256) v.prefetch_ahead = 256;
+    return v;
+  }();
+  return t;
+}
+
+constexpr uint32_t kSyncCounters = 1u << 16;  // per buffer: 64 Ki intervals = 1 Mi k-steps per CTA pair
+constexpr int kSyncBuffers = 8;               // launches that may be in flight at once without sharing
+uint32_t *next_sync_buffer() {
+  static uint32_t *pool[kSyncBuffers] = {};
+  static int pool_dev[kSyncBuffers] = {};
+  static int next = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  const int i = next;
+  next = (next + 1) % kSyncBuffers;
+  if (pool[i] != nullptr && pool_dev[i] != dev) {
+    pool[i] = nullptr;  // another device's buffer: leak-free enough for a per-process pool of 8 x 256 KB
+  }
+  if (pool[i] == nullptr) {
+    if (cudaMalloc(&pool[i], kSyncCounters * sizeof(uint32_t)) != cudaSuccess) {
+      pool[i] = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+    pool_dev[i] = dev;
+  }
+  return pool[i];
+}
+
+template <uint32_t BN_>
+int launch_pair(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_slices, size_t pitch,
+                cudaStream_t stream) {
+  using Cfg = PairCfg<BN_>;
+  FusedParams p = p0;
+  CUtensorMap ta, tb;
+  int rc = make_slice_tmap(&ta, a_slices, p.m, pitch, p.num_split, BM);
+  if (rc) return rc;
+  rc = make_slice_tmap(&tb, b_slices, p.n, pitch, p.num_split, BN_ / 2);
+  if (rc) return rc;
+  p.super_m = ceil_div_u32(p.m, 2 * BM);
+  p.super_n = ceil_div_u32(p.n, BN_);
+  p.group_m = 8;
+  const PairTuning &tune = pair_tuning();
+  p.prefetch_ahead = tune.prefetch_ahead;
+  p.sync_window = tune.sync_window;
+
+  auto kern = oz_gemm_pair_kernel<BN_>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    OZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  int dev = 0, sms = 0;
+  OZ_CUDA_TRY(cudaGetDevice(&dev));
+  OZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int cached_max = -1;
+  if (cached_max < 0) {
+    cfg.gridDim = dim3(static_cast<unsigned>(sms) / 2 * 2);
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) cached_max = nc;
+    else cached_max = sms / 2;
+  }
+  const uint32_t num_tiles = p.super_m * p.super_n;
+  const uint32_t pairs = num_tiles < static_cast<uint32_t>(cached_max) ? num_tiles : static_cast<uint32_t>(cached_max);
+  if (pairs == 0) return 0;
+  cfg.gridDim = dim3(pairs * 2);
+  // lockstep counters only pay off when several waves of tiles stream through L2
+  p.sync_ctr = nullptr;
+  if (tune.sync_window > 0 && pairs > 1 && p.single_a == 0) {
+    const uint64_t steps = static_cast<uint64_t>(ceil_div_u32(num_tiles, pairs)) * (p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
+    const uint64_t need = steps / kSyncEvery + 1;
+    if (need <= kSyncCounters) {
+      uint32_t *buf = next_sync_buffer();
+      if (buf) {
+        OZ_CUDA_TRY(cudaMemsetAsync(buf, 0, need * sizeof(uint32_t), stream));
+        p.sync_ctr = buf;
+        p.sync_len = static_cast<uint32_t>(need);
+      }
+    }
+  }
+  OZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  count_launch(1);
+  return 0;
+}
+
 int dispatch_fused(const FusedParams &p, const int8_t *a_slices, const int8_t *b_slices, size_t pitch,
                    cudaStream_t stream) {
   int shape = g_cluster_override;
-  if (shape == 0) shape = 11;
+  if (shape == 0) shape = 192;
   switch (shape) {
+    case 192: return launch_pair<192>(p, a_slices, b_slices, pitch, stream);
+    case 128: return launch_pair<128>(p, a_slices, b_slices, pitch, stream);
     case 11: return launch_fused<1, 1>(p, a_slices, b_slices, pitch, stream);
     case 21: return launch_fused<2, 1>(p, a_slices, b_slices, pitch, stream);
     case 12: return launch_fused<1, 2>(p, a_slices, b_slices, pitch, stream);
@@ -427,7 +840,8 @@ bool valid_common(size_t m, size_t n, size_t k, size_t pitch, unsigned num_split
 
 // Test/tuning hook: force the cluster shape of the fused kernel (0 = default heuristic).
 extern "C" int ozk_set_cluster_shape(int cm, int cn) {
-  oz::g_cluster_override = (cm <= 0 || cn <= 0) ? 0 : cm * 10 + cn;
+  if (cm == 0 && (cn == 128 || cn == 192)) oz::g_cluster_override = cn;  // CTA-pair kernel, BN = cn
+  else oz::g_cluster_override = (cm <= 0 || cn <= 0) ? 0 : cm * 10 + cn;
   return 0;
 }
 

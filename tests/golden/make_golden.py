@@ -21,12 +21,14 @@ from gpu_util import Reference, to_dev  # noqa: E402
 
 # (op_a, op_b, m, n, k, num_split, kind, alpha, beta, ld_extra)
 GEMM_CASES = [
+    # m is a multiple of 4 everywhere: cuBLAS 12.9 on sm_100 rejects the reference's int8 GemmEx
+    # (src/gemm.cu:322, ldc = m) otherwise -- the reference's own ci_test sizes 1023/1025 fail on B200.
     (0, 0, 24, 20, 40, 9, "urand01", 1.0, 0.0, 0),
-    (1, 0, 17, 23, 33, 13, "exp_rand-2", -1.5, 0.75, 3),
-    (0, 1, 31, 9, 64, 3, "normal01", 2.0, 0.0, 1),
-    (1, 1, 20, 28, 50, 18, "mixed", 1.0, -1.0, 0),
-    (0, 0, 5, 7, 131, 6, "exp_rand-1", 0.5, 2.0, 2),
-    (0, 0, 16, 16, 300, 10, "exp_rand-4", 1.0, 0.0, 0),
+    (1, 0, 16, 23, 33, 13, "exp_rand-2", -1.5, 0.75, 3),
+    (0, 1, 32, 9, 64, 3, "normal01", 2.0, 0.0, 1),
+    (1, 1, 20, 27, 50, 18, "mixed", 1.0, -1.0, 0),
+    (0, 0, 4, 7, 131, 6, "exp_rand-1", 0.5, 2.0, 2),
+    (0, 0, 16, 15, 300, 10, "exp_rand-4", 1.0, 0.0, 0),
 ]
 # auto mode: no exact zeros and k % 32 == 0, the only regime where the reference's counters are
 # reliable; only the first 8 counters exist in the reference (App. B.1)

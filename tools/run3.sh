@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+(timeout 300 python -m pytest tests/test_gpu_kernels.py -q --maxfail=4 -k "pair_product") > gpurun_out/t_kernels_pair.log 2>&1; echo "pair rc=$?"; tail -15 gpurun_out/t_kernels_pair.log
+(timeout 900 python -m pytest tests/test_gpu_gemm.py -q --maxfail=6) > gpurun_out/t_gemm.log 2>&1; echo "gemm rc=$?"; tail -15 gpurun_out/t_gemm.log
+(timeout 300 python tools/perf_probe.py 4096 9 --shapes p192,p128,11) > gpurun_out/perf4096.log 2>&1; echo "perf rc=$?"; cat gpurun_out/perf4096.log
+(timeout 300 python tools/perf_probe.py 8192 9 --shapes p192,p128,11) > gpurun_out/perf8192.log 2>&1; echo "perf rc=$?"; cat gpurun_out/perf8192.log
