@@ -330,22 +330,25 @@ oz_gemm_fused_kernel(const __grid_constant__ CUtensorMap tmap_a,
 constexpr uint32_t kSyncEvery = 16;      // k-steps per soft-lockstep interval of the pair kernel
 
 // Position in one CTA's operand stream of the pair kernel: (tile, slice pair, k-block), in issue order.
-template <uint32_t BN_>
+// With a PM x PN cluster of CTA pairs each CTA fetches only its 1/PN share of the A rows and 1/PM
+// share of the B rows it needs (the rest arrives by TMA multicast from its cluster neighbours).
+template <uint32_t BN_, uint32_t PM, uint32_t PN>
 struct KCursor {
   const FusedParams &p;
-  uint32_t t, step, num_tiles, kb, rank;
+  uint32_t t, step, num_tiles, kb, rank, pm, pn;
   PairIter it;
   int row_a, row_b;
-  __device__ KCursor(const FusedParams &p_, uint32_t first, uint32_t step_, uint32_t num_tiles_, uint32_t rank_)
-      : p(p_), t(first), step(step_), num_tiles(num_tiles_), kb(0), rank(rank_), it(p_) {
+  __device__ KCursor(const FusedParams &p_, uint32_t first, uint32_t step_, uint32_t num_tiles_, uint32_t rank_,
+                     uint32_t pm_, uint32_t pn_)
+      : p(p_), t(first), step(step_), num_tiles(num_tiles_), kb(0), rank(rank_), pm(pm_), pn(pn_), it(p_) {
     set_rows();
   }
   __device__ void set_rows() {
     if (t >= num_tiles) return;
     uint32_t tm, tn;
     super_tile_coords(p, t, tm, tn);
-    row_a = static_cast<int>(tm * 2 * BM + rank * BM);
-    row_b = static_cast<int>(tn * BN_ + rank * (BN_ / 2));
+    row_a = static_cast<int>((tm * PM + pm) * 2 * BM + rank * BM + pn * (BM / PN));
+    row_b = static_cast<int>((tn * PN + pn) * BN_ + rank * (BN_ / 2) + pm * (BN_ / 2 / PM));
   }
   __device__ bool valid() const { return t < num_tiles; }
   __device__ int k0() const { return static_cast<int>(kb * BK); }
@@ -380,11 +383,12 @@ struct PairCfg {
   static constexpr uint32_t kRegsEpi = (BN_ == 128) ? 224 : 232;
 };
 
-template <uint32_t BN_>
+template <uint32_t BN_, uint32_t PM, uint32_t PN>
 __global__ void __launch_bounds__(kThreads, 1)
 oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const FusedParams p) {
   using Cfg = PairCfg<BN_>;
+  constexpr uint32_t CSZ = 2 * PM * PN;  // CTAs per cluster: PM x PN CTA pairs
   constexpr uint32_t kStagesP = Cfg::kStages, kBufs = Cfg::kAccBufs, kCols = Cfg::kColsPerThread;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -402,15 +406,19 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // produced under lane-divergent control flow force a per-instruction ELECT/R2UR waterfall.
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0);  // 0 = leader
-  const uint32_t pair_id = blockIdx.x >> 1;
-  const uint32_t num_pairs = gridDim.x >> 1;
-  const uint32_t num_tiles = p.super_m * p.super_n;  // super_m: 256-row tiles, super_n: BN-column tiles
+  const uint32_t crank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0);
+  const uint32_t rank = crank & 1u;      // within the CTA pair: 0 = leader (issues the MMAs)
+  const uint32_t pidx = crank >> 1;      // pair index in the cluster
+  const uint32_t pm = pidx % PM, pn = pidx / PM;
+  const uint32_t lead = crank & ~1u;     // cluster rank of this pair's leader
+  const uint32_t pair_id = blockIdx.x / CSZ;       // cluster index (one cluster tile at a time)
+  const uint32_t num_pairs = gridDim.x / CSZ;
+  const uint32_t num_tiles = p.super_m * p.super_n;  // cluster tiles: (PM*256) rows x (PN*BN) columns
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < kStagesP; s++) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), PM + PN - 1);  // one release per pair that reads what this CTA stages
     }
     for (uint32_t b = 0; b < kBufs; b++) {
       ptx::mbar_init(tfull_bar(b), 1);
@@ -438,7 +446,12 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // survives in L2 between uses, so without this the ring (7 stages ~ 1.6 us) eats HBM latency.
       const bool issuer = ptx::elect_one();
       uint32_t stage = 0, ph = 0;
-      KCursor<BN_> ahead(p, pair_id, num_pairs, num_tiles, rank);
+      KCursor<BN_, PM, PN> ahead(p, pair_id, num_pairs, num_tiles, rank, pm, pn);
+      // TMA multicast: this CTA's share of the A rows goes to the same-rank CTA of every pair in its
+      // cluster row, its share of the B rows to the same-rank CTA of every pair in its cluster column
+      uint16_t mask_a = 0, mask_b = 0;
+      for (uint32_t j = 0; j < PN; j++) mask_a |= static_cast<uint16_t>(1u << (2 * (pm + PM * j) + rank));
+      for (uint32_t i = 0; i < PM; i++) mask_b |= static_cast<uint16_t>(1u << (2 * (i + PM * pn) + rank));
       for (uint32_t i = 0; i < p.prefetch_ahead && ahead.valid(); i++, ahead.next()) {
         if (issuer) ahead.prefetch(&tmap_a, &tmap_b);
       }
@@ -451,9 +464,9 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t steps_per_tile = (p.single_a != 0 ? 1u : p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
       const uint32_t tiles_max = (num_tiles + num_pairs - 1) / num_pairs;
       const uint32_t pairs_last = num_tiles - (tiles_max - 1) * num_pairs;  // pairs that own tiles_max tiles
-      bool lockstep = p.sync_ctr != nullptr && rank == 0;
+      bool lockstep = p.sync_ctr != nullptr && crank == 0;
       uint32_t g = 0;
-      for (KCursor<BN_> cur(p, pair_id, num_pairs, num_tiles, rank); cur.valid(); cur.next(), g++) {
+      for (KCursor<BN_, PM, PN> cur(p, pair_id, num_pairs, num_tiles, rank, pm, pn); cur.valid(); cur.next(), g++) {
         if (lockstep && (g % kSyncEvery) == 0) {
           const uint32_t j = g / kSyncEvery;
           if (j >= p.sync_len) {
@@ -477,12 +490,15 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         ptx::mbar_wait(empty_bar(stage), ph ^ 1u);
-        const uint32_t leader_full = ptx::mapa(full_bar(stage), 0);
-        const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+        const uint32_t leader_full = ptx::mapa(full_bar(stage), lead);
+        const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes + pn * (BM / PN) * BK;
+        const uint32_t b_dst = smem_base + stage * Cfg::kStageBytes + BM * BK + pm * (BN_ / 2 / PM) * BK;
         if (issuer) {
           if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          ptx::tma_load_3d_2sm(a_dst, &tmap_a, leader_full, cur.k0(), cur.row_a, cur.sa());
-          ptx::tma_load_3d_2sm(a_dst + BM * BK, &tmap_b, leader_full, cur.k0(), cur.row_b, cur.sb());
+          if (PN > 1) ptx::tma_load_3d_2sm_mc(a_dst, &tmap_a, leader_full, cur.k0(), cur.row_a, cur.sa(), mask_a);
+          else ptx::tma_load_3d_2sm(a_dst, &tmap_a, leader_full, cur.k0(), cur.row_a, cur.sa());
+          if (PM > 1) ptx::tma_load_3d_2sm_mc(b_dst, &tmap_b, leader_full, cur.k0(), cur.row_b, cur.sb(), mask_b);
+          else ptx::tma_load_3d_2sm(b_dst, &tmap_b, leader_full, cur.k0(), cur.row_b, cur.sb());
           if (ahead.valid()) ahead.prefetch(&tmap_a, &tmap_b);
         }
         if (ahead.valid()) ahead.next();
@@ -492,6 +508,12 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // ===================== MMA issuer (leader CTA; whole warp loops, one lane issues) ============
       constexpr uint32_t idesc = ptx::make_i8_idesc(2 * BM, BN_);
       const bool issuer = ptx::elect_one();
+      // "stage consumed" goes to every CTA that stages data for this pair: both CTAs of all pairs in
+      // this pair's cluster row and column; "product ready" to the two CTAs of this pair
+      uint16_t mask_e = 0;
+      for (uint32_t j = 0; j < PN; j++) mask_e |= static_cast<uint16_t>(3u << (2 * (pm + PM * j)));
+      for (uint32_t i = 0; i < PM; i++) mask_e |= static_cast<uint16_t>(3u << (2 * (i + PM * pn)));
+      const uint16_t mask_t = static_cast<uint16_t>(3u << (2 * pidx));
       uint32_t stage = 0, ph = 0, buf = 0, bph = 0;
       for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
         for (PairIter it(p); it.valid(); it.next()) {
@@ -509,12 +531,12 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               for (uint32_t kk = 0; kk < BK / kUmmaK; kk++)
                 ptx::mma_i8_ss_2sm(d_tmem, a_desc + kk * (kUmmaK >> 4), b_desc + kk * (kUmmaK >> 4), idesc,
                                    (kb | kk) != 0 ? 1u : 0u);
-              ptx::tc_commit_2sm_mc(empty_bar(stage), 0x3);
+              ptx::tc_commit_2sm_mc(empty_bar(stage), mask_e);
             }
             __syncwarp();
             if (++stage == kStagesP) { stage = 0; ph ^= 1u; }
           }
-          if (issuer) ptx::tc_commit_2sm_mc(tfull_bar(buf), 0x3);
+          if (issuer) ptx::tc_commit_2sm_mc(tfull_bar(buf), mask_t);
           __syncwarp();
           if (++buf == kBufs) { buf = 0; bph ^= 1u; }
         }
@@ -530,8 +552,8 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
       uint32_t tm, tn;
       super_tile_coords(p, t, tm, tn);
-      const uint32_t row = tm * 2 * BM + rank * BM + q * 32u + lane;
-      const uint32_t col0 = tn * BN_ + half * kCols;
+      const uint32_t row = (tm * PM + pm) * 2 * BM + rank * BM + q * 32u + lane;
+      const uint32_t col0 = (tn * PN + pn) * BN_ + half * kCols;
       double acc[kCols];
 #pragma unroll
       for (uint32_t j = 0; j < kCols; j++) acc[j] = 0.0;
@@ -573,7 +595,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __syncwarp();
         if (lane == 0) {
           if (rank == 0) ptx::mbar_arrive(tempty_bar(buf));
-          else ptx::mbar_arrive_remote(ptx::mapa(tempty_bar(buf), 0));
+          else ptx::mbar_arrive_remote(ptx::mapa(tempty_bar(buf), lead));
         }
       }
       if (!raw && row < p.m) {
@@ -747,24 +769,25 @@ uint32_t *next_sync_buffer() {
   return pool[i];
 }
 
-template <uint32_t BN_>
+template <uint32_t BN_, uint32_t PM, uint32_t PN>
 int launch_pair(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_slices, size_t pitch,
                 cudaStream_t stream) {
   using Cfg = PairCfg<BN_>;
+  constexpr uint32_t CSZ = 2 * PM * PN;
   FusedParams p = p0;
   CUtensorMap ta, tb;
-  int rc = make_slice_tmap(&ta, a_slices, p.m, pitch, p.num_split, BM);
+  int rc = make_slice_tmap(&ta, a_slices, p.m, pitch, p.num_split, BM / PN);
   if (rc) return rc;
-  rc = make_slice_tmap(&tb, b_slices, p.n, pitch, p.num_split, BN_ / 2);
+  rc = make_slice_tmap(&tb, b_slices, p.n, pitch, p.num_split, BN_ / 2 / PM);
   if (rc) return rc;
-  p.super_m = ceil_div_u32(p.m, 2 * BM);
-  p.super_n = ceil_div_u32(p.n, BN_);
-  p.group_m = 8;
+  p.super_m = ceil_div_u32(p.m, 2 * BM * PM);
+  p.super_n = ceil_div_u32(p.n, BN_ * PN);
+  p.group_m = 8 / PM;
   const PairTuning &tune = pair_tuning();
   p.prefetch_ahead = tune.prefetch_ahead;
   p.sync_window = tune.sync_window;
 
-  auto kern = oz_gemm_pair_kernel<BN_>;
+  auto kern = oz_gemm_pair_kernel<BN_, PM, PN>;
   static bool attr_done = false;
   if (!attr_done) {
     OZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -780,22 +803,25 @@ int launch_pair(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_s
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = CSZ;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   static int cached_max = -1;
   if (cached_max < 0) {
-    cfg.gridDim = dim3(static_cast<unsigned>(sms) / 2 * 2);
+    cfg.gridDim = dim3(static_cast<unsigned>(sms) / CSZ * CSZ);
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) cached_max = nc;
-    else cached_max = sms / 2;
+    else cached_max = sms / static_cast<int>(CSZ);
+    if (std::getenv("OZIMMU_B200_DEBUG"))
+      std::fprintf(stderr, "[ozimmu_b200] pair kernel BN=%u cluster %ux%u pairs: %d clusters resident (%d of %d SMs)\n", BN_,
+                   PM, PN, cached_max, cached_max * static_cast<int>(CSZ), sms);
   }
   const uint32_t num_tiles = p.super_m * p.super_n;
   const uint32_t pairs = num_tiles < static_cast<uint32_t>(cached_max) ? num_tiles : static_cast<uint32_t>(cached_max);
   if (pairs == 0) return 0;
-  cfg.gridDim = dim3(pairs * 2);
+  cfg.gridDim = dim3(pairs * CSZ);
   // lockstep counters only pay off when several waves of tiles stream through L2
   p.sync_ctr = nullptr;
   if (tune.sync_window > 0 && pairs > 1 && p.single_a == 0) {
@@ -820,8 +846,11 @@ int dispatch_fused(const FusedParams &p, const int8_t *a_slices, const int8_t *b
   int shape = g_cluster_override;
   if (shape == 0) shape = 192;
   switch (shape) {
-    case 192: return launch_pair<192>(p, a_slices, b_slices, pitch, stream);
-    case 128: return launch_pair<128>(p, a_slices, b_slices, pitch, stream);
+    case 192: return launch_pair<192, 1, 1>(p, a_slices, b_slices, pitch, stream);
+    case 128: return launch_pair<128, 1, 1>(p, a_slices, b_slices, pitch, stream);
+    case 1120: return launch_pair<192, 2, 1>(p, a_slices, b_slices, pitch, stream);
+    case 1210: return launch_pair<192, 1, 2>(p, a_slices, b_slices, pitch, stream);
+    case 1220: return launch_pair<192, 2, 2>(p, a_slices, b_slices, pitch, stream);
     case 11: return launch_fused<1, 1>(p, a_slices, b_slices, pitch, stream);
     case 21: return launch_fused<2, 1>(p, a_slices, b_slices, pitch, stream);
     case 12: return launch_fused<1, 2>(p, a_slices, b_slices, pitch, stream);
@@ -841,6 +870,8 @@ bool valid_common(size_t m, size_t n, size_t k, size_t pitch, unsigned num_split
 // Test/tuning hook: force the cluster shape of the fused kernel (0 = default heuristic).
 extern "C" int ozk_set_cluster_shape(int cm, int cn) {
   if (cm == 0 && (cn == 128 || cn == 192)) oz::g_cluster_override = cn;  // CTA-pair kernel, BN = cn
+  else if (cm == 100 && (cn == 21 || cn == 12 || cn == 22))              // BN=192, PM x PN pairs multicast
+    oz::g_cluster_override = 1000 + cn * 10;
   else oz::g_cluster_override = (cm <= 0 || cn <= 0) ? 0 : cm * 10 + cn;
   return 0;
 }

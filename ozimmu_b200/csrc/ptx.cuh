@@ -142,6 +142,17 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap *m, int c0,
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// CTA-pair + multicast: the box lands at the same SMEM offset of every CTA in `mask`; each
+// destination pair's leader barrier (the one `bar` names: an even-rank CTA) gets the bytes.
+__device__ __forceinline__ void tma_load_3d_2sm_mc(uint32_t dst, const CUtensorMap *m, uint32_t bar,
+                                                   int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+
 // ---- tcgen05 --------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

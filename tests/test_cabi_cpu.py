@@ -1,0 +1,82 @@
+"""CPU: the C-ABI shared library loads without a GPU and exports every symbol include/ozimmu_b200.h
+declares, plus the cuBLAS entry points it interposes; host-only entry points behave like the reference's."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+import ozimmu_b200 as oz
+from ozimmu_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "ozimmu_b200.h"
+
+
+def declared_functions():
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(oz(?:k|immu)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    names = declared_functions()
+    for must in ("ozk_split_int8", "ozk_gemm_i8_fused", "ozk_mantissa_loss", "ozimmu_create", "ozimmu_gemm",
+                 "ozimmu_gemm_host", "ozimmu_auto_mode_select"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = oz.lib()
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/ozimmu_b200.h but not exported"
+    assert sorted(declared_functions()) == sorted(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+
+
+def test_library_exports_cublas_interposers():
+    out = subprocess.run(["nm", "-D", "--defined-only", str(oz.LIB_PATH)], capture_output=True, text=True, check=True)
+    defined = {line.split()[-1] for line in out.stdout.splitlines() if " T " in line}
+    for name in _lib.INTERPOSED:
+        assert name in defined
+    # the C++ API of the reference header is exported too (namespace mtk::ozimmu)
+    mangled = subprocess.run(["nm", "-DC", "--defined-only", str(oz.LIB_PATH)], capture_output=True, text=True).stdout
+    for fn in ("mtk::ozimmu::create", "mtk::ozimmu::destroy", "mtk::ozimmu::gemm", "mtk::ozimmu::auto_mode_select",
+               "mtk::ozimmu::reallocate_working_memory", "mtk::ozimmu::get_compute_mode_name_str",
+               "mtk::ozimmu::get_auto_mantissa_loss_threashold", "mtk::ozimmu::set_cuda_stream"):
+        assert re.search(re.escape(fn) + r"(\[abi:cxx11\])?\(", mangled), fn
+
+
+def test_kernels_are_blackwell_native():
+    """SASS of the shipped library must contain tcgen05 MMA (UTCIMMA), TMEM loads (LDTM) and TMA (UTMALDG)."""
+    out = subprocess.run(["cuobjdump", "-sass", str(oz.LIB_PATH)], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG", "UTMAPF"):
+        assert mnemonic in out.stdout, mnemonic
+
+
+def test_mode_names_and_sizes():
+    assert oz.get_compute_mode_name_str(oz.compute_mode_t.dgemm) == "dgemm"
+    assert oz.get_compute_mode_name_str(oz.compute_mode_t.sgemm) == "sgemm"
+    assert oz.get_compute_mode_name_str(oz.compute_mode_t.fp64_int8_auto) == "fp64_int8_auto"
+    for s in range(3, 19):
+        assert oz.get_compute_mode_name_str(oz.fp64_int8(s)) == f"fp64_int8_{s}"
+        assert oz.num_split_of(oz.fp64_int8(s)) == s
+    assert oz.lib().ozimmu_get_compute_mode_name_str(77) is None
+    assert int(oz.lib().ozk_slice_pitch(1)) == 16 and int(oz.lib().ozk_slice_pitch(4097)) == 4112
+
+
+def test_invalid_arguments_rejected_without_gpu():
+    lib = oz.lib()
+    one = C.c_double(1.0)
+    # null handle / bad mode -> 1 (invalid argument), never a crash
+    assert lib.ozimmu_gemm(None, 0, 0, 8, 8, 8, C.addressof(one), None, 8, None, 8, C.addressof(one), None, 8, 8, 0) == 1
+    assert lib.ozimmu_gemm_host(None, 0, 0, 8, 8, 8, C.addressof(one), None, 8, None, 8, C.addressof(one), None, 8, 8) == 1
+    # kernel launchers validate before touching the device
+    assert lib.ozk_split_int8(None, 17, None, None, 4, 4, None, 4, 0, 9, 7, None) != 0   # pitch % 16
+    assert lib.ozk_split_int8(None, 16, None, None, 4, 4, None, 4, 0, 2, 7, None) != 0   # num_split < 3
+    assert lib.ozk_gemm_i8_fused(8, 8, 8, None, None, 16, None, None, 19, 7, 1.0, 0.0, None, 8, None) != 0
+    assert lib.ozk_gemm_i8_fused(8, 8, 8, None, None, 16, None, None, 9, 7, 1.0, 0.0, None, 4, None) != 0  # ldc < m
+    assert lib.ozk_gemm_i8_fused(0, 8, 8, None, None, 16, None, None, 9, 7, 1.0, 0.0, None, 1, None) == 0  # empty
+    assert lib.ozimmu_launch_count() == 0

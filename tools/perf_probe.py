@@ -44,7 +44,12 @@ def main():
     flop = 2.0 * n ** 3
     pairs = s * (s + 1) // 2
     for shape in args.shapes.split(","):
-        cm, cn = (0, int(shape[1:])) if shape.startswith("p") else (int(shape[0]), int(shape[1]))
+        if shape.startswith("p"):      # CTA-pair kernel, BN = 128 / 192
+            cm, cn = 0, int(shape[1:])
+        elif shape.startswith("c"):    # CTA-pair kernel BN=192 in a PM x PN multicast cluster: c21, c12, c22
+            cm, cn = 100, int(shape[1:])
+        else:                          # legacy single-CTA kernel, cm x cn multicast cluster
+            cm, cn = int(shape[0]), int(shape[1])
         L.ozk_set_cluster_shape(cm, cn)
         ms = timed(lambda: oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(s)), args.iters)
         print(f"ozimmu_b200 n={n} s={s} cluster={cm}x{cn}: {ms:.3f} ms  {flop / ms / 1e9:.2f} TFLOP/s-equiv  "
