@@ -71,6 +71,13 @@ int ozk_split_int8(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch
                    size_t len, const double *in, size_t ld, int col_major, unsigned num_split,
                    unsigned bits_per_int8, void *stream);
 
+/* ozk_split_int8 on one plane of an interleaved complex matrix (reference src/split.cu:69-152,
+ * 211-216: real and imaginary parts are scaled and cut independently): `in` points at the plane's
+ * first double, elem_stride = 2, ld counts complex elements.  elem_stride = 1 is ozk_split_int8. */
+int ozk_split_int8_strided(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, size_t rows,
+                           size_t len, const double *in, size_t ld, int col_major, unsigned num_split,
+                           unsigned bits_per_int8, unsigned elem_stride, void *stream);
+
 /* reference src/gemm.cu:266-334 (matmul_core -> cublasGemmEx int8) + :77-102
  * (accumulate_in_f64) + :104-122 (init_accumulator_buffer) + :124-158 (axby), fused:
  * for every (i,j) of the reference pair order (src/config.cu:85-92) an exact
@@ -82,6 +89,15 @@ int ozk_gemm_i8_fused(size_t m, size_t n, size_t k, const int8_t *a_slices, cons
                       size_t pitch, const double *amax, const double *bmax, unsigned num_split,
                       unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
                       void *stream);
+
+/* One of the four real products of a complex GEMM (reference src/gemm.cu:479-518 loop body +
+ * :160-186 axy_complex + :188-239 init_c_complex): x = the fp64_int8 product of the given planes,
+ * C[i,j] = fma(x, (coef_re, coef_im), C'[i,j]) with C' = beta*C if apply_beta (first launch of the
+ * four; C not read when beta == 0) else C.  c: cuDoubleComplex*, ldc in complex elements. */
+int ozk_gemm_i8_fused_complex(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
+                              size_t pitch, const double *amax, const double *bmax, unsigned num_split,
+                              unsigned bits_per_int8, double coef_re, double coef_im, int apply_beta,
+                              double beta_re, double beta_im, void *c, size_t ldc, void *stream);
 
 /* Degenerate k == 0 product: C = beta * C (C not read when beta == 0; reference
  * src/gemm.cu:143-147 applied to an all-zero accumulator). */
@@ -104,6 +120,11 @@ int ozk_gemm_i8_pair(size_t m, size_t n, size_t k, const int8_t *a_slices, const
 int ozk_mantissa_loss(unsigned long long *counters16, uint32_t *scratch, size_t rows, size_t len,
                       const double *in, size_t ld, int col_major, unsigned bits_per_int8,
                       void *stream);
+
+/* ozk_mantissa_loss on one plane of an interleaved complex matrix (elem_stride = 2). */
+int ozk_mantissa_loss_strided(unsigned long long *counters16, uint32_t *scratch, size_t rows, size_t len,
+                              const double *in, size_t ld, int col_major, unsigned bits_per_int8,
+                              unsigned elem_stride, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * 2. Host API (C spelling of reference include/ozimmu/ozimmu.hpp)

@@ -55,20 +55,26 @@ uint32_t oz_slice_ld(uint32_t k) { return ((k + 3) / 4) * 4; }
 
 /* element (row r, position c) of a "row" of op(X): src/split.cu:203,210
  * col_major: in[c*ld + r]   else: in[c + r*ld] */
+static inline double oz_at_s(const double *in, size_t ld, int col_major, size_t r, size_t c, size_t es) {
+  return col_major ? in[(c * ld + r) * es] : in[(c + r * ld) * es];
+}
 static inline double oz_at(const double *in, size_t ld, int col_major, size_t r, size_t c) {
-  return col_major ? in[c * ld + r] : in[c + r * ld];
+  return oz_at_s(in, ld, col_major, r, c, 1);
 }
 
 /* src/split.cu:14-67 + :191,202-204: max over the row of the exponent-only value, times 2.
  * (cutf::math::max on doubles -> fmax; operands are never NaN unless exponent==0x7FF with
  *  mantissa cleared => +Inf, so fmax semantics are irrelevant.) */
-double oz_row_max_exp(const double *in, size_t ld, int col_major, size_t r, size_t len) {
+double oz_row_max_exp_s(const double *in, size_t ld, int col_major, size_t r, size_t len, size_t es) {
   double mx = 0.0;
   for (size_t c = 0; c < len; c++) {
-    double v = u2f(f2u(oz_at(in, ld, col_major, r, c)) & EXP_MASK);
+    double v = u2f(f2u(oz_at_s(in, ld, col_major, r, c, es)) & EXP_MASK);
     if (v > mx) mx = v;
   }
   return mx * 2.0;
+}
+double oz_row_max_exp(const double *in, size_t ld, int col_major, size_t r, size_t len) {
+  return oz_row_max_exp_s(in, ld, col_major, r, len, 1);
 }
 
 /* src/split.cu:155-185 cut_int8_core<double,__uint128_t>.  out[t*inc] for t<num_split.
@@ -92,17 +98,23 @@ void oz_cut_int8(int8_t *out, size_t inc, double a, double max_exp, unsigned num
 /* src/split.cu:193-242 split_int8_kernel (real) + :244-283 host wrappers.
  * rows x len view of op(X); out is [num_split][rows][ldo] int8, K contiguous, columns
  * len..ldo-1 zero-filled (:222-232); max_exp[rows] (:234-241). */
-void oz_split(int8_t *out, uint32_t ldo, double *max_exp, size_t rows, size_t len,
-              const double *in, size_t ld, int col_major, unsigned num_split, unsigned L) {
+/* es = 1: real matrix.  es = 2: one plane of an interleaved complex matrix (src/split.cu:69-152,
+ * 211-216: each plane has its own row maximum and is cut independently); `in` points at the plane. */
+void oz_split_s(int8_t *out, uint32_t ldo, double *max_exp, size_t rows, size_t len,
+                const double *in, size_t ld, int col_major, unsigned num_split, unsigned L, size_t es) {
   const size_t N = rows * (size_t)ldo;
   for (size_t r = 0; r < rows; r++) {
-    const double mx = oz_row_max_exp(in, ld, col_major, r, len);
+    const double mx = oz_row_max_exp_s(in, ld, col_major, r, len, es);
     for (size_t c = 0; c < len; c++)
-      oz_cut_int8(out + r * ldo + c, N, oz_at(in, ld, col_major, r, c), mx, num_split, L);
+      oz_cut_int8(out + r * ldo + c, N, oz_at_s(in, ld, col_major, r, c, es), mx, num_split, L);
     for (size_t c = len; c < ldo; c++)
       for (unsigned t = 0; t < num_split; t++) out[r * ldo + c + t * N] = 0;
     max_exp[r] = mx;
   }
+}
+void oz_split(int8_t *out, uint32_t ldo, double *max_exp, size_t rows, size_t len,
+              const double *in, size_t ld, int col_major, unsigned num_split, unsigned L) {
+  oz_split_s(out, ldo, max_exp, rows, len, in, ld, col_major, num_split, L, 1);
 }
 
 /* src/gemm.cu:315-329: cublasGemmEx(OP_T, OP_N, m, n, k4, 1, A_i(k4 x m), B_j(k4 x n), 0,
@@ -188,14 +200,77 @@ int oz_gemm(int op_a, int op_b, size_t m, size_t n, size_t k, double alpha, cons
   return 0;
 }
 
+/* src/gemm.cu:412-521 gemm_int8<cuDoubleComplex> with :160-186 axy_complex_kernel and :188-239
+ * init_c_complex (FMA contraction as in the reference's sm_100 SASS: t = c.y*b.y; c.x = fma(c.x, b.x, -t);
+ * t = c.x*b.y [the UPDATED c.x, the reference's aliasing bug]; c.y = fma(c.y, b.x, t)).
+ * a, b, c: interleaved (re, im) doubles; lda/ldb/ldc in complex elements; alpha/beta: {re, im}. */
+int oz_gemm_complex(int op_a, int op_b, size_t m, size_t n, size_t k, const double *alpha, const double *a,
+                    size_t lda, const double *b, size_t ldb, const double *beta, double *c, size_t ldc,
+                    unsigned num_split) {
+  const unsigned L = oz_bits_per_int8((uint32_t)k);
+  const uint32_t k4 = oz_slice_ld((uint32_t)k);
+  const size_t a_plane = (size_t)num_split * m * k4, b_plane = (size_t)num_split * n * k4;
+  int8_t *as = (int8_t *)malloc(2 * a_plane + 1);
+  int8_t *bs = (int8_t *)malloc(2 * b_plane + 1);
+  double *amax = (double *)malloc(sizeof(double) * (2 * m + 1));
+  double *bmax = (double *)malloc(sizeof(double) * (2 * n + 1));
+  double *acc = (double *)malloc(sizeof(double) * (m * n + 1));
+  int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * (m * n + 1));
+  int pa[200], pb[200];
+  if (!as || !bs || !amax || !bmax || !acc || !ci) return 1;
+  for (int part = 0; part < 2; part++) {
+    oz_split_s(as + part * a_plane, k4, amax + part * m, m, k, a + part, lda, op_a == 0, num_split, L, 2);
+    oz_split_s(bs + part * b_plane, k4, bmax + part * n, n, k, b + part, ldb, op_b != 0, num_split, L, 2);
+  }
+  /* init_c_complex */
+  for (size_t j = 0; j < n; j++)
+    for (size_t i = 0; i < m; i++) {
+      double *y = c + 2 * (i + j * ldc);
+      if (beta[0] == 0 && beta[1] == 0) {
+        y[0] = 0; y[1] = 0;
+      } else {
+        const double t = y[1] * beta[1];
+        y[0] = fma(y[0], beta[0], -t);
+        const double t2 = y[0] * beta[1];
+        y[1] = fma(y[1], beta[0], t2);
+      }
+    }
+  const int np = oz_pair_list((int)num_split, pa, pb);
+  static const int groups[4][2] = {{1, 1}, {0, 0}, {1, 0}, {0, 1}};          /* :479-480 */
+  for (int g = 0; g < 4; g++) {
+    const int ga = groups[g][0], gb = groups[g][1];
+    memset(acc, 0, sizeof(double) * m * n);
+    for (int p = 0; p < np; p++) {
+      oz_int8_gemm(ci, m, n, k4, as + ga * a_plane + (size_t)(pa[p] - 1) * m * k4,
+                   bs + gb * b_plane + (size_t)(pb[p] - 1) * n * k4);
+      oz_accumulate(acc, ci, m * n, (int32_t)L * (pa[p] + pb[p] - 2) - (7 - (int32_t)L) * 2);
+    }
+    double cr, cim;                                                            /* :497-509 */
+    if (ga == 0 && gb == 0) { cr = alpha[0]; cim = alpha[1]; }
+    else if (ga == 1 && gb == 1) { cr = -alpha[0]; cim = -alpha[1]; }
+    else { cr = -alpha[1]; cim = alpha[0]; }
+    for (size_t j = 0; j < n; j++)
+      for (size_t i = 0; i < m; i++) {
+        double x = acc[i + j * m] * 0x1p-44;
+        x = x * amax[ga * m + i];
+        x = x * bmax[gb * n + j];
+        double *y = c + 2 * (i + j * ldc);
+        y[0] = fma(x, cr, y[0]);
+        y[1] = fma(x, cim, y[1]);
+      }
+  }
+  free(as); free(bs); free(amax); free(bmax); free(acc); free(ci);
+  return 0;
+}
+
 /* src/split.cu:317-380 mantissa-loss totals, INTENDED semantics:
  * counters[16] for num_split = 3..18, accumulated (not reset) so A and B can be chained. */
-void oz_mantissa_loss(uint64_t counters[16], size_t rows, size_t len, const double *in, size_t ld,
-                      int col_major, unsigned L) {
+void oz_mantissa_loss_s(uint64_t counters[16], size_t rows, size_t len, const double *in, size_t ld,
+                        int col_major, unsigned L, size_t es) {
   for (size_t r = 0; r < rows; r++) {
-    const double mx = oz_row_max_exp(in, ld, col_major, r, len);
+    const double mx = oz_row_max_exp_s(in, ld, col_major, r, len, es);
     for (size_t c = 0; c < len; c++) {
-      const double x = oz_at(in, ld, col_major, r, c);
+      const double x = oz_at_s(in, ld, col_major, r, c, es);
       if (x == 0 || mx == 0) continue;                                    /* :322-324 */
       const uint64_t req = (((f2u(mx) & EXP_MASK) - (f2u(x) & EXP_MASK)) >> 52) + 53;
       for (unsigned s = 3; s <= 18; s++) {
@@ -204,6 +279,27 @@ void oz_mantissa_loss(uint64_t counters[16], size_t rows, size_t len, const doub
       }
     }
   }
+}
+
+void oz_mantissa_loss(uint64_t counters[16], size_t rows, size_t len, const double *in, size_t ld,
+                      int col_major, unsigned L) {
+  oz_mantissa_loss_s(counters, rows, len, in, ld, col_major, L, 1);
+}
+
+/* complex flavour of auto_mode_select_core (src/split.cu:365-372: both planes, each against its own row
+ * maximum; denominator counts complex elements, :484-493) */
+int oz_auto_select_complex(int op_a, int op_b, size_t m, size_t n, size_t k, const double *a, size_t lda,
+                           const double *b, size_t ldb, double threshold, uint64_t *counters_out) {
+  uint64_t cnt[16] = {0};
+  const unsigned L = oz_bits_per_int8((uint32_t)k);
+  for (int part = 0; part < 2; part++) {
+    oz_mantissa_loss_s(cnt, m, k, a + part, lda, op_a == 0, L, 2);
+    oz_mantissa_loss_s(cnt, n, k, b + part, ldb, op_b != 0, L, 2);
+  }
+  if (counters_out) memcpy(counters_out, cnt, sizeof(cnt));
+  for (int s = 3; s <= 18; s++)
+    if ((double)cnt[s - 3] / (double)(m * k + k * n) <= threshold) return s;
+  return 0;
 }
 
 /* src/split.cu:454-494 auto_mode_select_core: returns chosen num_split (3..18) or 0 for dgemm.

@@ -128,6 +128,62 @@ void gemm_int8_real(handle_t h, operation_t op_a, operation_t op_b, std::size_t 
   mark_done(h, s);
 }
 
+// reference src/gemm.cu:412-521 gemm_int8<cuDoubleComplex>: real and imaginary planes are split
+// independently, then four real fp64_int8 products are added into C in the order
+// (im,im) -> -alpha, (re,re) -> +alpha, (im,re) and (re,im) -> i*alpha, after C = beta*C.
+void gemm_int8_complex(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n, std::size_t k,
+                       const double *alpha, const double *a, std::size_t lda, const double *b, std::size_t ldb,
+                       const double *beta, double *c, std::size_t ldc, unsigned num_split) {
+  if (m == 0 || n == 0) return;
+  if (k == 0) throw std::runtime_error("ozIMMU: complex GEMM with k == 0 is not implemented");
+  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
+  const H::WorkspaceLayout w = H::workspace_layout(2 * m, 2 * n, k, num_split);  // two planes per operand
+  reallocate_working_memory(h, w.total);
+  ensure_streams(h);
+  char *ws = static_cast<char *>(h->working_memory_ptr);
+  double *amax = reinterpret_cast<double *>(ws + w.off_amax);   // [re m][im m]
+  double *bmax = reinterpret_cast<double *>(ws + w.off_bmax);   // [re n][im n]
+  auto *scr_a = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_a);
+  auto *scr_b = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_b);
+  auto *a_sl = reinterpret_cast<std::int8_t *>(ws + w.off_a_slices);
+  auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
+  const std::size_t a_plane = static_cast<std::size_t>(num_split) * m * w.pitch;
+  const std::size_t b_plane = static_cast<std::size_t>(num_split) * n * w.pitch;
+  cudaStream_t s = h->cuda_stream;
+  wait_previous(h, s);
+  const int a_col_major = (op_a == op_n), b_col_major = (op_b != op_n);
+  const bool overlap = !h->profiler.enabled;
+  cudaStream_t sb = overlap ? h->aux_stream : s;
+  if (overlap) {
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, h->ev_fork, 0));
+  }
+  h->profiler.start("split_A", s);
+  for (int part = 0; part < 2; part++)
+    OZ_KERNEL_CHECK(ozk_split_int8_strided(a_sl + part * a_plane, w.pitch, amax + part * m, scr_a + part * m, m, k,
+                                           a + part, lda, a_col_major, num_split, bits, 2, s));
+  h->profiler.stop("split_A", s);
+  h->profiler.start("split_B", sb);
+  for (int part = 0; part < 2; part++)
+    OZ_KERNEL_CHECK(ozk_split_int8_strided(b_sl + part * b_plane, w.pitch, bmax + part * n, scr_b + part * n, n, k,
+                                           b + part, ldb, b_col_major, num_split, bits, 2, sb));
+  h->profiler.stop("split_B", sb);
+  if (overlap) {
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, sb));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
+  }
+  // (A plane, B plane, coefficient): reference src/gemm.cu:479-518
+  const struct { int pa, pb; double re, im; } groups[4] = {
+      {1, 1, -alpha[0], -alpha[1]}, {0, 0, alpha[0], alpha[1]}, {1, 0, -alpha[1], alpha[0]}, {0, 1, -alpha[1], alpha[0]}};
+  h->profiler.start("int8tc_accumulate_fused", s);
+  for (int g = 0; g < 4; g++)
+    OZ_KERNEL_CHECK(ozk_gemm_i8_fused_complex(m, n, k, a_sl + groups[g].pa * a_plane, b_sl + groups[g].pb * b_plane,
+                                              w.pitch, amax + groups[g].pa * m, bmax + groups[g].pb * n, num_split, bits,
+                                              groups[g].re, groups[g].im, g == 0, beta[0], beta[1], c, ldc, s));
+  h->profiler.stop("int8tc_accumulate_fused", s);
+  mark_done(h, s);
+}
+
 template <class F>
 int guarded(F &&f) {
   try {
@@ -238,8 +294,8 @@ std::size_t mtk::ozimmu::reallocate_working_memory(handle_t h, const gemm_list_t
     if (H::is_int8_mode(mode)) s = H::num_split_of(mode);
     else if (mode == fp64_int8_auto) s = 18;
     if (s == 0) continue;
-    std::size_t bytes = H::workspace_layout(m, n, k, s).total;
-    if (kind == complx) bytes *= 2;
+    const std::size_t planes = kind == complx ? 2 : 1;
+    const std::size_t bytes = H::workspace_layout(planes * m, planes * n, k, s).total;
     need = std::max(need, bytes);
   }
   return reallocate_working_memory(h, need);
@@ -281,7 +337,7 @@ compute_mode_t mtk::ozimmu::auto_mode_select(handle_t h, const operation_t op_A,
                                              const void *const b_ptr, const std::size_t ldb,
                                              const element_kind_t element_kind,
                                              const double mantissa_loss_threshold) {
-  if (element_kind != real) throw std::runtime_error("ozIMMU: complex auto mode is not implemented");
+  const unsigned es = element_kind == real ? 1u : 2u;  // complex: both planes, each against its own row scale
   constexpr int N = handle::mantissa_loss_counter_length;
   for (int i = 0; i < N; i++) h->last_loss_counters[i] = 0;
   if (m == 0 || n == 0 || k == 0) return fp64_int8_3;
@@ -293,10 +349,12 @@ compute_mode_t mtk::ozimmu::auto_mode_select(handle_t h, const operation_t op_A,
   wait_previous(h, s);
   auto *scr = static_cast<std::uint32_t *>(h->working_memory_ptr);
   OZ_CUDA_CHECK(cudaMemsetAsync(h->d_mantissa_loss_counter_ptr, 0, sizeof(unsigned long long) * N, s));
-  OZ_KERNEL_CHECK(ozk_mantissa_loss(h->d_mantissa_loss_counter_ptr, scr, m, k, static_cast<const double *>(a_ptr),
-                                    lda, op_A == op_n, bits, s));
-  OZ_KERNEL_CHECK(ozk_mantissa_loss(h->d_mantissa_loss_counter_ptr, scr, n, k, static_cast<const double *>(b_ptr),
-                                    ldb, op_B != op_n, bits, s));
+  for (unsigned part = 0; part < es; part++) {
+    OZ_KERNEL_CHECK(ozk_mantissa_loss_strided(h->d_mantissa_loss_counter_ptr, scr, m, k,
+                                              static_cast<const double *>(a_ptr) + part, lda, op_A == op_n, bits, es, s));
+    OZ_KERNEL_CHECK(ozk_mantissa_loss_strided(h->d_mantissa_loss_counter_ptr, scr, n, k,
+                                              static_cast<const double *>(b_ptr) + part, ldb, op_B != op_n, bits, es, s));
+  }
   OZ_CUDA_CHECK(cudaMemcpyAsync(h->h_mantissa_loss_counter_ptr, h->d_mantissa_loss_counter_ptr,
                                 sizeof(unsigned long long) * N, cudaMemcpyDeviceToHost, s));
   mark_done(h, s);
@@ -326,7 +384,12 @@ int mtk::ozimmu::gemm(handle_t h, const operation_t op_A, const operation_t op_B
   if (arg_error) return 1;
 
   if (H::is_int8_mode(compute_mode)) {
-    if (element_kind != real) throw std::runtime_error("ozIMMU: the complex int8 path is not implemented");
+    if (element_kind != real) {
+      gemm_int8_complex(h, op_A, op_B, m, n, k, static_cast<const double *>(alpha), static_cast<const double *>(a_ptr),
+                        lda, static_cast<const double *>(b_ptr), ldb, static_cast<const double *>(beta),
+                        static_cast<double *>(c_ptr), ldc, H::num_split_of(compute_mode));
+      return 0;
+    }
     gemm_int8_real(h, op_A, op_B, m, n, k, *static_cast<const double *>(alpha), static_cast<const double *>(a_ptr),
                    lda, static_cast<const double *>(b_ptr), ldb, *static_cast<const double *>(beta),
                    static_cast<double *>(c_ptr), ldc, H::num_split_of(compute_mode));

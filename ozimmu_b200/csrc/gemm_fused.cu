@@ -59,6 +59,11 @@ struct FusedParams {
   const double *amax;
   const double *bmax;
   int32_t *c_i32;
+  // complex accumulation (reference src/gemm.cu:160-239,479-518): C is cuDoubleComplex (ldc in complex
+  // elements) and this launch adds one of the four real products: y = fma(x, (alpha, alpha_im), y),
+  // after y = beta * y (the reference's init_c_complex, applied once, by the first of the four launches)
+  uint32_t cplx, cplx_init;
+  double alpha_im, beta_im;
   // pair kernel tuning (see launch_pair): L2 prefetch lead in k-blocks; soft lockstep between CTA pairs
   uint32_t prefetch_ahead;
   uint32_t *sync_ctr;          // one arrival counter per kSyncEvery k-steps, zeroed before launch (or null)
@@ -371,14 +376,18 @@ struct KCursor {
 
 template <uint32_t BN_>
 struct PairCfg {
-  static constexpr uint32_t kBN = BN_;
   static constexpr uint32_t kStageBytes = (BM + BN_ / 2) * BK;       // per CTA
-  static constexpr uint32_t kStages = (BN_ == 128) ? 8 : 7;
+  static constexpr uint32_t kStages = (BN_ == 128) ? 8 : (BN_ == 192 ? 7 : 5);
   static constexpr uint32_t kAccBufs = (BN_ == 128) ? 4 : 2;
   static constexpr uint32_t kBufStride = (BN_ == 128) ? 128 : 256;   // TMEM columns between buffers
-  static constexpr uint32_t kBarBytes = 8 * (2 * kStages + 2 * kAccBufs) + 16;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
   static constexpr uint32_t kColsPerThread = BN_ / 2;                // epilogue: 2 column halves
+  // FP64 accumulators: up to 96 columns per thread in registers (192 registers); a wider tile keeps
+  // the rest in shared memory ([column][row] doubles, conflict-free for lane <-> row)
+  static constexpr uint32_t kRegCols = kColsPerThread < 96 ? kColsPerThread : 96;
+  static constexpr uint32_t kSpillCols = kColsPerThread - kRegCols;
+  static constexpr uint32_t kSpillBytes = 2 * kSpillCols * BM * 8;
+  static constexpr uint32_t kBarBytes = 8 * (2 * kStages + 2 * kAccBufs) + 16;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kSpillBytes + kBarBytes + 1024;
   static constexpr uint32_t kRegsOther = (BN_ == 128) ? 56 : 40;
   static constexpr uint32_t kRegsEpi = (BN_ == 128) ? 224 : 232;
 };
@@ -390,9 +399,11 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   using Cfg = PairCfg<BN_>;
   constexpr uint32_t CSZ = 2 * PM * PN;  // CTAs per cluster: PM x PN CTA pairs
   constexpr uint32_t kStagesP = Cfg::kStages, kBufs = Cfg::kAccBufs, kCols = Cfg::kColsPerThread;
+  constexpr uint32_t kRegCols = Cfg::kRegCols, kSpillCols = Cfg::kSpillCols;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStagesP * Cfg::kStageBytes;
+  const uint32_t spill_base = smem_base + kStagesP * Cfg::kStageBytes;
+  const uint32_t bar_base = spill_base + Cfg::kSpillBytes;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (kStagesP + s); };
   auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * kStagesP + b); };
@@ -554,9 +565,13 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       super_tile_coords(p, t, tm, tn);
       const uint32_t row = (tm * PM + pm) * 2 * BM + rank * BM + q * 32u + lane;
       const uint32_t col0 = (tn * PN + pn) * BN_ + half * kCols;
-      double acc[kCols];
+      double acc[kRegCols];
 #pragma unroll
-      for (uint32_t j = 0; j < kCols; j++) acc[j] = 0.0;
+      for (uint32_t j = 0; j < kRegCols; j++) acc[j] = 0.0;
+      // this thread's spill accumulators: columns [half*kSpillCols, +kSpillCols) of the [col][row] array
+      double *spill = reinterpret_cast<double *>(smem_raw + (spill_base - ptx::smem_u32(smem_raw))) +
+                      static_cast<size_t>(half * kSpillCols) * BM + (q * 32u + lane);
+      bool first = true;
       for (PairIter it(p); it.valid(); it.next(), pc++) {
         const uint32_t buf = pc % kBufs, bph = (pc / kBufs) & 1u;
         ptx::mbar_wait(tfull_bar(buf), bph);
@@ -579,9 +594,17 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               for (uint32_t j = 0; j < 8; j++)
                 d[j] = __dadd_rn(__hiloint2double(0x43300000, static_cast<int>(v[g + j] ^ 0x80000000u)),
                                  -4503601774854144.0);
+              if (c * 16 < kRegCols) {
 #pragma unroll
-              for (uint32_t j = 0; j < 8; j++)
-                acc[c * 16 + g + j] = __fma_rn(d[j], scale, acc[c * 16 + g + j]);
+                for (uint32_t j = 0; j < 8; j++)
+                  acc[(c * 16 + g + j) % kRegCols] = __fma_rn(d[j], scale, acc[(c * 16 + g + j) % kRegCols]);
+              } else {
+#pragma unroll
+                for (uint32_t j = 0; j < 8; j++) {
+                  double *sp = spill + static_cast<size_t>(c * 16 + g + j - kRegCols) * BM;
+                  *sp = __fma_rn(d[j], scale, first ? 0.0 : *sp);
+                }
+              }
             }
           } else if (row < p.m) {
 #pragma unroll
@@ -591,6 +614,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
         }
+        first = false;
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -606,14 +630,36 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (uint32_t j = 0; j < kCols; j++) {
           const uint32_t col = col0 + j;
           if (col < p.n) {
-            double x = __dmul_rn(acc[j], 0x1p-44);
+            const double a_j = (j < kRegCols) ? acc[j % kRegCols] : spill[static_cast<size_t>(j - kRegCols) * BM];
+            double x = __dmul_rn(a_j, 0x1p-44);
             x = __dmul_rn(x, am);
             x = __dmul_rn(x, __ldg(p.bmax + col));
-            double *dst = crow + static_cast<size_t>(col) * p.ldc;
-            if (p.beta != 0) {
-              *dst = __fma_rn(p.alpha, x, __dmul_rn(p.beta, *dst));
+            if (p.cplx) {
+              double2 *dst = reinterpret_cast<double2 *>(p.c) + static_cast<size_t>(col) * p.ldc + row;
+              double2 y = make_double2(0.0, 0.0);
+              if (p.cplx_init) {
+                if (p.beta != 0 || p.beta_im != 0) {
+                  // init_c_complex_kernel<false> as compiled (reference src/gemm.cu:214-222, incl. its use
+                  // of the already-updated real part): t = y.y*b.y; y.x = fma(y.x, b.x, -t);
+                  // t = y.x*b.y; y.y = fma(y.y, b.x, t)
+                  y = *dst;
+                  const double yx = __fma_rn(y.x, p.beta, -__dmul_rn(y.y, p.beta_im));
+                  y.y = __fma_rn(y.y, p.beta, __dmul_rn(yx, p.beta_im));
+                  y.x = yx;
+                }
+              } else {
+                y = *dst;
+              }
+              y.x = __fma_rn(x, p.alpha, y.x);      // axy_complex_kernel (reference src/gemm.cu:160-186)
+              y.y = __fma_rn(x, p.alpha_im, y.y);
+              *dst = y;
             } else {
-              *dst = __dmul_rn(p.alpha, x);
+              double *dst = crow + static_cast<size_t>(col) * p.ldc;
+              if (p.beta != 0) {
+                *dst = __fma_rn(p.alpha, x, __dmul_rn(p.beta, *dst));
+              } else {
+                *dst = __dmul_rn(p.alpha, x);
+              }
             }
           }
         }
@@ -669,7 +715,7 @@ int make_slice_tmap(CUtensorMap *map, const int8_t *base, size_t rows, size_t pi
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(cudaErrorInvalidValue);
 }
 
-// 0 = default (CTA-pair kernel, BN=192); 128/192 = CTA-pair kernel with that BN; CM*10+CN = the
+// 0 = default (CTA-pair kernel, BN chosen per problem); 128/192/256 = CTA-pair kernel with that BN; CM*10+CN = the
 // single-CTA kernel with a CM x CN multicast cluster (test/tuning hook, see ozk_set_cluster_shape)
 int g_cluster_override = 0;
 
@@ -844,10 +890,29 @@ int launch_pair(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_s
 int dispatch_fused(const FusedParams &p, const int8_t *a_slices, const int8_t *b_slices, size_t pitch,
                    cudaStream_t stream) {
   int shape = g_cluster_override;
-  if (shape == 0) shape = 192;
+  if (p.cplx && shape != 128 && shape != 192 && shape != 256) shape = 0;  // complex epilogue: CTA-pair kernel only
+  if (shape == 0) {
+    // The kernel is bound by L2->SM delivery, so a launch costs about
+    // rounds x bytes-per-k-block-per-SM = ceil(tiles / resident pairs) x (128 + BN/2).  BN=256 delivers
+    // the fewest bytes per MAC; narrower tiles win when they fill more SMs or avoid a ragged last round.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t pairs = static_cast<uint64_t>(sms > 1 ? sms / 2 : 1);
+    uint64_t best_cost = ~0ull;
+    for (int bn : {256, 192, 128}) {
+      const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 2 * BM)) * ceil_div_u32(p.n, bn);
+      const uint64_t cost = ((tiles + pairs - 1) / pairs) * (128 + bn / 2);
+      if (cost < best_cost) {
+        best_cost = cost;
+        shape = bn;
+      }
+    }
+  }
   switch (shape) {
     case 192: return launch_pair<192, 1, 1>(p, a_slices, b_slices, pitch, stream);
     case 128: return launch_pair<128, 1, 1>(p, a_slices, b_slices, pitch, stream);
+    case 256: return launch_pair<256, 1, 1>(p, a_slices, b_slices, pitch, stream);
     case 1120: return launch_pair<192, 2, 1>(p, a_slices, b_slices, pitch, stream);
     case 1210: return launch_pair<192, 1, 2>(p, a_slices, b_slices, pitch, stream);
     case 1220: return launch_pair<192, 2, 2>(p, a_slices, b_slices, pitch, stream);
@@ -869,7 +934,7 @@ bool valid_common(size_t m, size_t n, size_t k, size_t pitch, unsigned num_split
 
 // Test/tuning hook: force the cluster shape of the fused kernel (0 = default heuristic).
 extern "C" int ozk_set_cluster_shape(int cm, int cn) {
-  if (cm == 0 && (cn == 128 || cn == 192)) oz::g_cluster_override = cn;  // CTA-pair kernel, BN = cn
+  if (cm == 0 && (cn == 128 || cn == 192 || cn == 256)) oz::g_cluster_override = cn;  // CTA-pair kernel, BN = cn
   else if (cm == 100 && (cn == 21 || cn == 12 || cn == 22))              // BN=192, PM x PN pairs multicast
     oz::g_cluster_override = 1000 + cn * 10;
   else oz::g_cluster_override = (cm <= 0 || cn <= 0) ? 0 : cm * 10 + cn;
@@ -892,6 +957,33 @@ extern "C" int ozk_gemm_i8_fused(size_t m, size_t n, size_t k, const int8_t *a_s
   p.alpha = alpha;
   p.beta = beta;
   p.c = c;
+  p.ldc = ldc;
+  p.amax = amax;
+  p.bmax = bmax;
+  return oz::dispatch_fused(p, a_slices, b_slices, pitch, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ozk_gemm_i8_fused_complex(size_t m, size_t n, size_t k, const int8_t *a_slices,
+                                         const int8_t *b_slices, size_t pitch, const double *amax,
+                                         const double *bmax, unsigned num_split, unsigned bits_per_int8,
+                                         double coef_re, double coef_im, int apply_beta, double beta_re,
+                                         double beta_im, void *c, size_t ldc, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m)
+    return static_cast<int>(cudaErrorInvalidValue);
+  oz::FusedParams p{};
+  p.m = static_cast<uint32_t>(m);
+  p.n = static_cast<uint32_t>(n);
+  p.k_blocks = oz::ceil_div_u32(static_cast<uint32_t>(pitch), oz::BK);
+  p.num_split = num_split;
+  p.bits = static_cast<int32_t>(bits_per_int8);
+  p.alpha = coef_re;
+  p.alpha_im = coef_im;
+  p.beta = beta_re;
+  p.beta_im = beta_im;
+  p.cplx = 1;
+  p.cplx_init = apply_beta ? 1u : 0u;
+  p.c = static_cast<double *>(c);
   p.ldc = ldc;
   p.amax = amax;
   p.bmax = bmax;

@@ -10,8 +10,9 @@
 // CUBLAS_STATUS_INTERNAL_ERROR, the global handle is created on first use (no null deref when
 // the application's cublasCreate ran before this library was loaded), and device-pointer-mode
 // scalars fall through to the real cuBLAS instead of being dereferenced on the host.
-// Complex (CUDA_C_64F) GEMMs are passed through: the complex Ozaki path is a later row of the
-// scope table.
+// Complex (CUDA_C_64F) GEMMs take the complex Ozaki path (reference src/gemm.cu:412-521) unless an
+// operand is CUBLAS_OP_C: the reference silently treats OP_C as OP_T (src/cublas.cu:50-56), which
+// is wrong for complex data, so those calls go to the real cuBLAS instead.
 #include <cstring>
 #include <mutex>
 
@@ -88,8 +89,8 @@ bool should_intercept(handle_t h, compute_mode_t mode, int m, int n, int k, cuda
   return mode != dgemm && mode != sgemm && m >= 0 && n >= 0 && k >= 0 &&
          static_cast<std::uint32_t>(m) >= h->intercept_threshold_m &&
          static_cast<std::uint32_t>(n) >= h->intercept_threshold_n &&
-         static_cast<std::uint32_t>(k) >= h->intercept_threshold_k && a == CUDA_R_64F && b == CUDA_R_64F &&
-         c == CUDA_R_64F;
+         static_cast<std::uint32_t>(k) >= h->intercept_threshold_k &&
+         ((a == CUDA_R_64F && b == CUDA_R_64F && c == CUDA_R_64F) || (a == CUDA_C_64F && b == CUDA_C_64F && c == CUDA_C_64F));
 }
 
 // reference src/culip.cu:14-50: one "[CULiP Result][name] ns" line per intercepted call
@@ -114,25 +115,33 @@ struct CulipScope {
 
 const char *op_str(cublasOperation_t op) { return op == CUBLAS_OP_N ? "N" : (op == CUBLAS_OP_T ? "T" : "C"); }
 
-cublasStatus_t ozaki_dgemm(cublasHandle_t handle, compute_mode_t mode, cublasOperation_t ta, cublasOperation_t tb, int m,
-                           int n, int k, const double *alpha, const double *A, int lda, const double *B, int ldb,
-                           const double *beta, double *C, int ldc) {
+cublasStatus_t ozaki_gemm(cublasHandle_t handle, compute_mode_t mode, cublasOperation_t ta, cublasOperation_t tb, int m,
+                          int n, int k, const void *alpha, const void *A, int lda, const void *B, int ldb,
+                          const void *beta, void *C, int ldc, element_kind_t kind) {
   std::lock_guard<std::mutex> lock(g_mu);
   try {
     handle_t h = global_handle();
     cudaStream_t s = stream_of(handle);
     set_cuda_stream(h, s);
-    CulipScope scope(s, std::string("D") + get_compute_mode_name_str(mode) + "-" + op_str(ta) + op_str(tb) + "-m" +
+    CulipScope scope(s, std::string(kind == mtk::ozimmu::real ? "D" : "Z") + get_compute_mode_name_str(mode) + "-" + op_str(ta) + op_str(tb) + "-m" +
                             std::to_string(m) + "-n" + std::to_string(n) + "-k" + std::to_string(k));
     // reference src/cublas.cu:50-56: everything that is not OP_N is treated as OP_T (real data)
     const int err = gemm(h, ta == CUBLAS_OP_N ? op_n : op_t, tb == CUBLAS_OP_N ? op_n : op_t, m, n, k, alpha, A, lda, B,
-                         ldb, beta, C, ldc, mode, real);
+                         ldb, beta, C, ldc, mode, kind);
     return err ? CUBLAS_STATUS_INVALID_VALUE : CUBLAS_STATUS_SUCCESS;
   } catch (const std::exception &e) {
     H::log_error(e.what());
     return CUBLAS_STATUS_INTERNAL_ERROR;
   }
 }
+
+cublasStatus_t ozaki_dgemm(cublasHandle_t handle, compute_mode_t mode, cublasOperation_t ta, cublasOperation_t tb, int m,
+                           int n, int k, const double *alpha, const double *A, int lda, const double *B, int ldb,
+                           const double *beta, double *C, int ldc) {
+  return ozaki_gemm(handle, mode, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mtk::ozimmu::real);
+}
+
+bool no_conj(cublasOperation_t ta, cublasOperation_t tb) { return ta != CUBLAS_OP_C && tb != CUBLAS_OP_C; }
 
 }  // namespace
 
@@ -169,7 +178,9 @@ cublasStatus_t cublasGemmEx(cublasHandle_t handle, cublasOperation_t transa, cub
                             cudaDataType_t Btype, int ldb, const void *beta, void *C, cudaDataType_t Ctype, int ldc,
                             cublasComputeType_t computeType, cublasGemmAlgo_t algo) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm && mode != sgemm && Atype == CUDA_R_64F && Btype == CUDA_R_64F && Ctype == CUDA_R_64F) {
+  const bool is_real = Atype == CUDA_R_64F && Btype == CUDA_R_64F && Ctype == CUDA_R_64F;
+  const bool is_cplx = Atype == CUDA_C_64F && Btype == CUDA_C_64F && Ctype == CUDA_C_64F && no_conj(transa, transb);
+  if (mode != dgemm && mode != sgemm && (is_real || is_cplx)) {
     bool take = false;
     {
       std::lock_guard<std::mutex> lock(g_mu);
@@ -180,9 +191,8 @@ cublasStatus_t cublasGemmEx(cublasHandle_t handle, cublasOperation_t transa, cub
       }
     }
     if (take)
-      return ozaki_dgemm(handle, mode, transa, transb, m, n, k, static_cast<const double *>(alpha),
-                         static_cast<const double *>(A), lda, static_cast<const double *>(B), ldb,
-                         static_cast<const double *>(beta), static_cast<double *>(C), ldc);
+      return ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
+                        is_real ? mtk::ozimmu::real : complx);
   }
   auto fn = real_fn<GemmExFn>("cublasGemmEx");
   if (fn == nullptr) return CUBLAS_STATUS_NOT_INITIALIZED;
@@ -217,11 +227,25 @@ cublasStatus_t cublasDgemm_v2(cublasHandle_t handle, cublasOperation_t transa, c
   return fn(handle, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
-// reference src/cublas.cu:297-313 -- complex path: passthrough
+// reference src/cublas.cu:297-313
 cublasStatus_t cublasZgemm_v2(cublasHandle_t handle, cublasOperation_t transa, cublasOperation_t transb, int m, int n,
                               int k, const cuDoubleComplex *alpha, const cuDoubleComplex *A, int lda,
                               const cuDoubleComplex *B, int ldb, const cuDoubleComplex *beta, cuDoubleComplex *C,
                               int ldc) {
+  const compute_mode_t mode = env_compute_mode();
+  if (mode != dgemm && mode != sgemm && no_conj(transa, transb)) {
+    bool take = false;
+    {
+      std::lock_guard<std::mutex> lock(g_mu);
+      try {
+        take = should_intercept(global_handle(), mode, m, n, k, CUDA_C_64F, CUDA_C_64F, CUDA_C_64F) &&
+               host_pointer_mode(handle);
+      } catch (const std::exception &e) {
+        H::log_error(e.what());
+      }
+    }
+    if (take) return ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, complx);
+  }
   auto fn = real_fn<cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int,
                                     const cuDoubleComplex *, const cuDoubleComplex *, int, const cuDoubleComplex *, int,
                                     const cuDoubleComplex *, cuDoubleComplex *, int)>("cublasZgemm_v2");

@@ -100,15 +100,17 @@ template <int S, bool CACHED>
 __global__ void __launch_bounds__(kSplitThreads)
 split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
                   const size_t rows, const uint32_t len, const double *__restrict__ in,
-                  const size_t ld, const unsigned L) {
+                  const size_t ld, const unsigned L, const uint32_t es) {
+  // es: distance between consecutive elements in doubles (1 = real matrix, 2 = one plane of an
+  // interleaved complex matrix; `in` then points at the plane's first double, ld counts complex elements)
   extern __shared__ double s_row[];
   __shared__ uint32_t s_red[kSplitThreads / 32];
   const size_t row = blockIdx.x;
-  const double *__restrict__ src = in + row * ld;
+  const double *__restrict__ src = in + row * ld * es;
 
   uint32_t e = 0;
   for (uint32_t i = threadIdx.x; i < len; i += kSplitThreads) {
-    const double x = __ldg(src + i);
+    const double x = __ldg(src + static_cast<size_t>(i) * es);
     if (CACHED) s_row[swz(i)] = x;
     e = max(e, exp_field(x));
   }
@@ -128,7 +130,7 @@ split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
       if (CACHED) {
         v[j] = (i < len) ? s_row[(g * 16) | ((j ^ g) & 15u)] : 0.0;
       } else {
-        v[j] = (i < len) ? __ldg(src + i) : 0.0;
+        v[j] = (i < len) ? __ldg(src + static_cast<size_t>(i) * es) : 0.0;
       }
     }
     uint32_t w[S][4];
@@ -149,14 +151,14 @@ constexpr int kColChunk = 64;  // columns per CTA in the row-max pass
 
 __global__ void __launch_bounds__(256)
 rowmax_cols_kernel(uint32_t *__restrict__ emax, const size_t rows, const uint32_t len,
-                   const double *__restrict__ in, const size_t ld) {
+                   const double *__restrict__ in, const size_t ld, const uint32_t es) {
   const size_t r = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
   if (r >= rows) return;
   const uint32_t c0 = blockIdx.y * kColChunk;
   const uint32_t c1 = min(len, c0 + kColChunk);
   uint32_t e = 0;
 #pragma unroll 8
-  for (uint32_t c = c0; c < c1; c++) e = max(e, exp_field(__ldg(in + static_cast<size_t>(c) * ld + r)));
+  for (uint32_t c = c0; c < c1; c++) e = max(e, exp_field(__ldg(in + (static_cast<size_t>(c) * ld + r) * es)));
   atomicMax(emax + r, e);
 }
 
@@ -164,7 +166,7 @@ template <int S>
 __global__ void __launch_bounds__(256)
 split_cols_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
                   const uint32_t *__restrict__ emax, const size_t rows, const uint32_t len,
-                  const double *__restrict__ in, const size_t ld, const unsigned L) {
+                  const double *__restrict__ in, const size_t ld, const unsigned L, const uint32_t es) {
   const size_t r = static_cast<size_t>(blockIdx.x) * 64 + (threadIdx.x & 63);
   const uint32_t cbase = blockIdx.y * 64 + (threadIdx.x >> 6) * 16;
   if (r >= rows || cbase >= pitch) return;
@@ -176,7 +178,7 @@ split_cols_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
 #pragma unroll
   for (int j = 0; j < 16; j++) {
     const uint32_t c = cbase + j;
-    v[j] = (c < len) ? __ldg(in + static_cast<size_t>(c) * ld + r) : 0.0;
+    v[j] = (c < len) ? __ldg(in + (static_cast<size_t>(c) * ld + r) * es) : 0.0;
   }
   uint32_t w[S][4];
   cut16<S>(v, mx_bits, L, w);
@@ -222,11 +224,12 @@ __device__ __forceinline__ void loss_block_reduce(uint32_t (&cnt)[16], unsigned 
 
 __global__ void __launch_bounds__(kSplitThreads)
 loss_rows_kernel(unsigned long long *__restrict__ counters, const uint32_t len,
-                 const double *__restrict__ in, const size_t ld, const unsigned L) {
+                 const double *__restrict__ in, const size_t ld, const unsigned L, const uint32_t es) {
   __shared__ uint32_t s_red[kSplitThreads / 32];
-  const double *__restrict__ src = in + static_cast<size_t>(blockIdx.x) * ld;
+  const double *__restrict__ src = in + static_cast<size_t>(blockIdx.x) * ld * es;
   uint32_t e = 0;
-  for (uint32_t i = threadIdx.x; i < len; i += kSplitThreads) e = max(e, exp_field(__ldg(src + i)));
+  for (uint32_t i = threadIdx.x; i < len; i += kSplitThreads)
+    e = max(e, exp_field(__ldg(src + static_cast<size_t>(i) * es)));
   e = block_max_u32(e, s_red);
   const double mx = max_exp_from_field(e);
   const uint64_t mx_exp_bits = static_cast<uint64_t>(__double_as_longlong(mx)) & kExpMask;
@@ -234,14 +237,14 @@ loss_rows_kernel(unsigned long long *__restrict__ counters, const uint32_t len,
 #pragma unroll
   for (int s = 0; s < 16; s++) cnt[s] = 0;
   for (uint32_t i = threadIdx.x; i < len; i += kSplitThreads)
-    loss_accumulate(cnt, __ldg(src + i), mx_exp_bits, mx == 0, L);
+    loss_accumulate(cnt, __ldg(src + static_cast<size_t>(i) * es), mx_exp_bits, mx == 0, L);
   loss_block_reduce(cnt, counters);
 }
 
 __global__ void __launch_bounds__(256)
 loss_cols_kernel(unsigned long long *__restrict__ counters, const uint32_t *__restrict__ emax,
                  const size_t rows, const uint32_t len, const double *__restrict__ in,
-                 const size_t ld, const unsigned L) {
+                 const size_t ld, const unsigned L, const uint32_t es) {
   const size_t r = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
   uint32_t cnt[16];
 #pragma unroll
@@ -253,22 +256,22 @@ loss_cols_kernel(unsigned long long *__restrict__ counters, const uint32_t *__re
     const uint32_t c1 = min(len, c0 + kColChunk);
 #pragma unroll 4
     for (uint32_t c = c0; c < c1; c++)
-      loss_accumulate(cnt, __ldg(in + static_cast<size_t>(c) * ld + r), mx_exp_bits, mx == 0, L);
+      loss_accumulate(cnt, __ldg(in + (static_cast<size_t>(c) * ld + r) * es), mx_exp_bits, mx == 0, L);
   }
   loss_block_reduce(cnt, counters);
 }
 
 template <int S>
 int launch_split(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, size_t rows,
-                 size_t len, const double *in, size_t ld, int col_major, unsigned L,
+                 size_t len, const double *in, size_t ld, int col_major, unsigned L, uint32_t es,
                  cudaStream_t stream) {
   if (col_major) {
     OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), stream));
     dim3 g1(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk));
-    rowmax_cols_kernel<<<g1, 256, 0, stream>>>(scratch, rows, static_cast<uint32_t>(len), in, ld);
+    rowmax_cols_kernel<<<g1, 256, 0, stream>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es);
     dim3 g2(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((pitch + 63) / 64));
     split_cols_kernel<S><<<g2, 256, 0, stream>>>(out, pitch, max_exp, scratch, rows,
-                                                 static_cast<uint32_t>(len), in, ld, L);
+                                                 static_cast<uint32_t>(len), in, ld, L, es);
     count_launch(2);
   } else {
     if (len <= static_cast<size_t>(kMaxCachedLen)) {
@@ -279,10 +282,10 @@ int launch_split(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, 
                                          static_cast<int>(smem)));
       }
       split_rows_kernel<S, true><<<static_cast<unsigned>(rows), kSplitThreads, smem, stream>>>(
-          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L);
+          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es);
     } else {
       split_rows_kernel<S, false><<<static_cast<unsigned>(rows), kSplitThreads, 0, stream>>>(
-          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L);
+          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es);
     }
     count_launch(1);
   }
@@ -303,18 +306,19 @@ extern "C" uint32_t ozk_bits_per_int8(uint32_t k) {
 
 extern "C" size_t ozk_slice_pitch(size_t k) { return oz::slice_pitch(k); }
 
-extern "C" int ozk_split_int8(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch,
-                              size_t rows, size_t len, const double *in, size_t ld, int col_major,
-                              unsigned num_split, unsigned bits_per_int8, void *stream) {
+extern "C" int ozk_split_int8_strided(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch,
+                                      size_t rows, size_t len, const double *in, size_t ld, int col_major,
+                                      unsigned num_split, unsigned bits_per_int8, unsigned elem_stride,
+                                      void *stream) {
   if (rows == 0 || len == 0) return 0;
-  if (pitch % 16 != 0 || pitch < len || bits_per_int8 == 0 || bits_per_int8 > 7 ||
-      len > 0xFFFFFFF0ull || rows > 0x7FFFFFFFull || (col_major && scratch == nullptr))
+  if (pitch % 16 != 0 || pitch < len || bits_per_int8 == 0 || bits_per_int8 > 7 || elem_stride < 1 ||
+      elem_stride > 2 || len > 0xFFFFFFF0ull || rows > 0x7FFFFFFFull || (col_major && scratch == nullptr))
     return static_cast<int>(cudaErrorInvalidValue);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define OZ_SPLIT_CASE(S)                                                                       \
   case S:                                                                                      \
     return oz::launch_split<S>(out, pitch, max_exp, scratch, rows, len, in, ld, col_major,     \
-                               bits_per_int8, s);
+                               bits_per_int8, elem_stride, s);
   switch (num_split) {
     OZ_SPLIT_CASE(3) OZ_SPLIT_CASE(4) OZ_SPLIT_CASE(5) OZ_SPLIT_CASE(6) OZ_SPLIT_CASE(7)
     OZ_SPLIT_CASE(8) OZ_SPLIT_CASE(9) OZ_SPLIT_CASE(10) OZ_SPLIT_CASE(11) OZ_SPLIT_CASE(12)
@@ -326,25 +330,40 @@ extern "C" int ozk_split_int8(int8_t *out, size_t pitch, double *max_exp, uint32
 #undef OZ_SPLIT_CASE
 }
 
-extern "C" int ozk_mantissa_loss(unsigned long long *counters16, uint32_t *scratch, size_t rows,
-                                 size_t len, const double *in, size_t ld, int col_major,
-                                 unsigned bits_per_int8, void *stream) {
+extern "C" int ozk_split_int8(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch,
+                              size_t rows, size_t len, const double *in, size_t ld, int col_major,
+                              unsigned num_split, unsigned bits_per_int8, void *stream) {
+  return ozk_split_int8_strided(out, pitch, max_exp, scratch, rows, len, in, ld, col_major, num_split,
+                                bits_per_int8, 1, stream);
+}
+
+extern "C" int ozk_mantissa_loss_strided(unsigned long long *counters16, uint32_t *scratch, size_t rows,
+                                         size_t len, const double *in, size_t ld, int col_major,
+                                         unsigned bits_per_int8, unsigned elem_stride, void *stream) {
   if (rows == 0 || len == 0) return 0;
-  if (len > 0xFFFFFFF0ull || rows > 0x7FFFFFFFull || (col_major && scratch == nullptr))
+  if (len > 0xFFFFFFF0ull || rows > 0x7FFFFFFFull || (col_major && scratch == nullptr) || elem_stride < 1 ||
+      elem_stride > 2)
     return static_cast<int>(cudaErrorInvalidValue);
+  const uint32_t es = elem_stride;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   using namespace oz;
   if (col_major) {
     OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), s));
     dim3 g(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk));
-    rowmax_cols_kernel<<<g, 256, 0, s>>>(scratch, rows, static_cast<uint32_t>(len), in, ld);
+    rowmax_cols_kernel<<<g, 256, 0, s>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es);
     loss_cols_kernel<<<g, 256, 0, s>>>(counters16, scratch, rows, static_cast<uint32_t>(len), in, ld,
-                                       bits_per_int8);
+                                       bits_per_int8, es);
     count_launch(2);
   } else {
     loss_rows_kernel<<<static_cast<unsigned>(rows), kSplitThreads, 0, s>>>(
-        counters16, static_cast<uint32_t>(len), in, ld, bits_per_int8);
+        counters16, static_cast<uint32_t>(len), in, ld, bits_per_int8, es);
     count_launch(1);
   }
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ozk_mantissa_loss(unsigned long long *counters16, uint32_t *scratch, size_t rows,
+                                 size_t len, const double *in, size_t ld, int col_major,
+                                 unsigned bits_per_int8, void *stream) {
+  return ozk_mantissa_loss_strided(counters16, scratch, rows, len, in, ld, col_major, bits_per_int8, 1, stream);
 }

@@ -33,6 +33,13 @@ GEMM_CASES = [
 # auto mode: no exact zeros and k % 32 == 0, the only regime where the reference's counters are
 # reliable; only the first 8 counters exist in the reference (App. B.1)
 AUTO_CASES = [(0, 0, 32, 32, 64, 0.0), (1, 0, 32, 48, 96, 1.0), (0, 1, 64, 32, 32, 2.0), (1, 1, 32, 32, 128, 4.0)]
+# complex (zgemm) cases: (op_a, op_b, m, n, k, num_split, kind, alpha, beta)
+ZGEMM_CASES = [
+    (0, 0, 16, 12, 40, 9, "normal01", 1.0 + 0.0j, 0.0 + 0.0j),
+    (1, 0, 12, 9, 33, 13, "exp_rand-1", -0.5 + 1.25j, 0.75 - 0.5j),
+    (0, 1, 8, 15, 64, 4, "urand01", 2.0 - 1.0j, 0.0 + 1.0j),
+    (1, 1, 20, 7, 50, 18, "mixed", 0.0 + 1.0j, 1.0 + 0.0j),
+]
 AUTO_THRESHOLDS = [0.0, 0.5, 1.0, 1.5, 2.0, 4.0, 8.0, 30.0]
 
 
@@ -81,6 +88,19 @@ def main(out_dir: str) -> None:
                             thresholds=np.array(AUTO_THRESHOLDS), modes=np.array(modes),
                             counters8=np.array(counters, dtype=np.uint64))
         print("auto case", idx, "ok", modes)
+    for idx, (op_a, op_b, m, n, k, s, kind, alpha, beta) in enumerate(ZGEMM_CASES):
+        lda, ca = stored(op_a, m, k, 0)
+        ldb, cb = stored(op_b, k, n, 0)
+        a = oracle_lib.gen_complex(kind, lda * ca, 6000 + idx)
+        b = oracle_lib.gen_complex(kind, ldb * cb, 7000 + idx)
+        c = oracle_lib.gen_complex("normal01", m * n, 8000 + idx)
+        da, db, dc = to_dev(a), to_dev(b), to_dev(c)
+        ref.gemm_complex(op_a, op_b, m, n, k, alpha, da, lda, db, ldb, beta, dc, m, s - 1)
+        torch.cuda.synchronize()
+        np.savez_compressed(out / f"zgemm_{idx}.npz", op_a=op_a, op_b=op_b, m=m, n=n, k=k, num_split=s,
+                            alpha=np.complex128(alpha), beta=np.complex128(beta), lda=lda, ldb=ldb, ldc=m, a=a, b=b,
+                            c_in=c, c_out=dc.cpu().numpy(), kind=kind)
+        print("zgemm case", idx, "ok")
     ref.close()
 
 

@@ -70,6 +70,14 @@ class Reference:
                                ldb, C.addressof(be), c.data_ptr(), ldc, int(mode), 0)
         assert rc == 0, f"ozref_gemm -> {rc}"
 
+    def gemm_complex(self, op_a, op_b, m, n, k, alpha: complex, a, lda, b, ldb, beta: complex, c, ldc, mode):
+        al = (C.c_double * 2)(alpha.real, alpha.imag)
+        be = (C.c_double * 2)(beta.real, beta.imag)
+        self.L.ozref_set_stream(self.h, stream_ptr())
+        rc = self.L.ozref_gemm(self.h, int(op_a), int(op_b), m, n, k, C.addressof(al), a.data_ptr(), lda, b.data_ptr(),
+                               ldb, C.addressof(be), c.data_ptr(), ldc, int(mode), 1)
+        assert rc == 0, f"ozref_gemm (complex) -> {rc}"
+
     def split(self, x: torch.Tensor, ld: int, m: int, n: int, op: int, matrix: int, num_split: int, bits_: int):
         """reference split_int8<double>: rows = m (matrix A) / n (matrix B after the swap)."""
         length = n if matrix == 0 else m

@@ -41,6 +41,10 @@ def oracle() -> C.CDLL:
         L.oz_gemm.restype, L.oz_gemm.argtypes = i32, [i32, i32, sz, sz, sz, dbl, vp, sz, vp, sz, dbl, vp, sz, u32,
                                                       vp, vp, vp, vp]
         L.oz_mantissa_loss.restype, L.oz_mantissa_loss.argtypes = None, [vp, sz, sz, vp, sz, i32, u32]
+        L.oz_gemm_complex.restype, L.oz_gemm_complex.argtypes = i32, [i32, i32, sz, sz, sz, vp, vp, sz, vp, sz, vp, vp,
+                                                                      sz, u32]
+        L.oz_auto_select_complex.restype = i32
+        L.oz_auto_select_complex.argtypes = [i32, i32, sz, sz, sz, vp, sz, vp, sz, dbl, vp]
         L.oz_auto_select.restype, L.oz_auto_select.argtypes = i32, [i32, i32, sz, sz, sz, vp, sz, vp, sz, dbl, vp]
         _oracle = L
     return _oracle
@@ -96,6 +100,24 @@ def oracle_gemm(op_a: int, op_b: int, m: int, n: int, k: int, alpha: float, a: n
                    None, None)
     assert rc == 0
     return out
+
+
+def oracle_gemm_complex(op_a: int, op_b: int, m: int, n: int, k: int, alpha: complex, a: np.ndarray, lda: int,
+                        b: np.ndarray, ldb: int, beta: complex, c: np.ndarray, ldc: int, num_split: int) -> np.ndarray:
+    """a, b, c: complex128 flat column-major storage (ld in complex elements); returns the new C"""
+    L = oracle()
+    a = np.ascontiguousarray(a, dtype=np.complex128)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    out = np.array(c, dtype=np.complex128, copy=True)
+    al = np.array([alpha.real, alpha.imag], dtype=np.float64)
+    be = np.array([beta.real, beta.imag], dtype=np.float64)
+    rc = L.oz_gemm_complex(op_a, op_b, m, n, k, _p(al), _p(a), lda, _p(b), ldb, _p(be), _p(out), ldc, num_split)
+    assert rc == 0
+    return out
+
+
+def gen_complex(kind: str, count: int, seed: int) -> np.ndarray:
+    return gen_matrix(kind, count, seed) + 1j * gen_matrix(kind, count, seed + 7919)
 
 
 def oracle_auto_select(op_a: int, op_b: int, m: int, n: int, k: int, a: np.ndarray, lda: int, b: np.ndarray, ldb: int,

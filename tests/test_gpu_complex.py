@@ -1,0 +1,79 @@
+"""-m gpu: the complex path (cublasZgemm / gemm(..., complx); reference src/gemm.cu:412-521) through the
+C-ABI against the CPU oracle and, bit for bit, against the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib
+import ozimmu_b200 as oz
+from gpu_util import Reference, bits, to_dev, ulp_distance
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("op_a,op_b", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k,num_split,kind,alpha,beta", [
+    (64, 48, 100, 9, "normal01", 1.0 + 0.0j, 0.0 + 0.0j),
+    (130, 70, 257, 13, "exp_rand-1", -1.5 + 0.5j, 0.75 - 0.25j),
+    (33, 200, 16, 3, "urand01", 0.0 + 2.0j, 0.0 + 1.0j),
+    (129, 131, 300, 18, "mixed", 1.0 - 1.0j, 1.0 + 0.0j),
+])
+def test_zgemm_matches_oracle(handle, op_a, op_b, m, n, k, num_split, kind, alpha, beta):
+    lda = m if op_a == 0 else k
+    ldb = k if op_b == 0 else n
+    a = oracle_lib.gen_complex(kind, m * k, m + k)
+    b = oracle_lib.gen_complex(kind, k * n, n + k)
+    c = oracle_lib.gen_complex("normal01", m * n, 5)
+    want = oracle_lib.oracle_gemm_complex(op_a, op_b, m, n, k, alpha, a, lda, b, ldb, beta, c, m, num_split)
+    da, db, dc = to_dev(a), to_dev(b), to_dev(c)
+    rc = oz.gemm(handle, op_a, op_b, m, n, k, alpha, da, lda, db, ldb, beta, dc, m, oz.fp64_int8(num_split), oz.complx)
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = dc.cpu().numpy()
+    assert np.array_equal(got.view(np.int64), want.view(np.int64)), \
+        f"max ulp distance {ulp_distance(got.view(np.float64), want.view(np.float64))}"
+
+
+@pytest.mark.parametrize("op_a,op_b", [(0, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k,num_split", [(1024, 1024, 1024, 9), (1024, 1023, 1025, 12), (2048, 512, 768, 16)])
+def test_zgemm_bit_exact_vs_reference(handle, op_a, op_b, m, n, k, num_split):
+    if oracle_lib.reference() is None:
+        pytest.skip("oracle/_ref/libozref.so not built")
+    ref = Reference()
+    try:
+        g = torch.Generator(device="cuda").manual_seed(num_split)
+        lda = m if op_a == 0 else k
+        ldb = k if op_b == 0 else n
+        a = torch.randn(m * k, dtype=torch.complex128, device="cuda", generator=g)
+        b = torch.randn(k * n, dtype=torch.complex128, device="cuda", generator=g)
+        c0 = torch.randn(m * n, dtype=torch.complex128, device="cuda", generator=g)
+        for alpha, beta in ((1.0 + 0j, 0j), (0.5 - 1.5j, -0.25 + 2.0j)):
+            c_ref, c_new = c0.clone(), c0.clone()
+            ref.gemm_complex(op_a, op_b, m, n, k, alpha, a, lda, b, ldb, beta, c_ref, m, num_split - 1)
+            assert oz.gemm(handle, op_a, op_b, m, n, k, alpha, a, lda, b, ldb, beta, c_new, m, oz.fp64_int8(num_split),
+                           oz.complx) == 0
+            torch.cuda.synchronize()
+            assert torch.equal(torch.view_as_real(c_ref).view(torch.int64), torch.view_as_real(c_new).view(torch.int64))
+        # accuracy against cuBLAS ZGEMM (column-major: C^T = B^T A^T in torch's row-major view)
+        if op_a == 0 and op_b == 0 and num_split >= 12:
+            c_new = torch.zeros_like(c0)
+            assert oz.gemm(handle, 0, 0, m, n, k, 1.0 + 0j, a, m, b, k, 0j, c_new, m, oz.fp64_int8(num_split), oz.complx) == 0
+            want = (b.view(n, k) @ a.view(k, m)).reshape(-1)
+            assert (torch.linalg.vector_norm(c_new - want) / torch.linalg.vector_norm(want)).item() < 1e-14
+    finally:
+        ref.close()
+
+
+def test_complex_auto_mode_vs_oracle(handle):
+    m, n, k = 96, 80, 160
+    a = oracle_lib.gen_complex("exp_rand-2", m * k, 1)
+    b = oracle_lib.gen_complex("exp_rand-2", k * n, 2)
+    import ctypes as C
+    L = oracle_lib.oracle()
+    for thr in (0.0, 1.0, 4.0):
+        cnt_want = np.zeros(16, dtype=np.uint64)
+        s = L.oz_auto_select_complex(0, 0, m, n, k, a.ctypes.data, m, b.ctypes.data, k, thr, cnt_want.ctypes.data)
+        cnt = []
+        mode = oz.auto_mode_select(handle, 0, 0, m, n, k, to_dev(a), m, to_dev(b), k, oz.complx, thr, cnt)
+        assert cnt == [int(v) for v in cnt_want]
+        assert mode == (oz.fp64_int8(s) if s else oz.compute_mode_t.dgemm)

@@ -51,7 +51,7 @@ def test_split_special_rows():
 
 # (0, BN): CTA-pair kernel (cta_group::2) with BN columns; (100, PM PN): the same with BN=192 in a PM x PN
 # multicast cluster of pairs; (cm, cn): single-CTA kernel, cm x cn multicast cluster
-@pytest.mark.parametrize("shape", [(0, 192), (0, 128), (100, 21), (100, 12), (100, 22), (1, 1), (2, 1), (1, 2), (2, 2)])
+@pytest.mark.parametrize("shape", [(0, 256), (0, 192), (0, 128), (100, 21), (100, 12), (100, 22), (1, 1), (2, 1), (1, 2), (2, 2)])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 384, 512), (100, 60, 70), (513, 259, 1031), (1, 1, 1),
                                    (1025, 1023, 1024)])
 def test_int8_pair_product_exact(shape, m, n, k):

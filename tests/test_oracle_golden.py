@@ -14,6 +14,7 @@ import oracle_lib
 GOLDEN = Path(__file__).resolve().parent / "golden"
 GEMM_FILES = sorted(glob.glob(str(GOLDEN / "gemm_*.npz")))
 AUTO_FILES = sorted(glob.glob(str(GOLDEN / "auto_*.npz")))
+ZGEMM_FILES = sorted(glob.glob(str(GOLDEN / "zgemm_*.npz")))
 
 
 def test_fixtures_present():
@@ -57,3 +58,18 @@ def test_auto_mode_matches_reference(path):
             assert s - 1 == int(ref_mode)
         elif s != 0:
             assert s >= 11
+
+
+@pytest.mark.parametrize("path", ZGEMM_FILES, ids=lambda p: Path(p).stem)
+def test_zgemm_matches_reference_bits(path):
+    """complex path (reference src/gemm.cu:412-521), incl. the reference's beta pre-scale as compiled"""
+    g = np.load(path)
+    op_a, op_b, m, n, k, s = (int(g[x]) for x in ("op_a", "op_b", "m", "n", "k", "num_split"))
+    got = oracle_lib.oracle_gemm_complex(op_a, op_b, m, n, k, complex(g["alpha"]), g["a"], int(g["lda"]), g["b"],
+                                         int(g["ldb"]), complex(g["beta"]), g["c_in"], int(g["ldc"]), s)
+    want = g["c_out"]
+    assert np.array_equal(got.view(np.int64), want.view(np.int64))
+
+
+def test_zgemm_fixtures_present():
+    assert len(ZGEMM_FILES) >= 4
