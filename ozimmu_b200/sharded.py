@@ -4,8 +4,11 @@
 on its block.  Bit-identical to the one-GPU result: the split scales A per row and B per column and
 K is never partitioned, so no cross-shard reduction exists.
 
-The broadcast is pipelined with the product: for op_n B (column panels are contiguous) B travels in
-column panels and the split + tcgen05 product of panel p run while panel p+1 is still on the wire.
+By default B travels as ONE broadcast followed by one product over the whole row block (the fused
+kernel then runs a single persistent launch, 14 full rounds of tiles at 8192^2).  `pipeline=True` sends B
+in column panels (contiguous for op_n B) and runs split + product per panel while the next panel is on the
+wire; on NVLink 5 the broadcast (512 MiB in < 1 ms) is too short to repay the ragged last round that each
+per-panel launch adds, so it is off unless B is very large relative to the product.
 """
 from __future__ import annotations
 
@@ -38,7 +41,7 @@ def column_panels(n: int, max_panels: int = 4, min_width: int = 1024) -> List[Tu
 
 def sharded_gemm(handle: api.handle_t, op_A: int, op_B: int, m_local: int, n: int, k: int, alpha: float, a_block,
                  lda: int, b, ldb: int, beta: float, c_block, ldc: int, compute_mode, *, src: int = 0, group=None,
-                 pipeline: bool = True) -> int:
+                 pipeline: bool = False) -> int:
     """C_block = alpha * op(A_block) * op(B) + beta * C_block on every rank.
 
     a_block / c_block: this rank's rows (device, column-major).  b: device buffer of the full B on every

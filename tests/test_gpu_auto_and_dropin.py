@@ -88,7 +88,12 @@ a = torch.rand(n, n, dtype=torch.float64, device="cuda")
 b = torch.rand(n, n, dtype=torch.float64, device="cuda")
 c = a @ b
 torch.cuda.synchronize()
-torch.save({"a": a.cpu(), "b": b.cpu(), "c": c.cpu()}, os.environ["OZ_DROPIN_OUT"])
+za = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+zb = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+zc = za @ zb
+torch.cuda.synchronize()
+torch.save({"a": a.cpu(), "b": b.cpu(), "c": c.cpu(), "za": za.cpu(), "zb": zb.cpu(), "zc": zc.cpu()},
+           os.environ["OZ_DROPIN_OUT"])
 """
 
 
@@ -113,3 +118,36 @@ def test_ld_preload_dropin(tmp_path, handle):
     # and it is an accurate DGEMM
     ref = d["a"] @ d["b"]
     assert (torch.linalg.norm(d["c"] - ref) / torch.linalg.norm(ref)).item() < 1e-15
+    # complex128 matmul -> cublasZgemm / cublasGemmEx(C_64F) -> the complex Ozaki path
+    assert "[CULiP Result][Zfp64_int8_9-" in p.stdout, p.stdout[-2000:]
+    za, zb = d["za"].cuda(), d["zb"].cuda()
+    zc = torch.zeros(n, n, dtype=torch.complex128, device="cuda")
+    assert oz.gemm(handle, 0, 0, n, n, n, 1.0 + 0j, zb, n, za, n, 0j, zc, n, oz.fp64_int8(9), oz.complx) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(torch.view_as_real(zc).cpu().view(torch.int64), torch.view_as_real(d["zc"]).view(torch.int64))
+    zref = d["za"] @ d["zb"]
+    assert (torch.linalg.norm(d["zc"] - zref) / torch.linalg.norm(zref)).item() < 1e-14
+
+
+def test_cuda_graph_capture(handle):
+    """The device entry has no hidden synchronisation (the reference calls cudaDeviceSynchronize twice per
+    GEMM, src/split.cu:261): once the workspace is sized it can be captured into a CUDA graph and replayed."""
+    m, n, k = 512, 640, 768
+    a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 1))
+    b = to_dev(oracle_lib.gen_matrix("exp_rand-1", k * n, 2))
+    c_eager = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+    c_graph = torch.zeros_like(c_eager)
+    s = torch.cuda.Stream()
+    oz.set_cuda_stream(handle, s)
+    with torch.cuda.stream(s):
+        assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c_eager, m, oz.fp64_int8(9)) == 0  # sizes the workspace
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c_graph, m, oz.fp64_int8(9)) == 0
+    for _ in range(3):
+        c_graph.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(c_graph.view(torch.int64), c_eager.view(torch.int64))
+    oz.set_cuda_stream(handle, None)

@@ -47,6 +47,19 @@ def test_gemm_matches_oracle(handle, op_a, op_b, m, n, k, num_split, kind, alpha
     assert np.array_equal(bits(got), bits(want)), f"max ulp distance {ulp_distance(got, want)}"
 
 
+def test_long_k_six_bit_slices(handle):
+    """k > 2^17 lowers the slice width to 6 bits (reference src/split.cu:520-536) and shifts every scale"""
+    m, n, k, s = 16, 24, 131200, 9
+    assert oz.get_bits_per_int8(k) == 6
+    a = oracle_lib.gen_matrix("exp_rand-1", m * k, 1)
+    b = oracle_lib.gen_matrix("exp_rand-1", k * n, 2)
+    want = oracle_lib.oracle_gemm(1, 0, m, n, k, 1.0, a, k, b, k, 0.0, np.zeros(m * n), m, s)
+    dc = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+    assert oz.gemm(handle, 1, 0, m, n, k, 1.0, to_dev(a), k, to_dev(b), k, 0.0, dc, m, oz.fp64_int8(s)) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(dc), bits(want))
+
+
 def test_gemm_k_zero_and_empty(handle):
     m, n = 40, 24
     c = oracle_lib.gen_matrix("normal01", m * n, 5)

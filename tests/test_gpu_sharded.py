@@ -27,6 +27,12 @@ c_blk = torch.zeros(n, rows, dtype=torch.float64, device="cuda")
 h = oz.create()
 assert oz.sharded_gemm(h, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_blk, rows, oz.fp64_int8(s), src=0) == 0
 torch.cuda.synchronize()
+c_pipe = torch.zeros_like(c_blk)
+if rank != 0:
+    b.zero_()
+assert oz.sharded_gemm(h, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_pipe, rows, oz.fp64_int8(s), src=0, pipeline=True) == 0
+torch.cuda.synchronize()
+assert torch.equal(c_pipe.view(torch.int64), c_blk.view(torch.int64)), "panel-pipelined broadcast differs"
 torch.save(c_blk.cpu(), os.environ["OZ_OUT"] + f"/c_{rank}.pt")
 dist.barrier(); oz.destroy(h); dist.destroy_process_group()
 """
