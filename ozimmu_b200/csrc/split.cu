@@ -74,6 +74,58 @@ __device__ __forceinline__ void cut16(const double (&v)[16], const uint64_t max_
   }
 }
 
+// The same cut for L == 7 (every k <= 2^17, i.e. every BASELINE configuration) with the 128-bit
+// aligned significand held in four 32-bit words: one variable shift (word select + funnel shifts),
+// then every slice is a COMPILE-TIME bit-field (2 instructions), signed by one IMAD and dropped into
+// its byte lane by one PRMT -- about half the integer instructions of the generic version, which is what
+// bounds the split kernels (they are issue-bound before they are HBM-bound).
+template <int S>
+__device__ __forceinline__ void cut16_l7(const double (&v)[16], const uint64_t max_exp_bits, uint32_t (&w)[S][4]) {
+  const uint32_t emaxp1 = static_cast<uint32_t>(max_exp_bits >> 52);  // exponent field of 2*max (sign is 0)
+#pragma unroll
+  for (int t = 0; t < S; t++) {
+    w[t][0] = w[t][1] = w[t][2] = w[t][3] = 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const uint32_t hi32 = static_cast<uint32_t>(__double2hiint(v[j]));
+    const uint32_t lo32 = static_cast<uint32_t>(__double2loint(v[j]));
+    const uint32_t ea = (hi32 >> 20) & 0x7FFu;
+    const int sgn = (v[j] > 0) ? 1 : -1;
+    const uint32_t mh = (hi32 & 0xFFFFFu) | (ea ? 0x100000u : 0u);
+    // significand MSB at bit 127: words (x3, x2, 0, 0), then >> off, off = (emax+1) - e(a) (mod 2^12 as in
+    // the reference's 64-bit subtraction followed by >> 52)
+    const uint32_t x3 = (mh << 11) | (lo32 >> 21), x2 = lo32 << 11;
+    const uint32_t off = (emaxp1 - ea) & 0xFFFu;
+    const uint32_t bs = off & 31u, ws = off >> 5;
+    const uint32_t u3 = x3 >> bs, u2 = __funnelshift_r(x2, x3, bs), u1 = __funnelshift_r(0u, x2, bs);
+    uint32_t W[4];  // W[3] = bits 127..96
+    W[3] = (ws == 0) ? u3 : 0u;
+    W[2] = (ws == 0) ? u2 : (ws == 1) ? u3 : 0u;
+    W[1] = (ws == 0) ? u1 : (ws == 1) ? u2 : (ws == 2) ? u3 : 0u;
+    W[0] = (ws == 1) ? u1 : (ws == 2) ? u2 : (ws == 3) ? u3 : 0u;
+#pragma unroll
+    for (int t = 0; t < S; t++) {
+      constexpr int kDummy = 0;
+      (void)kDummy;
+      const int p = 121 - 7 * t;          // bit position of the field's LSB (compile time after unrolling)
+      const int word = p >> 5, sh = p & 31;
+      uint32_t f;
+      if (sh <= 25) f = W[word] >> sh;
+      else f = __funnelshift_r(W[word], W[word + 1], sh);
+      const int sv = static_cast<int>(f & 0x7Fu) * sgn;
+      w[t][j >> 2] = __byte_perm(w[t][j >> 2], static_cast<uint32_t>(sv), 0x3210u ^ ((0x4u ^ (j & 3)) << (4 * (j & 3))));
+    }
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void cut16_any(const double (&v)[16], const uint64_t max_exp_bits, const unsigned L,
+                                          uint32_t (&w)[S][4]) {
+  if (L == 7) cut16_l7<S>(v, max_exp_bits, w);
+  else cut16<S>(v, max_exp_bits, L, w);
+}
+
 __device__ __forceinline__ uint32_t block_max_u32(uint32_t v, uint32_t *s_red) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -134,12 +186,79 @@ split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
       }
     }
     uint32_t w[S][4];
-    cut16<S>(v, mx_bits, L, w);
+    cut16_any<S>(v, mx_bits, L, w);
 #pragma unroll
     for (int t = 0; t < S; t++) {
       uint4 q = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
       // elements >= len are exact zeros => their slice bytes are already 0
       *reinterpret_cast<uint4 *>(dst + t * slice_stride + g * 16) = q;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rows contiguous, row length <= 32 * THREADS: the row lives in registers.  Every thread loads the
+// (up to two) 16-element groups it will cut as 16-byte vector loads (one HBM pass, no SMEM staging, so
+// occupancy is bounded by registers only and all of a row's loads are in flight at once), the block
+// reduces the exponent maximum, and the groups are cut straight from registers.
+// ---------------------------------------------------------------------------------------------
+template <int S, int THREADS, int GROUPS>
+__global__ void __launch_bounds__(THREADS)
+split_rows_reg_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
+                      const size_t rows, const uint32_t len, const double *__restrict__ in,
+                      const size_t ld, const unsigned L) {
+  __shared__ uint32_t s_red[THREADS / 32];
+  __shared__ uint32_t s_max;
+  const size_t row = blockIdx.x;
+  const double *__restrict__ src = in + row * ld;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+  double v[GROUPS][16];
+  uint32_t e = 0;
+#pragma unroll
+  for (int gi = 0; gi < GROUPS; gi++) {
+    const uint32_t g = threadIdx.x + gi * THREADS;
+    const uint32_t i0 = g * 16;
+    if (i0 + 16 <= len && vec_ok) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const double2 d = __ldg(reinterpret_cast<const double2 *>(src + i0) + q);
+        v[gi][2 * q] = d.x;
+        v[gi][2 * q + 1] = d.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j++) v[gi][j] = (i0 + j < len) ? __ldg(src + i0 + j) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) e = max(e, exp_field(v[gi][j]));
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t x = (threadIdx.x < THREADS / 32) ? s_red[threadIdx.x] : 0u;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
+    if (threadIdx.x == 0) s_max = x;
+  }
+  __syncthreads();
+  const double mx = max_exp_from_field(s_max);
+  const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
+  if (threadIdx.x == 0) max_exp[row] = mx;
+
+  const size_t slice_stride = rows * pitch;
+  int8_t *__restrict__ dst = out + row * pitch;
+  const uint32_t ngroups = static_cast<uint32_t>(pitch / 16);
+#pragma unroll
+  for (int gi = 0; gi < GROUPS; gi++) {
+    const uint32_t g = threadIdx.x + gi * THREADS;
+    if (g < ngroups) {
+      uint32_t w[S][4];
+      cut16_any<S>(v[gi], mx_bits, L, w);
+#pragma unroll
+      for (int t = 0; t < S; t++)
+        *reinterpret_cast<uint4 *>(dst + t * slice_stride + g * 16) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
     }
   }
 }
@@ -162,31 +281,50 @@ rowmax_cols_kernel(uint32_t *__restrict__ emax, const size_t rows, const uint32_
   atomicMax(emax + r, e);
 }
 
+// CTA = 32 rows x 128 K-positions: warp w cuts K-group w (16 positions) of 32 consecutive rows, so every
+// gathered load is one coalesced 256-byte row segment of a column.  The 16-byte slice pieces are
+// transposed through shared memory (XOR-swizzled, conflict-free) and leave as full 128-byte lines per
+// row and slice -- writing them straight from the cutting threads would scatter 16-byte partial-sector
+// stores over 32 rows per instruction.
+constexpr int kColsRows = 32, kColsK = 128;
+
 template <int S>
 __global__ void __launch_bounds__(256)
 split_cols_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
                   const uint32_t *__restrict__ emax, const size_t rows, const uint32_t len,
                   const double *__restrict__ in, const size_t ld, const unsigned L, const uint32_t es) {
-  const size_t r = static_cast<size_t>(blockIdx.x) * 64 + (threadIdx.x & 63);
-  const uint32_t cbase = blockIdx.y * 64 + (threadIdx.x >> 6) * 16;
-  if (r >= rows || cbase >= pitch) return;
-  const double mx = max_exp_from_field(emax[r]);
-  const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
-  if (blockIdx.y == 0 && threadIdx.x < 64) max_exp[r] = mx;
-
-  double v[16];
+  extern __shared__ uint4 s_out[];  // [S][32 rows][8 chunks of 16 B], chunk index ^ (row & 7)
+  const uint32_t rl = threadIdx.x & 31, cg = threadIdx.x >> 5;
+  const size_t r = static_cast<size_t>(blockIdx.x) * kColsRows + rl;
+  const uint32_t kbase = blockIdx.y * kColsK;
+  const uint32_t cbase = kbase + cg * 16;
+  if (r < rows && cbase < pitch) {
+    const double mx = max_exp_from_field(emax[r]);
+    const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
+    if (blockIdx.y == 0 && cg == 0) max_exp[r] = mx;
+    double v[16];
 #pragma unroll
-  for (int j = 0; j < 16; j++) {
-    const uint32_t c = cbase + j;
-    v[j] = (c < len) ? __ldg(in + (static_cast<size_t>(c) * ld + r) * es) : 0.0;
+    for (int j = 0; j < 16; j++) {
+      const uint32_t c = cbase + j;
+      v[j] = (c < len) ? __ldg(in + (static_cast<size_t>(c) * ld + r) * es) : 0.0;
+    }
+    uint32_t w[S][4];
+    cut16_any<S>(v, mx_bits, L, w);
+#pragma unroll
+    for (int t = 0; t < S; t++)
+      s_out[(t * kColsRows + rl) * 8 + (cg ^ (rl & 7))] = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
   }
-  uint32_t w[S][4];
-  cut16<S>(v, mx_bits, L, w);
-  const size_t slice_stride = rows * pitch;
-  int8_t *__restrict__ dst = out + r * pitch + cbase;
+  __syncthreads();
+  // write-out: 8 consecutive threads cover one row's 128-byte line of one slice
+  const uint32_t orow = threadIdx.x >> 3, chunk = threadIdx.x & 7;
+  const size_t gr = static_cast<size_t>(blockIdx.x) * kColsRows + orow;
+  const uint32_t gk = kbase + chunk * 16;
+  if (gr < rows && gk < pitch) {
+    const size_t slice_stride = rows * pitch;
+    int8_t *__restrict__ dst = out + gr * pitch + gk;
 #pragma unroll
-  for (int t = 0; t < S; t++) {
-    *reinterpret_cast<uint4 *>(dst + t * slice_stride) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+    for (int t = 0; t < S; t++)
+      *reinterpret_cast<uint4 *>(dst + t * slice_stride) = s_out[(t * kColsRows + orow) * 8 + (chunk ^ (orow & 7))];
   }
 }
 
@@ -269,10 +407,32 @@ int launch_split(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, 
     OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), stream));
     dim3 g1(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk));
     rowmax_cols_kernel<<<g1, 256, 0, stream>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es);
-    dim3 g2(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((pitch + 63) / 64));
-    split_cols_kernel<S><<<g2, 256, 0, stream>>>(out, pitch, max_exp, scratch, rows,
-                                                 static_cast<uint32_t>(len), in, ld, L, es);
+    dim3 g2(static_cast<unsigned>((rows + kColsRows - 1) / kColsRows), static_cast<unsigned>((pitch + kColsK - 1) / kColsK));
+    const size_t smem_cols = static_cast<size_t>(S) * kColsRows * kColsK;
+    if (smem_cols > 48 * 1024) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        OZ_CUDA_TRY(cudaFuncSetAttribute(split_cols_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_cols)));
+        attr_done = true;
+      }
+    }
+    split_cols_kernel<S><<<g2, 256, smem_cols, stream>>>(out, pitch, max_exp, scratch, rows,
+                                                         static_cast<uint32_t>(len), in, ld, L, es);
     count_launch(2);
+  } else if (es == 1 && len <= 16384) {
+    // register-resident rows: (threads, 16-element groups per thread) sized to the row
+    const unsigned nrows = static_cast<unsigned>(rows);
+    const uint32_t len32 = static_cast<uint32_t>(len);
+    if (len <= 2048)
+      split_rows_reg_kernel<S, 128, 1><<<nrows, 128, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L);
+    else if (len <= 4096)
+      split_rows_reg_kernel<S, 256, 1><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L);
+    else if (len <= 8192)
+      split_rows_reg_kernel<S, 256, 2><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L);
+    else
+      split_rows_reg_kernel<S, 512, 2><<<nrows, 512, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L);
+    count_launch(1);
   } else {
     if (len <= static_cast<size_t>(kMaxCachedLen)) {
       const size_t smem = ((len + 15) / 16 * 16) * sizeof(double);

@@ -31,7 +31,7 @@ def main():
     ap.add_argument("n", type=int, nargs="?", default=4096)
     ap.add_argument("s", type=int, nargs="?", default=9)
     ap.add_argument("--ref", action="store_true")
-    ap.add_argument("--shapes", default="p192", help="p128,p192 = CTA-pair kernel; 11,21,12,22 = single-CTA clusters")
+    ap.add_argument("--shapes", default="00", help="p128,p192 = CTA-pair kernel; 11,21,12,22 = single-CTA clusters")
     ap.add_argument("--iters", type=int, default=5)
     args = ap.parse_args()
     n, s = args.n, args.s
