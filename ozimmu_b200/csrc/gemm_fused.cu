@@ -24,6 +24,7 @@
 //    buffer, acc = fma((double)p, 2^(32-rshift), acc).  After the last pair:
 //    x = acc*2^-44*amax[r]*bmax[c]; C = alpha*x (+ beta*C), coalesced along rows of column-major C.
 #include <cstdlib>
+#include <mutex>
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -683,6 +684,15 @@ oz_scale_c_kernel(double *__restrict__ c, const size_t ldc, const uint32_t m, co
 }
 
 // ---- host side --------------------------------------------------------------------------------
+// One-time, per-device kernel setup (dynamic SMEM opt-in, resident cluster count), safe for concurrent
+// callers and for one process driving several GPUs.
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[kMaxDevices] = {};
+  int value[kMaxDevices] = {};
+};
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -734,14 +744,10 @@ int launch_fused(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_
   p.group_m = (12 / CM) > 0 ? 12 / CM : 1;
 
   auto kern = oz_gemm_fused_kernel<CM, CN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    OZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_done = true;
-  }
   int dev = 0, sms = 0;
   OZ_CUDA_TRY(cudaGetDevice(&dev));
   OZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 0 || dev >= kMaxDevices) return static_cast<int>(cudaErrorInvalidDevice);
 
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
@@ -756,14 +762,22 @@ int launch_fused(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static int cached_max = -1;
-    if (cached_max < 0) {
-      cfg.gridDim = dim3(static_cast<unsigned>(sms) / (CM * CN) * (CM * CN));
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) cached_max = nc;
-      else cached_max = static_cast<int>(max_clusters);
+  }
+  static PerDeviceOnce once;
+  {
+    std::lock_guard<std::mutex> lock(once.mu);
+    if (!once.done[dev]) {
+      OZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      once.value[dev] = static_cast<int>(max_clusters);
+      if (CM * CN > 1) {
+        cfg.gridDim = dim3(static_cast<unsigned>(sms) / (CM * CN) * (CM * CN));
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) once.value[dev] = nc;
+        cudaGetLastError();
+      }
+      once.done[dev] = true;
     }
-    max_clusters = static_cast<uint32_t>(cached_max);
+    max_clusters = static_cast<uint32_t>(once.value[dev]);
   }
   const uint32_t num_super = p.super_m * p.super_n;
   const uint32_t clusters = num_super < max_clusters ? num_super : max_clusters;
@@ -794,11 +808,13 @@ const PairTuning &pair_tuning() {
 constexpr uint32_t kSyncCounters = 1u << 16;  // per buffer: 64 Ki intervals = 1 Mi k-steps per CTA pair
 constexpr int kSyncBuffers = 8;               // launches that may be in flight at once without sharing
 uint32_t *next_sync_buffer() {
+  static std::mutex mu;
   static uint32_t *pool[kSyncBuffers] = {};
   static int pool_dev[kSyncBuffers] = {};
   static int next = 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
   const int i = next;
   next = (next + 1) % kSyncBuffers;
   if (pool[i] != nullptr && pool_dev[i] != dev) {
@@ -834,14 +850,10 @@ int launch_pair(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_s
   p.sync_window = tune.sync_window;
 
   auto kern = oz_gemm_pair_kernel<BN_, PM, PN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    OZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
   int dev = 0, sms = 0;
   OZ_CUDA_TRY(cudaGetDevice(&dev));
   OZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 0 || dev >= kMaxDevices) return static_cast<int>(cudaErrorInvalidDevice);
 
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
@@ -854,15 +866,23 @@ int launch_pair(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int cached_max = -1;
-  if (cached_max < 0) {
-    cfg.gridDim = dim3(static_cast<unsigned>(sms) / CSZ * CSZ);
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) cached_max = nc;
-    else cached_max = sms / static_cast<int>(CSZ);
-    if (std::getenv("OZIMMU_B200_DEBUG"))
-      std::fprintf(stderr, "[ozimmu_b200] pair kernel BN=%u cluster %ux%u pairs: %d clusters resident (%d of %d SMs)\n", BN_,
-                   PM, PN, cached_max, cached_max * static_cast<int>(CSZ), sms);
+  static PerDeviceOnce once;
+  int cached_max = 0;
+  {
+    std::lock_guard<std::mutex> lock(once.mu);
+    if (!once.done[dev]) {
+      OZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      cfg.gridDim = dim3(static_cast<unsigned>(sms) / CSZ * CSZ);
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0) once.value[dev] = nc;
+      else once.value[dev] = sms / static_cast<int>(CSZ);
+      cudaGetLastError();
+      once.done[dev] = true;
+      if (std::getenv("OZIMMU_B200_DEBUG"))
+        std::fprintf(stderr, "[ozimmu_b200] pair kernel BN=%u cluster %ux%u pairs: %d clusters resident (%d of %d SMs)\n", BN_,
+                     PM, PN, once.value[dev], once.value[dev] * static_cast<int>(CSZ), sms);
+    }
+    cached_max = once.value[dev];
   }
   const uint32_t num_tiles = p.super_m * p.super_n;
   const uint32_t pairs = num_tiles < static_cast<uint32_t>(cached_max) ? num_tiles : static_cast<uint32_t>(cached_max);

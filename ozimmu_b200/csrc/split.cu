@@ -409,14 +409,9 @@ int launch_split(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, 
     rowmax_cols_kernel<<<g1, 256, 0, stream>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es);
     dim3 g2(static_cast<unsigned>((rows + kColsRows - 1) / kColsRows), static_cast<unsigned>((pitch + kColsK - 1) / kColsK));
     const size_t smem_cols = static_cast<size_t>(S) * kColsRows * kColsK;
-    if (smem_cols > 48 * 1024) {
-      static bool attr_done = false;
-      if (!attr_done) {
-        OZ_CUDA_TRY(cudaFuncSetAttribute(split_cols_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem_cols)));
-        attr_done = true;
-      }
-    }
+    if (smem_cols > 48 * 1024)  // per device and cheap: no caching
+      OZ_CUDA_TRY(cudaFuncSetAttribute(split_cols_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem_cols)));
     split_cols_kernel<S><<<g2, 256, smem_cols, stream>>>(out, pitch, max_exp, scratch, rows,
                                                          static_cast<uint32_t>(len), in, ld, L, es);
     count_launch(2);
