@@ -38,17 +38,42 @@ NUM_SPLIT = int(os.environ.get("OZ_BENCH_SPLIT", "9"))
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled
+    every 5 ms from a thread (nvidia-smi -lms cannot deliver more than a couple of samples in a 0.2 s
+    region); falls back to nvidia-smi when pynvml is unavailable."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
+        self.samples = []          # (sm_mhz, power_w, reasons bitmask)
+        self.max_mhz = None
+        self.stop_flag = False
+        self.thread = None
         self.proc = None
         self.lines = []
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -58,11 +83,40 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:  # noqa: BLE001
+                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, pw, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            sm = sorted(x[0] for x in self.samples)
+            bits = 0
+            for x in self.samples:
+                bits |= x[2]
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake_slowdown"}
+            return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(x[1] for x in self.samples), "samples": len(sm), "source": "nvml 5 ms poll",
+                    "reasons": sorted(v for k, v in names.items() if bits & k)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -87,7 +141,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "source": "nvidia-smi -lms 100", "reasons": sorted(reasons)}
 
 
 def dist_setup(gpus: int):
@@ -121,12 +175,14 @@ def max_over_ranks(ms: float, world: int) -> float:
     return float(t.item())
 
 
-def timed_loop(fn, steps: int, warmup: int, world: int) -> float:
+def timed_loop(fn, steps: int, warmup: int, world: int, sampler=None) -> float:
     """ms per step: W untimed steps, then exactly K steps between barrier+sync, CUDA events, max over ranks."""
     import torch
     for _ in range(warmup):
         fn()
     barrier_sync(world)
+    if sampler is not None:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -193,7 +249,7 @@ def measured_peaks() -> dict:
 
 def ncu_traffic_bytes():
     """dram bytes per launch of the fused kernel from the committed ncu capture (profiles/), or None"""
-    p = ROOT / "profiles" / "r1_fused_pair192_8192.json"
+    p = ROOT / "profiles" / "r1_fused_pair256_8192.json"
     if p.exists():
         try:
             d = json.loads(p.read_text())
@@ -221,9 +277,7 @@ def run_ours(args) -> dict:
 
     sampler = ClockSampler(local)
     launches0 = oz.launch_count()
-    if rank == 0:
-        sampler.start()
-    ms = timed_loop(step, args.steps, args.warmup, world)
+    ms = timed_loop(step, args.steps, args.warmup, world, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     launches = (oz.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
     flop_step = 2.0 * n * n * n * world
@@ -325,8 +379,7 @@ def run_reference(args) -> dict:
         ref.gemm(0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, s - 1)
 
     sampler = ClockSampler(local)
-    sampler.start()
-    ms = timed_loop(step, args.steps, args.warmup, 1)
+    ms = timed_loop(step, args.steps, args.warmup, 1, sampler)
     clocks = sampler.stop()
     flop = 2.0 * n * n * n
     ha = torch.empty(n * n, dtype=torch.float64).pin_memory(); ha.copy_(a)
