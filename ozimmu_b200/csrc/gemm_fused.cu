@@ -453,9 +453,10 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     ptx::reg_dealloc<Cfg::kRegsOther>();
     if (warp == 0) {
       // ===================== TMA producer (both CTAs; whole warp loops, one lane issues) ==========
-      // A second cursor runs kPrefetchAhead k-blocks ahead of the ring and pulls the boxes into L2
-      // (cp.async.bulk.prefetch): a slice panel is re-read once per pair that uses it and rarely
-      // survives in L2 between uses, so without this the ring (7 stages ~ 1.6 us) eats HBM latency.
+      // Optional (OZIMMU_B200_PREFETCH=n, default off): a second cursor runs n k-blocks ahead of the ring
+      // and pulls the boxes into L2 (cp.async.bulk.prefetch).  It hides HBM latency, but the kernel is
+      // bound by L2->SM delivery and the extra L2 lookups cost more than they save: -5 % at 8192^3
+      // (profiles/r1_sweep_prefetch_lockstep_256.txt).
       const bool issuer = ptx::elect_one();
       uint32_t stage = 0, ph = 0;
       KCursor<BN_, PM, PN> ahead(p, pair_id, num_pairs, num_tiles, rank, pm, pn);
@@ -796,7 +797,7 @@ struct PairTuning {
 };
 const PairTuning &pair_tuning() {
   static const PairTuning t = [] {
-    PairTuning v{16, 2};
+    PairTuning v{0, 2};
     if (const char *e = std::getenv("OZIMMU_B200_PREFETCH")) v.prefetch_ahead = static_cast<uint32_t>(std::atoi(e));
     if (const char *e = std::getenv("OZIMMU_B200_LOCKSTEP")) v.sync_window = static_cast<uint32_t>(std::atoi(e));
     if (v.prefetch_ahead > 256) v.prefetch_ahead = 256;
