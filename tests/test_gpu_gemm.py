@@ -47,6 +47,36 @@ def test_gemm_matches_oracle(handle, op_a, op_b, m, n, k, num_split, kind, alpha
     assert np.array_equal(bits(got), bits(want)), f"max ulp distance {ulp_distance(got, want)}"
 
 
+def test_random_shapes_vs_oracle(handle):
+    """40 seeded random problems: shapes, op combinations, leading dimensions, 8-byte-only aligned operands,
+    alpha/beta, split counts and input distributions -- all bit-exact against the CPU oracle."""
+    rng = np.random.default_rng(2024)
+    kinds = ["urand01", "normal01", "exp_rand-1", "exp_rand-4", "mixed"]
+    for case in range(40):
+        m, n, k = int(rng.integers(1, 161)), int(rng.integers(1, 161)), int(rng.integers(1, 401))
+        op_a, op_b = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        s = int(rng.integers(3, 19))
+        ex = int(rng.integers(0, 4))
+        kind = kinds[int(rng.integers(0, len(kinds)))]
+        alpha = float(rng.choice([1.0, -1.0, 0.5, 2.5, 0.0]))
+        beta = float(rng.choice([0.0, 0.0, 1.0, -0.75]))
+        lda, ca = stored_shape(op_a, m, k, ex)
+        ldb, cb = stored_shape(op_b, k, n, ex)
+        ldc = m + ex
+        off = int(rng.integers(0, 2))  # shift every operand by one double: only 8-byte aligned
+        a = oracle_lib.gen_matrix(kind, lda * ca + off, 100 + case)
+        b = oracle_lib.gen_matrix(kind, ldb * cb + off, 200 + case)
+        c = oracle_lib.gen_matrix("normal01", ldc * n + off, 300 + case)
+        want = oracle_lib.oracle_gemm(op_a, op_b, m, n, k, alpha, a[off:], lda, b[off:], ldb, beta, c[off:], ldc, s)
+        da, db, dc = to_dev(a), to_dev(b), to_dev(c)
+        rc = oz.gemm(handle, op_a, op_b, m, n, k, alpha, da.data_ptr() + 8 * off, lda, db.data_ptr() + 8 * off, ldb,
+                     beta, dc.data_ptr() + 8 * off, ldc, oz.fp64_int8(s))
+        assert rc == 0
+        torch.cuda.synchronize()
+        got = dc.cpu().numpy()[off:]
+        assert np.array_equal(bits(got), bits(want)), (case, op_a, op_b, m, n, k, s, kind, alpha, beta, ex, off)
+
+
 def test_long_k_six_bit_slices(handle):
     """k > 2^17 lowers the slice width to 6 bits (reference src/split.cu:520-536) and shifts every scale"""
     m, n, k, s = 16, 24, 131200, 9
