@@ -346,7 +346,7 @@ def run_ours(args) -> dict:
     oz.destroy(h)
     out = {"metric": "FP64-equiv TFLOP/s at fp64_int8_9, 8192^3 (2*m*n*k/t)", "value": value, "unit": "TFLOP/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "int8 tensor-core products, FP64 accumulation (f64 in/out)",
+           "scaling": "weak", "vs_baseline": None, "dtype": "int8 (int32 products, f64 accumulation; f64 in/out)",
            "data": "synthetic urand01 (0,1], seeded torch.rand on device",
            "config": {"workload": f"DGEMM N/N {n}x{n}x{n} per GPU, fp64_int8_{s}, alpha=1 beta=0, tight ld"
                                   + ("" if world == 1 else f"; global m={n * world} row-sharded, B broadcast from rank 0 over NCCL every step"),
@@ -400,7 +400,7 @@ def run_reference(args) -> dict:
     value = flop / ms / 1e9
     return {"impl": "reference", "metric": "FP64-equiv TFLOP/s at fp64_int8_9, 8192^3 (2*m*n*k/t)", "value": value,
             "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 tensor-core products, FP64 accumulation",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 (int32 products, f64 accumulation; f64 in/out)",
             "data": "synthetic urand01 (0,1], seeded torch.rand on device",
             "config": {"workload": f"DGEMM N/N {n}x{n}x{n}, fp64_int8_{s}, alpha=1 beta=0, tight ld",
                        "timing": "CUDA events, inputs larger than L2"},
@@ -427,7 +427,7 @@ def reference_cpu_port(args, why: str) -> dict:
     v = 2.0 * m ** 3 / dt / 1e12
     return {"impl": "reference", "metric": "FP64-equiv TFLOP/s at fp64_int8_9, 8192^3 (2*m*n*k/t)", "value": v, "unit": "TFLOP/s",
             "n_gpus": 1, "steps": steps, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int8 products, FP64 accumulation", "data": "synthetic urand01",
+            "vs_baseline": None, "dtype": "int8 (int32 products, f64 accumulation; f64 in/out)", "data": "synthetic urand01",
             "config": {"workload": f"bounded sample {m}^3 fp64_int8_{NUM_SPLIT} of the 8192^3 workload ({why})"},
             "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": 1, "kind": "port", "sample": f"oracle/oz_oracle.c {m}^3 x{steps}"},
             "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
