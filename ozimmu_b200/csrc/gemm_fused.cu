@@ -70,6 +70,7 @@ struct FusedParams {
   uint32_t *sync_ctr;          // one arrival counter per kSyncEvery k-steps, zeroed before launch (or null)
   uint32_t sync_window;        // a pair starts sync interval j only after interval j - window is complete
   uint32_t sync_len;           // counters available
+  uint32_t idle_sleep_ns;      // __nanosleep between barrier probes of the idle roles (0 = spin)
 };
 
 // reference src/config.cu:85-92: for sum = 2..s+1, for j = 1..sum-1: (A_id=j, B_id=sum-j)
@@ -502,7 +503,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (!ok) lockstep = false;
           }
         }
-        ptx::mbar_wait(empty_bar(stage), ph ^ 1u);
+        ptx::mbar_wait_relaxed(empty_bar(stage), ph ^ 1u, p.idle_sleep_ns);
         const uint32_t leader_full = ptx::mapa(full_bar(stage), lead);
         const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes + pn * (BM / PN) * BK;
         const uint32_t b_dst = smem_base + stage * Cfg::kStageBytes + BM * BK + pm * (BN_ / 2 / PM) * BK;
@@ -576,7 +577,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       bool first = true;
       for (PairIter it(p); it.valid(); it.next(), pc++) {
         const uint32_t buf = pc % kBufs, bph = (pc / kBufs) & 1u;
-        ptx::mbar_wait(tfull_bar(buf), bph);
+        ptx::mbar_wait_relaxed(tfull_bar(buf), bph, p.idle_sleep_ns);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * Cfg::kBufStride + half * kCols;
         const double scale = it.scale(p.bits);
@@ -794,10 +795,12 @@ int launch_fused(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_
 struct PairTuning {
   uint32_t prefetch_ahead;  // k-blocks of L2 prefetch lead (0 = off)
   uint32_t sync_window;     // soft-lockstep window in kSyncEvery-step intervals (0 = off)
+  uint32_t idle_sleep_ns;   // OZIMMU_B200_IDLE_SLEEP: nanosleep of idle roles between barrier probes
 };
 const PairTuning &pair_tuning() {
   static const PairTuning t = [] {
-    PairTuning v{0, 2};
+    PairTuning v{0, 2, 0};
+    if (const char *e = std::getenv("OZIMMU_B200_IDLE_SLEEP")) v.idle_sleep_ns = static_cast<uint32_t>(std::atoi(e));
     if (const char *e = std::getenv("OZIMMU_B200_PREFETCH")) v.prefetch_ahead = static_cast<uint32_t>(std::atoi(e));
     if (const char *e = std::getenv("OZIMMU_B200_LOCKSTEP")) v.sync_window = static_cast<uint32_t>(std::atoi(e));
     if (v.prefetch_ahead > 256) v.prefetch_ahead = 256;
@@ -849,6 +852,7 @@ int launch_pair(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_s
   const PairTuning &tune = pair_tuning();
   p.prefetch_ahead = tune.prefetch_ahead;
   p.sync_window = tune.sync_window;
+  p.idle_sleep_ns = tune.idle_sleep_ns;
 
   auto kern = oz_gemm_pair_kernel<BN_, PM, PN>;
   int dev = 0, sms = 0;

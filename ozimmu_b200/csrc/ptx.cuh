@@ -72,6 +72,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// wait for warps that sit idle for long stretches (epilogue waiting for a product, producer waiting for a
+// free stage): sleeps between probes so the idle warps stop competing for issue slots and power
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns) __nanosleep(ns);
+  }
+}
 // wait that also acquires at cluster scope (barrier receives remote arrivals from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
