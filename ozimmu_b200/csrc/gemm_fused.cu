@@ -893,9 +893,10 @@ int launch_pair(const FusedParams &p0, const int8_t *a_slices, const int8_t *b_s
   const uint32_t pairs = num_tiles < static_cast<uint32_t>(cached_max) ? num_tiles : static_cast<uint32_t>(cached_max);
   if (pairs == 0) return 0;
   cfg.gridDim = dim3(pairs * CSZ);
-  // lockstep counters only pay off when several waves of tiles stream through L2
+  // lockstep counters only pay off when several rounds of tiles stream through L2 (pairs cannot drift apart
+  // within a single round, and the polling costs ~7 % there)
   p.sync_ctr = nullptr;
-  if (tune.sync_window > 0 && pairs > 1 && p.single_a == 0) {
+  if (tune.sync_window > 0 && pairs > 1 && num_tiles > pairs && p.single_a == 0) {
     const uint64_t steps = static_cast<uint64_t>(ceil_div_u32(num_tiles, pairs)) * (p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
     const uint64_t need = steps / kSyncEvery + 1;
     if (need <= kSyncCounters) {
