@@ -335,8 +335,10 @@ def run_ours(args) -> dict:
         int8_ops = s * (s + 1) / 2 * 2.0 * n * n * n
         peaks = measured_peaks()
         peak = 2.0 * peaks["bf16"]
+        traffic = ncu_traffic_bytes()
         roof = {"bound": "tensor", "achieved": int8_ops / kms / 1e9, "peak": peak, "unit": "TFLOP/s",
-                "frac": int8_ops / kms / 1e9 / peak, "traffic": ncu_traffic_bytes(),
+                "frac": int8_ops / kms / 1e9 / peak, "traffic": traffic,
+                "hbm_gbs": (traffic / (kms * 1e-3) / 1e9) if traffic else None, "hbm_peak_gbs": peaks["hbm"],
                 "kernel": "oz_gemm_pair_kernel<256,1,1>", "kernel_ms": kms, "launches_timed": len(durs),
                 "ops_per_launch": int8_ops,
                 "note": f"int8 TOP/s; peak = 2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']}); "
