@@ -249,7 +249,7 @@ def measured_peaks() -> dict:
 
 def ncu_traffic_bytes():
     """dram bytes per launch of the fused kernel from the committed ncu capture (profiles/), or None"""
-    p = ROOT / "profiles" / "r1_fused_pair256_8192.json"
+    p = ROOT / "profiles" / "r1_fused_pair256_bulk_8192.json"
     if p.exists():
         try:
             d = json.loads(p.read_text())
@@ -312,8 +312,8 @@ def run_ours(args) -> dict:
     if rank == 0:
         pitch = int(L.ozk_slice_pitch(n))
         bits = int(L.ozk_bits_per_int8(n))
-        a_sl = torch.empty(s * n * pitch, dtype=torch.int8, device="cuda")
-        b_sl = torch.empty(s * n * pitch, dtype=torch.int8, device="cuda")
+        a_sl = torch.empty(int(L.ozk_slices_bytes(n, n, s)), dtype=torch.int8, device="cuda")
+        b_sl = torch.empty(int(L.ozk_slices_bytes(n, n, s)), dtype=torch.int8, device="cuda")
         amax = torch.empty(n, dtype=torch.float64, device="cuda")
         bmax = torch.empty(n, dtype=torch.float64, device="cuda")
         scr = torch.zeros(n, dtype=torch.int32, device="cuda")

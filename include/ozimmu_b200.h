@@ -54,16 +54,21 @@ typedef struct ozimmu_handle_s *ozimmu_handle_t;                /* mtk::ozimmu::
 /* reference src/split.cu:520-536 get_bits_per_int8 */
 uint32_t ozk_bits_per_int8(uint32_t k);
 
-/* Row pitch (bytes == elements) of one int8 slice row for inner length k: k rounded up to a
- * multiple of 16 (TMA global strides must be 16-byte multiples).  The reference pads to 4
- * (src/utils.hpp:30-39); the padding is zero in both, so products are identical. */
+/* int8 slice layout shared by the split and GEMM kernels ("blocked SW128"): one operand is
+ * [num_split][row tile][k block][128 rows][128 bytes] -- every 128-row x 128-byte tile is 16 KB contiguous
+ * and pre-swizzled for shared memory (16-byte chunk c of row r sits at chunk c ^ (r & 7)), rows are padded
+ * to a multiple of 256 and k to a multiple of 128 with zeros.  (The reference keeps [slice][row][k4] and pads
+ * k to 4, src/utils.hpp:30-39; the padding is zero in both, so products are identical.)
+ * ozk_slice_pitch(k): k rounded up to 128.  ozk_slices_bytes: bytes of one operand. */
 size_t ozk_slice_pitch(size_t k);
+size_t ozk_slices_bytes(size_t rows, size_t k, unsigned num_split);
 
 /* reference src/split.cu:193-283 (split_int8_kernel + split_int8_A/split_int8):
  * per-"row" max exponent scan and FP64 -> num_split x int8 mantissa split.
  *   in        : rows x len view of op(X).  col_major != 0: element (r,c) = in[c*ld + r]
  *               (op_n A / op_t B), else in[r*ld + c] (op_t A / op_n B).
- *   out       : [num_split][rows][pitch] int8, K contiguous, bytes len..pitch-1 zero.
+ *   out       : ozk_slices_bytes(rows, len, num_split) bytes in the blocked layout above; pitch =
+ *               ozk_slice_pitch(len); all padding (rows up to a multiple of 256, k up to pitch) is zeroed.
  *   max_exp   : [rows] doubles, 2 * 2^(emax-1023) (reference :191,202-204,234-241).
  *   scratch   : [rows] uint32 device scratch (only used when col_major != 0).
  */
@@ -103,8 +108,8 @@ int ozk_gemm_i8_fused_complex(size_t m, size_t n, size_t k, const int8_t *a_slic
  * src/gemm.cu:143-147 applied to an all-zero accumulator). */
 int ozk_scale_c(size_t m, size_t n, double beta, double *c, size_t ldc, void *stream);
 
-/* Test/tuning hook: force the thread-block-cluster shape (cm x cn CTAs sharing TMA-multicast
- * operand tiles) of the fused kernel; (0,0) restores the built-in heuristic. */
+/* Test/tuning hook: force the tile width of the fused kernel: (0, 128) or (0, 256); anything else restores
+ * the per-problem choice. */
 int ozk_set_cluster_shape(int cm, int cn);
 
 /* Debug/verification launcher: the raw int32 product of ONE slice pair (1-based ids), written

@@ -21,6 +21,7 @@ c_size_t, c_int, c_uint, c_void_p, c_double = C.c_size_t, C.c_int, C.c_uint, C.c
 PROTOTYPES = {
     "ozk_bits_per_int8": (C.c_uint32, [C.c_uint32]),
     "ozk_slice_pitch": (c_size_t, [c_size_t]),
+    "ozk_slices_bytes": (c_size_t, [c_size_t, c_size_t, c_uint]),
     "ozk_split_int8": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t,
                                c_int, c_uint, c_uint, c_void_p]),
     "ozk_split_int8_strided": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t,

@@ -137,7 +137,7 @@ void gemm_int8_complex(handle_t h, operation_t op_a, operation_t op_b, std::size
   if (m == 0 || n == 0) return;
   if (k == 0) throw std::runtime_error("ozIMMU: complex GEMM with k == 0 is not implemented");
   const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
-  const H::WorkspaceLayout w = H::workspace_layout(2 * m, 2 * n, k, num_split);  // two planes per operand
+  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split, 2);  // two planes per operand
   reallocate_working_memory(h, w.total);
   ensure_streams(h);
   char *ws = static_cast<char *>(h->working_memory_ptr);
@@ -147,8 +147,7 @@ void gemm_int8_complex(handle_t h, operation_t op_a, operation_t op_b, std::size
   auto *scr_b = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_b);
   auto *a_sl = reinterpret_cast<std::int8_t *>(ws + w.off_a_slices);
   auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
-  const std::size_t a_plane = static_cast<std::size_t>(num_split) * m * w.pitch;
-  const std::size_t b_plane = static_cast<std::size_t>(num_split) * n * w.pitch;
+  const std::size_t a_plane = w.a_plane, b_plane = w.b_plane;
   cudaStream_t s = h->cuda_stream;
   wait_previous(h, s);
   const int a_col_major = (op_a == op_n), b_col_major = (op_b != op_n);
@@ -294,8 +293,7 @@ std::size_t mtk::ozimmu::reallocate_working_memory(handle_t h, const gemm_list_t
     if (H::is_int8_mode(mode)) s = H::num_split_of(mode);
     else if (mode == fp64_int8_auto) s = 18;
     if (s == 0) continue;
-    const std::size_t planes = kind == complx ? 2 : 1;
-    const std::size_t bytes = H::workspace_layout(planes * m, planes * n, k, s).total;
+    const std::size_t bytes = H::workspace_layout(m, n, k, s, kind == complx ? 2 : 1).total;
     need = std::max(need, bytes);
   }
   return reallocate_working_memory(h, need);

@@ -55,11 +55,13 @@ struct StageProfiler {
 // (src/gemm.cu:359-379) also holds an m*n FP64 accumulator and an m*n int32 product buffer;
 // the fused kernel needs neither.
 struct WorkspaceLayout {
-  std::size_t pitch;       // bytes per slice row
+  std::size_t pitch;       // bytes of K per slice row (k rounded up to 128)
+  std::size_t a_plane, b_plane;  // bytes of one operand plane (all slices; blocked layout, rows padded to 256)
   std::size_t off_amax, off_bmax, off_scr_a, off_scr_b, off_a_slices, off_b_slices;
   std::size_t total;
 };
-WorkspaceLayout workspace_layout(std::size_t m, std::size_t n, std::size_t k, unsigned num_split);
+// planes = 1 (real) or 2 (complex: real and imaginary planes of each operand, back to back)
+WorkspaceLayout workspace_layout(std::size_t m, std::size_t n, std::size_t k, unsigned num_split, unsigned planes = 1);
 
 inline bool is_int8_mode(mtk::ozimmu::compute_mode_t mode) {
   return mode >= mtk::ozimmu::fp64_int8_3 && mode <= mtk::ozimmu::fp64_int8_18;

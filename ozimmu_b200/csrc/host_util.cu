@@ -143,16 +143,18 @@ namespace {
 std::size_t align_up(std::size_t v, std::size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
-WorkspaceLayout workspace_layout(std::size_t m, std::size_t n, std::size_t k, unsigned num_split) {
+WorkspaceLayout workspace_layout(std::size_t m, std::size_t n, std::size_t k, unsigned num_split, unsigned planes) {
   WorkspaceLayout w{};
   w.pitch = slice_pitch(k);
+  w.a_plane = slices_bytes(m, k, num_split);
+  w.b_plane = slices_bytes(n, k, num_split);
   std::size_t off = 0;
-  w.off_amax = off;      off = align_up(off + sizeof(double) * m, 256);
-  w.off_bmax = off;      off = align_up(off + sizeof(double) * n, 256);
-  w.off_scr_a = off;     off = align_up(off + sizeof(std::uint32_t) * m, 256);
-  w.off_scr_b = off;     off = align_up(off + sizeof(std::uint32_t) * n, 256);
-  w.off_a_slices = off;  off = align_up(off + static_cast<std::size_t>(num_split) * m * w.pitch, 1024);
-  w.off_b_slices = off;  off = align_up(off + static_cast<std::size_t>(num_split) * n * w.pitch, 1024);
+  w.off_amax = off;      off = align_up(off + sizeof(double) * m * planes, 256);
+  w.off_bmax = off;      off = align_up(off + sizeof(double) * n * planes, 256);
+  w.off_scr_a = off;     off = align_up(off + sizeof(std::uint32_t) * m * planes, 256);
+  w.off_scr_b = off;     off = align_up(off + sizeof(std::uint32_t) * n * planes, 256);
+  w.off_a_slices = off;  off = align_up(off + w.a_plane * planes, 1024);
+  w.off_b_slices = off;  off = align_up(off + w.b_plane * planes, 1024);
   w.total = off;
   return w;
 }

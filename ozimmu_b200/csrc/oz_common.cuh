@@ -13,8 +13,23 @@ constexpr uint64_t kMantMask = 0x000FFFFFFFFFFFFFull;  // binary64 fraction fiel
 extern unsigned long long g_launch_count;
 inline void count_launch(unsigned n = 1) { g_launch_count += n; }
 
-// k rounded up to 16: TMA needs 16-byte global strides.
-inline size_t slice_pitch(size_t k) { return (k + 15) / 16 * 16; }
+// ---- int8 slice layout ("blocked SW128") -------------------------------------------------------
+// One operand plane is [slice][row tile][k block][128 rows][128 bytes]: every 128-row x 128-byte tile is
+// 16 KB CONTIGUOUS in HBM and already carries the shared-memory 128-byte swizzle (16-byte chunk c of row r
+// sits at chunk c ^ (r & 7)), so the GEMM kernel stages a tile with ONE linear bulk copy
+// (cp.async.bulk, 54-76 B/clk/SM measured) instead of a tiled TMA box of 128 separate rows (33-48 B/clk/SM;
+// profiles/r1_ubench_sm_ingest.txt, r1_ubench_bulk_pair.txt).  Rows are padded to a multiple of 256 (one CTA
+// pair's 2 x 128 rows), k to a multiple of 128; padding is zero.
+constexpr size_t kTileRows = 128, kTileK = 128, kTileBytes = kTileRows * kTileK;
+inline size_t slice_pitch(size_t k) { return (k + kTileK - 1) / kTileK * kTileK; }              // bytes of K per row
+__host__ __device__ inline size_t slice_row_tiles(size_t rows) { return (rows + 255) / 256 * 2; }  // 128-row tiles
+inline size_t slices_bytes(size_t rows, size_t k, unsigned num_split) {
+  return static_cast<size_t>(num_split) * slice_row_tiles(rows) * kTileRows * slice_pitch(k);
+}
+// byte offset of the 16-byte chunk holding k positions [16*g, 16*g + 16) of row r inside one slice plane
+__host__ __device__ inline size_t slice_chunk_offset(size_t r, size_t g, size_t k_blocks) {
+  return ((r >> 7) * k_blocks + (g >> 3)) * kTileBytes + (r & 127) * kTileK + (((g & 7) ^ (r & 7)) << 4);
+}
 
 __host__ __device__ inline uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 

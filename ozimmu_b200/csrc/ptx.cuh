@@ -107,6 +107,13 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
   return v;
 }
 
+// same without the release fence (the ERRBAR/MEMBAR of a .release arrive costs ~1 us): for hand-offs whose
+// payload was written by the async proxy and already observed complete through an mbarrier (the relay of the
+// pair kernel), so there is no generic-proxy write of this thread to publish
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -132,6 +139,12 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap *
       : "memory");
 }
 
+// Linear bulk copy global -> this CTA's SMEM (no tensor map): `bytes` (multiple of 16, 16-byte aligned source)
+// are credited to `bar`, which must live in the destination CTA.
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 // CTA-pair variant: the box lands in this CTA's SMEM, the bytes are credited to `bar`, which may
 // live in the peer (leader) CTA -- `bar` is a shared::cluster address.
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap *m, uint32_t bar,

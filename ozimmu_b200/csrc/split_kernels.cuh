@@ -15,8 +15,8 @@
 //  * no device synchronisation (the reference calls cudaDeviceSynchronize per split,
 //    src/split.cu:261).
 //
-// Output layout: out[slice][row][pitch] int8, K contiguous, pitch = k rounded up to 16,
-// padding bytes zero -- the K-major layout the tcgen05 kernel's TMA descriptors expect.
+// Output layout: the blocked, pre-swizzled [slice][row tile][k block][128][128] layout of oz_common.cuh
+// (slice_chunk_offset); pitch = k rounded up to 128, rows padded to 256, padding zero.
 #pragma once
 #include "oz_common.cuh"
 #include "ozimmu_b200.h"
@@ -172,8 +172,8 @@ split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
   const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
   if (threadIdx.x == 0) max_exp[row] = mx;
 
-  const size_t slice_stride = rows * pitch;
-  int8_t *__restrict__ dst = out + row * pitch;
+  const size_t slice_stride = slice_row_tiles(rows) * kTileRows * pitch;
+  const size_t kblocks = pitch / kTileK;
   const uint32_t ngroups = static_cast<uint32_t>(pitch / 16);
   for (uint32_t g = threadIdx.x; g < ngroups; g += kSplitThreads) {
     double v[16];
@@ -192,7 +192,7 @@ split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
     for (int t = 0; t < S; t++) {
       uint4 q = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
       // elements >= len are exact zeros => their slice bytes are already 0
-      *reinterpret_cast<uint4 *>(dst + t * slice_stride + g * 16) = q;
+      *reinterpret_cast<uint4 *>(out + t * slice_stride + slice_chunk_offset(row, g, kblocks)) = q;
     }
   }
 }
@@ -248,8 +248,8 @@ split_rows_reg_kernel(int8_t *__restrict__ out, const size_t pitch, double *__re
   const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
   if (threadIdx.x == 0) max_exp[row] = mx;
 
-  const size_t slice_stride = rows * pitch;
-  int8_t *__restrict__ dst = out + row * pitch;
+  const size_t slice_stride = slice_row_tiles(rows) * kTileRows * pitch;
+  const size_t kblocks = pitch / kTileK;
   const uint32_t ngroups = static_cast<uint32_t>(pitch / 16);
 #pragma unroll
   for (int gi = 0; gi < GROUPS; gi++) {
@@ -257,9 +257,10 @@ split_rows_reg_kernel(int8_t *__restrict__ out, const size_t pitch, double *__re
     if (g < ngroups) {
       uint32_t w[S][4];
       cut16_any<S>(v[gi], mx_bits, L, w);
+      int8_t *__restrict__ dst = out + slice_chunk_offset(row, g, kblocks);
 #pragma unroll
       for (int t = 0; t < S; t++)
-        *reinterpret_cast<uint4 *>(dst + t * slice_stride + g * 16) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+        *reinterpret_cast<uint4 *>(dst + t * slice_stride) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
     }
   }
 }
@@ -321,8 +322,8 @@ split_cols_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
   const size_t gr = static_cast<size_t>(blockIdx.x) * kColsRows + orow;
   const uint32_t gk = kbase + chunk * 16;
   if (gr < rows && gk < pitch) {
-    const size_t slice_stride = rows * pitch;
-    int8_t *__restrict__ dst = out + gr * pitch + gk;
+    const size_t slice_stride = slice_row_tiles(rows) * kTileRows * pitch;
+    int8_t *__restrict__ dst = out + slice_chunk_offset(gr, gk >> 4, pitch / kTileK);
 #pragma unroll
     for (int t = 0; t < S; t++)
       *reinterpret_cast<uint4 *>(dst + t * slice_stride) = s_out[(t * kColsRows + orow) * 8 + (chunk ^ (orow & 7))];

@@ -35,17 +35,57 @@ def ulp_distance(x, y) -> int:
     return int(d.max()) if d.size else 0
 
 
+def blocked_index(rows: int, pitch: int) -> np.ndarray:
+    """byte offset inside one slice plane of element (r, c) in the blocked, pre-swizzled slice layout
+    (include/ozimmu_b200.h): [row tile][k block][128 rows][128 B], 16-byte chunk c16 of row r at c16 ^ (r & 7)"""
+    r = np.arange(rows, dtype=np.int64)[:, None]
+    c = np.arange(pitch, dtype=np.int64)[None, :]
+    kb = pitch // 128
+    g = c >> 4
+    return ((r >> 7) * kb + (g >> 3)) * 16384 + (r & 127) * 128 + (((g & 7) ^ (r & 7)) << 4) + (c & 15)
+
+
+def plane_bytes(rows: int, pitch: int) -> int:
+    return ((rows + 255) // 256) * 256 * pitch
+
+
+def unblock(buf: np.ndarray, num_split: int, rows: int, pitch: int) -> np.ndarray:
+    """flat blocked int8 buffer -> [num_split, rows, pitch]; also checks that all padding rows are zero"""
+    plane = plane_bytes(rows, pitch)
+    b = np.ascontiguousarray(buf).reshape(-1).view(np.int8)[:num_split * plane].reshape(num_split, plane)
+    idx = blocked_index(rows, pitch)
+    out = b[:, idx.reshape(-1)].reshape(num_split, rows, pitch)
+    mask = np.ones(plane, dtype=bool)
+    mask[idx.reshape(-1)] = False
+    assert not b[:, mask].any(), "row padding of the slice planes must be zero"
+    return out
+
+
+def block(slices: np.ndarray, pitch: int) -> np.ndarray:
+    """[num_split, rows, k] int8 -> flat blocked buffer (zero padded)"""
+    s, rows, k = slices.shape
+    plane = plane_bytes(rows, pitch)
+    padded = np.zeros((s, rows, pitch), dtype=np.int8)
+    padded[:, :, :k] = slices
+    out = np.zeros((s, plane), dtype=np.int8)
+    out[:, blocked_index(rows, pitch).reshape(-1)] = padded.reshape(s, -1)
+    return out.reshape(-1)
+
+
 def split_product(x: torch.Tensor, ld: int, rows: int, length: int, col_major: bool, num_split: int, bits_: int):
-    """ozk_split_int8 -> (slices[num_split, rows, pitch] int8 tensor, max_exp[rows] tensor)"""
+    """ozk_split_int8 -> (slices[num_split, rows, pitch] int8 numpy array in plain layout, max_exp[rows] tensor)"""
     L = oz.lib()
     pitch = int(L.ozk_slice_pitch(length))
-    out = torch.full((num_split, rows, pitch), 77, dtype=torch.int8, device="cuda")
+    nbytes = int(L.ozk_slices_bytes(rows, length, num_split))
+    assert nbytes == num_split * plane_bytes(rows, pitch)
+    out = torch.full((nbytes,), 77, dtype=torch.int8, device="cuda")
     mx = torch.full((rows,), -1.0, dtype=torch.float64, device="cuda")
     scratch = torch.zeros(max(rows, 1), dtype=torch.int32, device="cuda")
     rc = L.ozk_split_int8(out.data_ptr(), pitch, mx.data_ptr(), scratch.data_ptr(), rows, length, x.data_ptr(), ld,
                           int(col_major), num_split, bits_, stream_ptr())
     assert rc == 0, f"ozk_split_int8 -> {rc}"
-    return out, mx
+    torch.cuda.synchronize()
+    return unblock(out.cpu().numpy(), num_split, rows, pitch), mx
 
 
 class Reference:

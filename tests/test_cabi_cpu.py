@@ -52,7 +52,7 @@ def test_kernels_are_blackwell_native():
     out = subprocess.run(["cuobjdump", "-sass", str(oz.LIB_PATH)], capture_output=True, text=True)
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
-    for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG", "UTMAPF"):
+    for mnemonic in ("UTCIMMA", "LDTM", "UBLKCP"):
         assert mnemonic in out.stdout, mnemonic
 
 
@@ -64,7 +64,10 @@ def test_mode_names_and_sizes():
         assert oz.get_compute_mode_name_str(oz.fp64_int8(s)) == f"fp64_int8_{s}"
         assert oz.num_split_of(oz.fp64_int8(s)) == s
     assert oz.lib().ozimmu_get_compute_mode_name_str(77) is None
-    assert int(oz.lib().ozk_slice_pitch(1)) == 16 and int(oz.lib().ozk_slice_pitch(4097)) == 4112
+    assert int(oz.lib().ozk_slice_pitch(1)) == 128 and int(oz.lib().ozk_slice_pitch(4097)) == 4224
+    # blocked slice layout: rows padded to 256, k to 128
+    assert int(oz.lib().ozk_slices_bytes(1, 1, 9)) == 9 * 256 * 128
+    assert int(oz.lib().ozk_slices_bytes(8192, 8192, 9)) == 9 * 8192 * 8192
 
 
 def test_invalid_arguments_rejected_without_gpu():
@@ -75,8 +78,9 @@ def test_invalid_arguments_rejected_without_gpu():
     assert lib.ozimmu_gemm_host(None, 0, 0, 8, 8, 8, C.addressof(one), None, 8, None, 8, C.addressof(one), None, 8, 8) == 1
     # kernel launchers validate before touching the device
     assert lib.ozk_split_int8(None, 17, None, None, 4, 4, None, 4, 0, 9, 7, None) != 0   # pitch % 16
-    assert lib.ozk_split_int8(None, 16, None, None, 4, 4, None, 4, 0, 2, 7, None) != 0   # num_split < 3
-    assert lib.ozk_gemm_i8_fused(8, 8, 8, None, None, 16, None, None, 19, 7, 1.0, 0.0, None, 8, None) != 0
-    assert lib.ozk_gemm_i8_fused(8, 8, 8, None, None, 16, None, None, 9, 7, 1.0, 0.0, None, 4, None) != 0  # ldc < m
-    assert lib.ozk_gemm_i8_fused(0, 8, 8, None, None, 16, None, None, 9, 7, 1.0, 0.0, None, 1, None) == 0  # empty
+    assert lib.ozk_split_int8(None, 128, None, None, 4, 4, None, 4, 0, 2, 7, None) != 0  # num_split < 3
+    assert lib.ozk_gemm_i8_fused(8, 8, 8, None, None, 128, None, None, 19, 7, 1.0, 0.0, None, 8, None) != 0
+    assert lib.ozk_gemm_i8_fused(8, 8, 8, None, None, 128, None, None, 9, 7, 1.0, 0.0, None, 4, None) != 0  # ldc < m
+    assert lib.ozk_gemm_i8_fused(8, 8, 8, None, None, 16, None, None, 9, 7, 1.0, 0.0, None, 8, None) != 0   # pitch % 128
+    assert lib.ozk_gemm_i8_fused(0, 8, 8, None, None, 128, None, None, 9, 7, 1.0, 0.0, None, 1, None) == 0  # empty
     assert lib.ozimmu_launch_count() == 0

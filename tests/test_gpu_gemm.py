@@ -194,14 +194,14 @@ def test_headline_8192_bit_exact_vs_reference(ref, handle):
         f"max ulp distance {ulp_distance(c_ref, c_new)}"
 
 
-@pytest.mark.parametrize("shape", [(0, 256), (0, 192), (0, 128), (100, 21), (100, 12), (100, 22), (2, 1), (1, 2), (2, 2)])
+@pytest.mark.parametrize("shape", [(0, 256), (0, 128)])
 def test_cluster_shapes_same_bits(handle, shape):
     m, n, k = 1000, 900, 2050
     a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 1))
     b = to_dev(oracle_lib.gen_matrix("exp_rand-1", k * n, 2))
     c0 = torch.zeros(m * n, dtype=torch.float64, device="cuda")
     c1 = torch.zeros_like(c0)
-    oz.lib().ozk_set_cluster_shape(1, 1)
+    oz.lib().ozk_set_cluster_shape(0, 0)
     assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c0, m, oz.fp64_int8(9)) == 0
     oz.lib().ozk_set_cluster_shape(*shape)
     try:

@@ -6,7 +6,7 @@ import torch
 
 import oracle_lib
 import ozimmu_b200 as oz
-from gpu_util import bits, split_product, stream_ptr, to_dev
+from gpu_util import bits, block, split_product, stream_ptr, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -23,8 +23,6 @@ def test_split_matches_oracle(col_major, rows, length, ld_extra, kind, num_split
     L = oz.lib().ozk_bits_per_int8(length)
     want, want_mx = oracle_lib.oracle_split(x, ld, rows, length, col_major, num_split, L)
     got, got_mx = split_product(to_dev(x), ld, rows, length, col_major, num_split, L)
-    torch.cuda.synchronize()
-    got = got.cpu().numpy()
     assert np.array_equal(bits(got_mx), bits(want_mx))
     assert np.array_equal(got[:, :, :length], want[:, :, :length])
     assert not got[:, :, length:].any(), "padding bytes must be zero"
@@ -44,14 +42,12 @@ def test_split_special_rows():
         ld = rows if col_major else length
         want, want_mx = oracle_lib.oracle_split(store, ld, rows, length, col_major, 9, 7)
         got, got_mx = split_product(to_dev(store), ld, rows, length, col_major, 9, 7)
-        torch.cuda.synchronize()
         assert np.array_equal(bits(got_mx), bits(want_mx))
-        assert np.array_equal(got.cpu().numpy()[:, :, :length], want[:, :, :length])
+        assert np.array_equal(got[:, :, :length], want[:, :, :length])
 
 
-# (0, BN): CTA-pair kernel (cta_group::2) with BN columns; (100, PM PN): the same with BN=192 in a PM x PN
-# multicast cluster of pairs; (cm, cn): single-CTA kernel, cm x cn multicast cluster
-@pytest.mark.parametrize("shape", [(0, 256), (0, 192), (0, 128), (100, 21), (100, 12), (100, 22), (1, 1), (2, 1), (1, 2), (2, 2)])
+# (0, BN): force the CTA-pair kernel's tile width; (0, 0): per-problem choice
+@pytest.mark.parametrize("shape", [(0, 256), (0, 128), (0, 0)])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 384, 512), (100, 60, 70), (513, 259, 1031), (1, 1, 1),
                                    (1025, 1023, 1024)])
 def test_int8_pair_product_exact(shape, m, n, k):
@@ -61,11 +57,9 @@ def test_int8_pair_product_exact(shape, m, n, k):
     rng = np.random.default_rng(m * 31 + n * 17 + k)
     pitch = int(L.ozk_slice_pitch(k))
     s = 3
-    a = np.zeros((s, m, pitch), dtype=np.int8)
-    b = np.zeros((s, n, pitch), dtype=np.int8)
-    a[:, :, :k] = rng.integers(-127, 128, size=(s, m, k), dtype=np.int8)
-    b[:, :, :k] = rng.integers(-127, 128, size=(s, n, k), dtype=np.int8)
-    da, db = to_dev(a), to_dev(b)
+    a = rng.integers(-127, 128, size=(s, m, k), dtype=np.int8)
+    b = rng.integers(-127, 128, size=(s, n, k), dtype=np.int8)
+    da, db = to_dev(block(a, pitch)), to_dev(block(b, pitch))
     out = torch.full((n, m), 12345, dtype=torch.int32, device="cuda")  # column-major m x n, ld = m
     L.ozk_set_cluster_shape(*shape)
     try:

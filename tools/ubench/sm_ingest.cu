@@ -47,8 +47,9 @@ ingest(const uint8_t *__restrict__ g, uint32_t chunks_in_buffer, uint32_t iters_
         const uint8_t *src = g + static_cast<size_t>(c % chunks_in_buffer) * kChunk;
         c += 13;
         if (mode & 4) {  // tiled TMA box of 128 B x 128 rows (what the GEMM kernel issues)
-          const uint32_t t = c % (tiles_x * tiles_y);
-          const int cx = static_cast<int>((t % tiles_x) * 128), cy = static_cast<int>((t / tiles_x) * 128);
+          const uint32_t ty = tiles_y & 0xFFFFu, bx = (tiles_y >> 16) & 0xFFu ? ((tiles_y >> 16) & 0xFFu) : 256u, by = tiles_y >> 24;
+          const uint32_t t = c % (tiles_x * ty);
+          const int cx = static_cast<int>((t % tiles_x) * bx), cy = static_cast<int>((t / tiles_x) * by);
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                        ::"r"(base + slot * kChunk), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(bar), "r"(cx), "r"(cy) : "memory");
         } else {
@@ -113,24 +114,26 @@ int main() {
   cudaDriverEntryPointQueryResult q;
   cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q);
   EncodeFn enc = reinterpret_cast<EncodeFn>(fp);
-  struct Shape { const char *name; cuuint64_t inner, rows; } shapes[] = {
-      {"tiled TMA, matrix [8192 rows][8192 B] (row stride 8 KB, the GEMM's slice layout)", 8192, 8192},
-      {"tiled TMA, matrix [524288 rows][128 B] (each 128x128 B box is one contiguous 16 KB)", 128, 524288},
-      {"tiled TMA, matrix [2048 rows][32768 B] (row stride 32 KB)", 32768, 2048}};
+  struct Shape { const char *name; cuuint64_t inner, rows; CUtensorMapDataType dt; cuuint32_t esz, bx, by; CUtensorMapSwizzle sw; } shapes[] = {
+      {"tiled TMA u8 box 128 B x 128 rows SW128, matrix [8192][8192 B]", 8192, 8192, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B},
+      {"tiled TMA u8 box 128 B x 128 rows SW128, matrix [524288][128 B] (contiguous 16 KB)", 128, 524288, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B},
+      {"tiled TMA u64 box 2 KB x 8 rows no swizzle, matrix [32768][2 KB] (contiguous 16 KB)", 256, 32768, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, 256, 8, CU_TENSOR_MAP_SWIZZLE_NONE},
+      {"tiled TMA u32 box 1 KB x 16 rows no swizzle, matrix [65536][1 KB] (contiguous 16 KB)", 256, 65536, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, 256, 16, CU_TENSOR_MAP_SWIZZLE_NONE},
+      {"tiled TMA u8 box 256 B x 64 rows no swizzle, matrix [262144][256 B] (contiguous 16 KB)", 256, 262144, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 256, 64, CU_TENSOR_MAP_SWIZZLE_NONE}};
   for (auto &sh : shapes) {
     CUtensorMap tm;
     cuuint64_t dims[2] = {sh.inner, sh.rows};
-    cuuint64_t strides[1] = {sh.inner};
-    cuuint32_t box[2] = {128, 128}, es[2] = {1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, g, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t strides[1] = {sh.inner * sh.esz};
+    cuuint32_t box[2] = {sh.bx, sh.by}, es[2] = {1, 1};
+    CUresult r = enc(&tm, sh.dt, 2, g, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     sh.sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); continue; }
     for (int rep = 0; rep < 2; rep++) {
       cudaMemset(out, 0, sizeof(unsigned long long) * 4 * 256);
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaEventRecord(e0);
-      ingest<<<grid, 288, kSmem>>>(g, chunks, 6000, 0, 5, out, tm, static_cast<uint32_t>(sh.inner / 128), static_cast<uint32_t>(sh.rows / 128));
+      ingest<<<grid, 288, kSmem>>>(g, chunks, 6000, 0, 5, out, tm, static_cast<uint32_t>(sh.inner / sh.bx), static_cast<uint32_t>(sh.rows / sh.by) | (sh.bx << 16) | (sh.by << 24));
       cudaEventRecord(e1);
       cudaError_t err = cudaDeviceSynchronize();
       float ms; cudaEventElapsedTime(&ms, e0, e1);
