@@ -69,6 +69,7 @@ struct FusedParams {
   uint32_t *sync_ctr;          // one arrival counter per kSyncEvery k-steps, zeroed before launch (or null)
   uint32_t sync_window;        // a pair starts sync interval j only after interval j - window is complete
   uint32_t sync_len;           // counters available
+  uint32_t prefetch_ahead;     // k-steps of L2 prefetch lead (OZIMMU_B200_PREFETCH, 0 = off)
 };
 
 // reference src/config.cu:85-92: for sum = 2..s+1, for j = 1..sum-1: (A_id=j, B_id=sum-j)
@@ -215,7 +216,25 @@ oz_gemm_pair_kernel(const FusedParams p) {
           const int8_t *a_src = p.a_slices + ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
           const int8_t *b_src =
               p.b_slices + ((it.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
+          // optional L2 prefetch `prefetch_ahead` k-steps ahead (into the next product of this tile if needed)
+          PairIter nx = it;
+          nx.next();
+          const int8_t *a_nx = nullptr, *b_nx = nullptr;
+          if (p.prefetch_ahead && nx.valid()) {
+            a_nx = p.a_slices + ((nx.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
+            b_nx = p.b_slices + ((nx.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
+          }
           for (uint32_t kb = 0; kb < p.k_blocks; kb++, g++) {
+            if (p.prefetch_ahead && issuer) {
+              const uint32_t kf = kb + p.prefetch_ahead;
+              if (kf < p.k_blocks) {
+                ptx::bulk_prefetch_l2(a_src + static_cast<size_t>(kf) * kTileBytes, BM * BK);
+                ptx::bulk_prefetch_l2(b_src + static_cast<size_t>(kf) * kTileBytes, Cfg::kBBytes);
+              } else if (a_nx != nullptr && kf - p.k_blocks < p.k_blocks) {
+                ptx::bulk_prefetch_l2(a_nx + static_cast<size_t>(kf - p.k_blocks) * kTileBytes, BM * BK);
+                ptx::bulk_prefetch_l2(b_nx + static_cast<size_t>(kf - p.k_blocks) * kTileBytes, Cfg::kBBytes);
+              }
+            }
             if (lockstep && (g % kSyncEvery) == 0) {
               const uint32_t j = g / kSyncEvery;
               if (j >= p.sync_len) {
@@ -446,6 +465,15 @@ uint32_t lockstep_window() {
   return w;
 }
 
+uint32_t prefetch_ahead() {
+  static const uint32_t v = [] {
+    uint32_t x = 0;
+    if (const char *e = std::getenv("OZIMMU_B200_PREFETCH")) x = static_cast<uint32_t>(std::atoi(e));
+    return x > 64 ? 64u : x;
+  }();
+  return v;
+}
+
 constexpr uint32_t kSyncCounters = 1u << 16;  // per buffer: 64 Ki intervals = 1 Mi k-steps per CTA pair
 constexpr int kSyncBuffers = 8;               // launches that may be in flight at once without sharing
 uint32_t *next_sync_buffer() {
@@ -480,6 +508,7 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   p.rt_a = static_cast<uint32_t>(slice_row_tiles(p.m));
   p.rt_b = static_cast<uint32_t>(slice_row_tiles(p.n));
   p.sync_window = lockstep_window();
+  p.prefetch_ahead = prefetch_ahead();
 
   auto kern = oz_gemm_pair_kernel<BN_>;
   int dev = 0, sms = 0;

@@ -145,6 +145,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// pull `bytes` of global memory into L2 (no SMEM, no barrier)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // CTA-pair variant: the box lands in this CTA's SMEM, the bytes are credited to `bar`, which may
 // live in the peer (leader) CTA -- `bar` is a shared::cluster address.
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap *m, uint32_t bar,
