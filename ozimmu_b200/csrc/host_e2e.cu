@@ -13,6 +13,7 @@
 // Results are bit-identical to the one-shot path: a column panel of C depends only on A and the
 // same columns of op(B), and the split scales B per column (reference src/split.cu:277-282).
 #include <algorithm>
+#include <cstdlib>
 
 #include "host.hpp"
 #include "oz_common.cuh"
@@ -104,9 +105,15 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
 
   const unsigned s = H::num_split_of(mode);
   const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
-  // column panels of C: multiples of 128 columns, at most kMaxPanels, roughly 2048 wide
-  std::size_t panels = std::min<std::size_t>(handle::kMaxPanels, std::max<std::size_t>(1, n / 2048));
-  std::size_t pw = ((n + panels - 1) / panels + 127) / 128 * 128;
+  // column panels of C: multiples of 256 columns (the kernel's tile width), at most kMaxPanels, roughly
+  // `target` wide (OZIMMU_B200_E2E_PANEL, default 1024)
+  static const std::size_t target = [] {
+    const char *e = std::getenv("OZIMMU_B200_E2E_PANEL");
+    const long v = e ? std::atol(e) : 0;
+    return static_cast<std::size_t>(v >= 256 ? v : 1024);
+  }();
+  std::size_t panels = std::min<std::size_t>(handle::kMaxPanels, std::max<std::size_t>(1, n / target));
+  std::size_t pw = ((n + panels - 1) / panels + 255) / 256 * 256;
   panels = (n + pw - 1) / pw;
 
   // workspace: A slices for all of A, B slices for one panel

@@ -1,0 +1,27 @@
+"""Times ozimmu_gemm_host (host operands, pinned) at n^3: python tools/e2e_probe.py [n]"""
+import sys, time
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import ozimmu_b200 as oz
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+a = torch.rand(n * n, dtype=torch.float64).pin_memory()
+b = torch.rand(n * n, dtype=torch.float64).pin_memory()
+c = torch.zeros(n * n, dtype=torch.float64).pin_memory()
+h = oz.create()
+for _ in range(2):
+    oz.gemm_host(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(9))
+t0 = time.perf_counter()
+it = 5
+for _ in range(it):
+    oz.gemm_host(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(9))
+dt = (time.perf_counter() - t0) / it
+print(f"gemm_host n={n}: {dt*1e3:.2f} ms  {2*n**3/dt/1e12:.2f} TFLOP/s-equiv")
+# raw PCIe numbers for context
+d = torch.empty(n * n, dtype=torch.float64, device="cuda")
+torch.cuda.synchronize(); t0 = time.perf_counter(); d.copy_(a, non_blocking=True); torch.cuda.synchronize()
+print(f"H2D {n*n*8/2**20:.0f} MiB: {(time.perf_counter()-t0)*1e3:.2f} ms")
+t0 = time.perf_counter(); c.copy_(d, non_blocking=True); torch.cuda.synchronize()
+print(f"D2H {n*n*8/2**20:.0f} MiB: {(time.perf_counter()-t0)*1e3:.2f} ms")
+oz.destroy(h)
