@@ -83,6 +83,16 @@ int ozk_split_int8_strided(int8_t *out, size_t pitch, double *max_exp, uint32_t 
                            size_t len, const double *in, size_t ld, int col_major, unsigned num_split,
                            unsigned bits_per_int8, unsigned elem_stride, void *stream);
 
+/* Row block [row0, row0 + rows) of an operand whose slice planes hold plane_rows rows (the host-operand
+ * pipeline splits blocks of A / B as they arrive over PCIe; the split scales every row on its own, reference
+ * src/split.cu:193-242, so a block-wise split is bit-identical to a whole-matrix one).  out = base of the
+ * operand's slices; max_exp / scratch / in point at row row0's entries.  row0 must be a multiple of 256 and
+ * the block must end on a multiple of 256 or at plane_rows; the block that ends the plane zeroes the padding. */
+int ozk_split_int8_block(int8_t *out, size_t pitch, size_t plane_rows, size_t row0, double *max_exp,
+                         uint32_t *scratch, size_t rows, size_t len, const double *in, size_t ld,
+                         int col_major, unsigned num_split, unsigned bits_per_int8, unsigned elem_stride,
+                         void *stream);
+
 /* reference src/gemm.cu:266-334 (matmul_core -> cublasGemmEx int8) + :77-102
  * (accumulate_in_f64) + :104-122 (init_accumulator_buffer) + :124-158 (axby), fused:
  * for every (i,j) of the reference pair order (src/config.cu:85-92) an exact
@@ -94,6 +104,17 @@ int ozk_gemm_i8_fused(size_t m, size_t n, size_t k, const int8_t *a_slices, cons
                       size_t pitch, const double *amax, const double *bmax, unsigned num_split,
                       unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
                       void *stream);
+
+/* ozk_gemm_i8_fused on the m x n block of C whose first element is (row0, col0) (both multiples of 256):
+ * a_slices / b_slices are the bases of operands split for a_plane_rows / b_plane_rows rows, amax / bmax / c
+ * point at the block's first entries.  flags: OZK_FUSED_NO_LOCKSTEP = do not pace the CTA pairs against
+ * each other (for launches that share the GPU with another launch). */
+#define OZK_FUSED_NO_LOCKSTEP 1u
+int ozk_gemm_i8_fused_block(size_t m, size_t n, size_t k, const int8_t *a_slices, size_t a_plane_rows,
+                            size_t row0, const int8_t *b_slices, size_t b_plane_rows, size_t col0,
+                            size_t pitch, const double *amax, const double *bmax, unsigned num_split,
+                            unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
+                            unsigned flags, void *stream);
 
 /* One of the four real products of a complex GEMM (reference src/gemm.cu:479-518 loop body +
  * :160-186 axy_complex + :188-239 init_c_complex): x = the fp64_int8 product of the given planes,

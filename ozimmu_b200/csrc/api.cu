@@ -229,12 +229,20 @@ int mtk::ozimmu::destroy(handle_t h) {
   cudaFree(h->stage_c);
   for (cudaStream_t s : {h->aux_stream, h->h2d_stream, h->d2h_stream, h->compute_stream})
     if (s) cudaStreamDestroy(s);
-  for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_done, h->ev_a_in})
+  for (cudaStream_t s : h->product_stream)
+    if (s) cudaStreamDestroy(s);
+  for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_done})
     if (e) cudaEventDestroy(e);
-  for (int i = 0; i < handle::kMaxPanels; i++) {
-    if (h->ev_panel_in[i]) cudaEventDestroy(h->ev_panel_in[i]);
-    if (h->ev_panel_out[i]) cudaEventDestroy(h->ev_panel_out[i]);
-  }
+  for (auto &row : h->ev_block_in)
+    for (cudaEvent_t e : row)
+      if (e) cudaEventDestroy(e);
+  for (auto &row : h->ev_block_split)
+    for (cudaEvent_t e : row)
+      if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_rect_out)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_product_tail)
+    if (e) cudaEventDestroy(e);
   delete h;
   return 0;
 }

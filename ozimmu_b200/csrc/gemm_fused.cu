@@ -70,6 +70,7 @@ struct FusedParams {
   uint32_t sync_window;        // a pair starts sync interval j only after interval j - window is complete
   uint32_t sync_len;           // counters available
   uint32_t prefetch_ahead;     // k-steps of L2 prefetch lead (OZIMMU_B200_PREFETCH, 0 = off)
+  uint32_t no_lockstep;        // host only: never pace this launch (it shares the GPU with other launches)
 };
 
 // reference src/config.cu:85-92: for sum = 2..s+1, for j = 1..sum-1: (A_id=j, B_id=sum-j)
@@ -505,8 +506,8 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   p.tiles_m = ceil_div_u32(p.m, 2 * BM);
   p.tiles_n = ceil_div_u32(p.n, BN_);
   p.group_m = 8;
-  p.rt_a = static_cast<uint32_t>(slice_row_tiles(p.m));
-  p.rt_b = static_cast<uint32_t>(slice_row_tiles(p.n));
+  if (p.rt_a == 0) p.rt_a = static_cast<uint32_t>(slice_row_tiles(p.m));  // != 0: block of a larger plane
+  if (p.rt_b == 0) p.rt_b = static_cast<uint32_t>(slice_row_tiles(p.n));
   p.sync_window = lockstep_window();
   p.prefetch_ahead = prefetch_ahead();
 
@@ -551,7 +552,7 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   // lockstep counters only pay off when several rounds of tiles stream through L2 (pairs cannot drift apart
   // within a single round, and the polling costs ~7 % there)
   p.sync_ctr = nullptr;
-  if (p.sync_window > 0 && pairs > 1 && num_tiles > pairs && p.single_a == 0) {
+  if (p.sync_window > 0 && pairs > 1 && num_tiles > pairs && p.single_a == 0 && !p.no_lockstep) {
     const uint64_t steps = static_cast<uint64_t>(ceil_div_u32(num_tiles, pairs)) * (p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
     const uint64_t need = steps / kSyncEvery + 1;
     if (need <= kSyncCounters) {
@@ -631,6 +632,32 @@ extern "C" int ozk_gemm_i8_fused(size_t m, size_t n, size_t k, const int8_t *a_s
   if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m)
     return static_cast<int>(cudaErrorInvalidValue);
   oz::FusedParams p = oz::base_params(m, n, pitch, a_slices, b_slices, num_split, bits_per_int8);
+  p.alpha = alpha;
+  p.beta = beta;
+  p.c = c;
+  p.ldc = ldc;
+  p.amax = amax;
+  p.bmax = bmax;
+  return oz::dispatch_fused(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ozk_gemm_i8_fused_block(size_t m, size_t n, size_t k, const int8_t *a_slices, size_t a_plane_rows,
+                                       size_t row0, const int8_t *b_slices, size_t b_plane_rows, size_t col0,
+                                       size_t pitch, const double *amax, const double *bmax, unsigned num_split,
+                                       unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
+                                       unsigned flags, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m || row0 % 256 != 0 ||
+      col0 % 256 != 0 || row0 + m > a_plane_rows || col0 + n > b_plane_rows || a_plane_rows >= (1ull << 31) ||
+      b_plane_rows >= (1ull << 31))
+    return static_cast<int>(cudaErrorInvalidValue);
+  // a block starts on a row-tile boundary of its plane: the kernel only needs the plane's slice stride
+  const size_t tile_row_bytes = pitch * oz::kTileRows;
+  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices + (row0 / oz::kTileRows) * tile_row_bytes,
+                                      b_slices + (col0 / oz::kTileRows) * tile_row_bytes, num_split, bits_per_int8);
+  p.rt_a = static_cast<uint32_t>(oz::slice_row_tiles(a_plane_rows));
+  p.rt_b = static_cast<uint32_t>(oz::slice_row_tiles(b_plane_rows));
+  p.no_lockstep = (flags & OZK_FUSED_NO_LOCKSTEP) ? 1u : 0u;
   p.alpha = alpha;
   p.beta = beta;
   p.c = c;

@@ -113,9 +113,14 @@ struct mtk::ozimmu::handle {
   // staging for ozimmu_gemm_host (grow-only device buffers + copy streams/events)
   void *stage_a = nullptr, *stage_b = nullptr, *stage_c = nullptr;
   std::size_t stage_a_bytes = 0, stage_b_bytes = 0, stage_c_bytes = 0;
+  // compute_stream: the splits (and the one-shot path); product_stream[]: the fused launches, round-robin, so
+  // that a launch back-fills the SMs the previous one leaves idle in its last round of tiles
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, compute_stream = nullptr;
-  static constexpr int kMaxPanels = 16;
-  cudaEvent_t ev_panel_in[kMaxPanels] = {}, ev_panel_out[kMaxPanels] = {};
-  cudaEvent_t ev_a_in = nullptr;
+  static constexpr int kMaxBlocks = 16;        // row blocks of op(A) / column blocks of op(B)
+  static constexpr int kProductStreams = 3;
+  cudaStream_t product_stream[kProductStreams] = {};
+  cudaEvent_t ev_block_in[2][kMaxBlocks] = {}, ev_block_split[2][kMaxBlocks] = {};  // [0] = A, [1] = B
+  cudaEvent_t ev_rect_out[2 * kMaxBlocks] = {};                                     // one per fused launch
+  cudaEvent_t ev_product_tail[kProductStreams] = {};
   int device = 0;
 };

@@ -3,17 +3,26 @@
 //
 // The reference has no such entry: an application does cudaMemcpy(A), cudaMemcpy(B),
 // cublasDgemm (intercepted -> reference src/cublas.cu:280-295 -> src/gemm.cu:344-410),
-// cudaMemcpy(C), strictly one after the other.  Here the three legs are pipelined over column
-// panels of op(B)/C on three streams:
+// cudaMemcpy(C), strictly one after the other.  Here the call is PCIe-bound (8192^3: 1 GiB in ~ 20 ms
+// against ~ 17 ms of products), so the work is cut into row blocks of op(A) and column blocks of op(B)
+// that travel alternately, and every block of C is computed as soon as both of its operands are on the GPU:
 //
-//   h2d stream : B panel 0 | A | B panel 1 | B panel 2 | ...
-//   compute    :               split(A) split(B0) fused(0) | split(B1) fused(1) | ...
-//   d2h stream :                                  C panel 0          | C panel 1 | ...
+//   h2d stream      : B0 | A0 | B1 | A1 | B2 | A2 | ...
+//   compute stream  :      split(B0) split(A0) split(B1) split(A1) ...
+//   product streams :                fused(A0 x B0) | fused(A0 x B1) | fused(A1 x [B0 B1]) | ...   (round-robin)
+//   d2h stream      :                                 C(A0,B0) | C(A0,B1) | C(A1,[B0 B1]) | ...
 //
-// Results are bit-identical to the one-shot path: a column panel of C depends only on A and the
-// same columns of op(B), and the split scales B per column (reference src/split.cu:277-282).
+// After a of A's blocks and b of B's have arrived a*b blocks of C are computable, so alternating the operands
+// keeps the most work available per byte transferred; what remains after the last byte has landed is only the
+// last block's row / column of C.  The fused launches rotate over several streams so that a launch back-fills
+// the SMs the previous one leaves idle in its last (ragged) round of tiles.
+//
+// Results are bit-identical to the one-shot path: a block of C depends only on the same rows of op(A) and the
+// same columns of op(B), and the split scales every row of A / column of B on its own (reference
+// src/split.cu:193-242,277-282).
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "host.hpp"
 #include "oz_common.cuh"
@@ -38,14 +47,35 @@ void ensure_stage(void **ptr, std::size_t *have, std::size_t need) {
 
 void ensure_e2e_streams(handle_t h) {
   if (h->h2d_stream) return;
+  int lo = 0, hi = 0;
+  OZ_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   OZ_CUDA_CHECK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
   OZ_CUDA_CHECK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
-  OZ_CUDA_CHECK(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
-  OZ_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_a_in, cudaEventDisableTiming));
-  for (int i = 0; i < handle::kMaxPanels; i++) {
-    OZ_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_panel_in[i], cudaEventDisableTiming));
-    OZ_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_panel_out[i], cudaEventDisableTiming));
-  }
+  // the splits are short and gate everything behind them: their CTAs go first when SMs free up
+  OZ_CUDA_CHECK(cudaStreamCreateWithPriority(&h->compute_stream, cudaStreamNonBlocking, hi));
+  for (auto &st : h->product_stream) OZ_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo));
+  auto make = [](cudaEvent_t &e) { OZ_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); };
+  for (auto &row : h->ev_block_in)
+    for (auto &e : row) make(e);
+  for (auto &row : h->ev_block_split)
+    for (auto &e : row) make(e);
+  for (auto &e : h->ev_rect_out) make(e);
+  for (auto &e : h->ev_product_tail) make(e);
+}
+
+// block edge: `want` rounded up to the kernel's 256-row tile, grown until `extent` needs at most kMaxBlocks
+std::size_t block_edge(std::size_t extent, std::size_t want) {
+  const std::size_t kmax = handle::kMaxBlocks;
+  std::size_t e = (std::max<std::size_t>(want, 256) + 255) / 256 * 256;
+  if ((extent + e - 1) / e > kmax) e = ((extent + kmax - 1) / kmax + 255) / 256 * 256;
+  return e;
+}
+
+std::size_t env_size(const char *name, std::size_t fallback) {
+  const char *e = std::getenv(name);
+  if (e == nullptr || *e == 0) return fallback;
+  const long v = std::atol(e);
+  return v < 0 ? fallback : static_cast<std::size_t>(v);
 }
 
 // column-major ld x cols matrix with `rows` valid rows per column (BLAS guarantees only
@@ -105,19 +135,15 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
 
   const unsigned s = H::num_split_of(mode);
   const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
-  // column panels of C: multiples of 256 columns (the kernel's tile width), at most kMaxPanels, roughly
-  // `target` wide (OZIMMU_B200_E2E_PANEL, default 1024)
-  static const std::size_t target = [] {
-    const char *e = std::getenv("OZIMMU_B200_E2E_PANEL");
-    const long v = e ? std::atol(e) : 0;
-    return static_cast<std::size_t>(v >= 256 ? v : 1024);
-  }();
-  std::size_t panels = std::min<std::size_t>(handle::kMaxPanels, std::max<std::size_t>(1, n / target));
-  std::size_t pw = ((n + panels - 1) / panels + 255) / 256 * 256;
-  panels = (n + pw - 1) / pw;
+  // Block edges (multiples of 256, the kernel's tile): OZIMMU_B200_E2E_PANEL = columns of op(B) / C per block,
+  // OZIMMU_B200_E2E_ROWBLOCK = rows of op(A) / C per block; 0 = the whole operand in one piece (ROWBLOCK=0:
+  // column panels only).  Read per call.
+  const std::size_t want_cols = env_size("OZIMMU_B200_E2E_PANEL", 1024);
+  const std::size_t want_rows = env_size("OZIMMU_B200_E2E_ROWBLOCK", 1024);
+  const std::size_t cb = block_edge(n, want_cols == 0 ? n : want_cols), rb = block_edge(m, want_rows == 0 ? m : want_rows);
+  const std::size_t nbb = (n + cb - 1) / cb, nab = (m + rb - 1) / rb;
 
-  // workspace: A slices for all of A, B slices for one panel
-  const H::WorkspaceLayout w = H::workspace_layout(m, pw, k, s);
+  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, s);
   reallocate_working_memory(h, w.total);
   if (h->has_pending) OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_done, 0));
   char *ws = static_cast<char *>(h->working_memory_ptr);
@@ -128,35 +154,89 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   auto *a_sl = reinterpret_cast<std::int8_t *>(ws + w.off_a_slices);
   auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
 
-  auto copy_b_panel = [&](std::size_t p) {
-    const std::size_t j0 = p * pw, nj = std::min(pw, n - j0);
+  auto copy_a_block = [&](std::size_t i) {
+    const std::size_t i0 = i * rb, mi = std::min(rb, m - i0);
+    if (op_a == op_n) {  // m x k column-major: rows i0..i0+mi of every column
+      copy_matrix(da + i0, a + i0, lda, mi, k, cudaMemcpyHostToDevice, sin);
+    } else {             // k x m column-major: a row block of op(A) is a contiguous column panel
+      copy_matrix(da + i0 * lda, a + i0 * lda, lda, k, mi, cudaMemcpyHostToDevice, sin);
+    }
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[0][i], sin));
+  };
+  auto copy_b_block = [&](std::size_t j) {
+    const std::size_t j0 = j * cb, nj = std::min(cb, n - j0);
     if (op_b == op_n) {  // k x n column-major: a column panel is contiguous
       copy_matrix(db + j0 * ldb, b + j0 * ldb, ldb, k, nj, cudaMemcpyHostToDevice, sin);
     } else {             // n x k column-major: rows j0..j0+nj of every column
-      OZ_CUDA_CHECK(cudaMemcpy2DAsync(db + j0, sizeof(double) * ldb, b + j0, sizeof(double) * ldb,
-                                      sizeof(double) * nj, k, cudaMemcpyHostToDevice, sin));
+      copy_matrix(db + j0, b + j0, ldb, nj, k, cudaMemcpyHostToDevice, sin);
     }
     if (beta != 0) copy_matrix(dc + j0 * ldc, c + j0 * ldc, ldc, m, nj, cudaMemcpyHostToDevice, sin);
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_panel_in[p], sin));
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[1][j], sin));
+  };
+  auto split_a_block = [&](std::size_t i) {
+    const std::size_t i0 = i * rb, mi = std::min(rb, m - i0);
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_block_in[0][i], 0));
+    const double *src = (op_a == op_n) ? da + i0 : da + i0 * lda;
+    OZ_KERNEL_CHECK(ozk_split_int8_block(a_sl, w.pitch, m, i0, amax + i0, scr_a + i0, mi, k, src, lda, op_a == op_n, s,
+                                         bits, 1, sc));
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[0][i], sc));
+  };
+  auto split_b_block = [&](std::size_t j) {
+    const std::size_t j0 = j * cb, nj = std::min(cb, n - j0);
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_block_in[1][j], 0));
+    const double *src = (op_b == op_n) ? db + j0 * ldb : db + j0;
+    OZ_KERNEL_CHECK(ozk_split_int8_block(b_sl, w.pitch, n, j0, bmax + j0, scr_b + j0, nj, k, src, ldb, op_b != op_n, s,
+                                         bits, 1, sc));
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[1][j], sc));
+  };
+  // C[i0 : i0+mi, j0 : j0+nj] once `ready` (the split that completed its operands; the compute stream runs the
+  // splits in arrival order, so it implies every earlier one) has fired
+  unsigned rects = 0;
+  bool used[handle::kProductStreams] = {};
+  auto product_rect = [&](std::size_t i0, std::size_t mi, std::size_t j0, std::size_t nj, cudaEvent_t ready) {
+    if (mi == 0 || nj == 0) return;
+    const unsigned r = rects % handle::kProductStreams;
+    cudaStream_t sp = h->product_stream[r];
+    used[r] = true;
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, ready, 0));
+    double *dblk = dc + j0 * ldc + i0;
+    OZ_KERNEL_CHECK(ozk_gemm_i8_fused_block(mi, nj, k, a_sl, m, i0, b_sl, n, j0, w.pitch, amax + i0, bmax + j0, s, bits,
+                                            alpha, beta, dblk, ldc, OZK_FUSED_NO_LOCKSTEP, sp));
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_rect_out[rects], sp));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sout, h->ev_rect_out[rects], 0));
+    copy_matrix(c + j0 * ldc + i0, dblk, ldc, mi, nj, cudaMemcpyDeviceToHost, sout);
+    rects++;
   };
 
-  copy_b_panel(0);
-  copy_matrix(da, a, lda, a_rows, a_cols, cudaMemcpyHostToDevice, sin);
-  OZ_CUDA_CHECK(cudaEventRecord(h->ev_a_in, sin));
-  for (std::size_t p = 1; p < panels; p++) copy_b_panel(p);
+  // arrival order: B0, A0, B1, A1, ... (the longer operand's remaining blocks follow at the end); queue every
+  // copy first so the H2D engine never waits for the host
+  struct Arrival { int which; std::size_t idx; };
+  std::vector<Arrival> order;
+  for (std::size_t ia = 0, ib = 0; ia < nab || ib < nbb;) {
+    if (ib < nbb && (ib <= ia || ia >= nab)) order.push_back({1, ib++});
+    else order.push_back({0, ia++});
+  }
+  for (const Arrival &x : order) x.which ? copy_b_block(x.idx) : copy_a_block(x.idx);
 
-  OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_a_in, 0));
-  OZ_KERNEL_CHECK(ozk_split_int8(a_sl, w.pitch, amax, scr_a, m, k, da, lda, op_a == op_n, s, bits, sc));
-  for (std::size_t p = 0; p < panels; p++) {
-    const std::size_t j0 = p * pw, nj = std::min(pw, n - j0);
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_panel_in[p], 0));
-    const double *bp = (op_b == op_n) ? db + j0 * ldb : db + j0;
-    OZ_KERNEL_CHECK(ozk_split_int8(b_sl, w.pitch, bmax, scr_b, nj, k, bp, ldb, op_b != op_n, s, bits, sc));
-    OZ_KERNEL_CHECK(ozk_gemm_i8_fused(m, nj, k, a_sl, b_sl, w.pitch, amax, bmax, s, bits, alpha, beta,
-                                      dc + j0 * ldc, ldc, sc));
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_panel_out[p], sc));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(sout, h->ev_panel_out[p], 0));
-    copy_matrix(c + j0 * ldc, dc + j0 * ldc, ldc, m, nj, cudaMemcpyDeviceToHost, sout);
+  std::size_t have_a = 0, have_b = 0;  // blocks split so far
+  for (const Arrival &x : order) {
+    if (x.which) {
+      split_b_block(x.idx);
+      const std::size_t j0 = x.idx * cb;
+      product_rect(0, std::min(m, have_a * rb), j0, std::min(cb, n - j0), h->ev_block_split[1][x.idx]);
+      have_b++;
+    } else {
+      split_a_block(x.idx);
+      const std::size_t i0 = x.idx * rb;
+      product_rect(i0, std::min(rb, m - i0), 0, std::min(n, have_b * cb), h->ev_block_split[0][x.idx]);
+      have_a++;
+    }
+  }
+  // the workspace is free again once every product stream has drained
+  for (int r = 0; r < handle::kProductStreams; r++) {
+    if (!used[r]) continue;
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_product_tail[r], h->product_stream[r]));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_product_tail[r], 0));
   }
   OZ_CUDA_CHECK(cudaEventRecord(h->ev_done, sc));
   h->has_pending = true;

@@ -4,12 +4,12 @@
 #include "split_kernels.cuh"
 
 namespace oz {
-int split_dispatch_lo(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, size_t rows, size_t len,
-                      const double *in, size_t ld, int col_major, unsigned num_split, unsigned L, uint32_t es,
-                      cudaStream_t stream);
-int split_dispatch_hi(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, size_t rows, size_t len,
-                      const double *in, size_t ld, int col_major, unsigned num_split, unsigned L, uint32_t es,
-                      cudaStream_t stream);
+int split_dispatch_lo(int8_t *out, size_t pitch, size_t plane_rows, double *max_exp, uint32_t *scratch, size_t rows,
+                      size_t len, const double *in, size_t ld, int col_major, unsigned num_split, unsigned L,
+                      uint32_t es, cudaStream_t stream);
+int split_dispatch_hi(int8_t *out, size_t pitch, size_t plane_rows, double *max_exp, uint32_t *scratch, size_t rows,
+                      size_t len, const double *in, size_t ld, int col_major, unsigned num_split, unsigned L,
+                      uint32_t es, cudaStream_t stream);
 }  // namespace oz
 
 extern "C" uint32_t ozk_bits_per_int8(uint32_t k) {
@@ -25,33 +25,47 @@ extern "C" size_t ozk_slice_pitch(size_t k) { return oz::slice_pitch(k); }
 
 extern "C" size_t ozk_slices_bytes(size_t rows, size_t k, unsigned num_split) { return oz::slices_bytes(rows, k, num_split); }
 
-extern "C" int ozk_split_int8_strided(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch,
-                                      size_t rows, size_t len, const double *in, size_t ld, int col_major,
-                                      unsigned num_split, unsigned bits_per_int8, unsigned elem_stride,
-                                      void *stream) {
+// Rows [row0, row0 + rows) of an operand whose slice planes hold plane_rows rows: `out` is the base of the
+// operand's slices, `max_exp` / `scratch` / `in` point at row row0's entries.  row0 must be a multiple of 256 and
+// the block must end on a multiple of 256 or at the end of the plane (so that blocks never share a row tile).
+extern "C" int ozk_split_int8_block(int8_t *out, size_t pitch, size_t plane_rows, size_t row0, double *max_exp,
+                                    uint32_t *scratch, size_t rows, size_t len, const double *in, size_t ld,
+                                    int col_major, unsigned num_split, unsigned bits_per_int8,
+                                    unsigned elem_stride, void *stream) {
   if (rows == 0 || len == 0) return 0;
   if (pitch % 128 != 0 || pitch < len || bits_per_int8 == 0 || bits_per_int8 > 7 || elem_stride < 1 ||
       elem_stride > 2 || num_split < 3 || num_split > 18 || len > 0xFFFFFFF0ull || rows > 0x7FFFFFFFull ||
-      (col_major && scratch == nullptr))
+      (col_major && scratch == nullptr) || row0 % 256 != 0 || row0 + rows > plane_rows ||
+      ((row0 + rows) % 256 != 0 && row0 + rows != plane_rows))
     return static_cast<int>(cudaErrorInvalidValue);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // rows are padded to a multiple of 256 per slice; the GEMM kernel reads the padding, so it must be zero:
-  // clear everything from the first partially filled 128-row tile to the end of each slice plane (the kernels
-  // below then overwrite the valid rows).  Nothing to do when rows is a multiple of 256.
-  const size_t row_tiles = oz::slice_row_tiles(rows), full_tiles = rows / oz::kTileRows;
-  if (full_tiles < row_tiles) {
-    const size_t tile_row_bytes = pitch * oz::kTileRows;  // one 128-row tile across all of K
+  // the block that ends the plane clears everything from the first partially filled 128-row tile to the end of
+  // each slice plane (the kernels below then overwrite the valid rows).  Nothing to do when the plane's row
+  // count is a multiple of 256.
+  const size_t row_tiles = oz::slice_row_tiles(plane_rows), full_tiles = (row0 + rows) / oz::kTileRows;
+  const size_t tile_row_bytes = pitch * oz::kTileRows;  // one 128-row tile across all of K
+  if (row0 + rows == plane_rows && full_tiles < row_tiles) {
     for (unsigned t = 0; t < num_split; t++)
       OZ_CUDA_TRY(cudaMemsetAsync(out + (t * row_tiles + full_tiles) * tile_row_bytes, 0,
                                   (row_tiles - full_tiles) * tile_row_bytes, s));
   }
+  int8_t *dst = out + (row0 / oz::kTileRows) * tile_row_bytes;
   if (num_split >= 3 && num_split <= 10)
-    return oz::split_dispatch_lo(out, pitch, max_exp, scratch, rows, len, in, ld, col_major, num_split, bits_per_int8,
-                                 elem_stride, s);
+    return oz::split_dispatch_lo(dst, pitch, plane_rows, max_exp, scratch, rows, len, in, ld, col_major, num_split,
+                                 bits_per_int8, elem_stride, s);
   if (num_split >= 11 && num_split <= 18)
-    return oz::split_dispatch_hi(out, pitch, max_exp, scratch, rows, len, in, ld, col_major, num_split, bits_per_int8,
-                                 elem_stride, s);
+    return oz::split_dispatch_hi(dst, pitch, plane_rows, max_exp, scratch, rows, len, in, ld, col_major, num_split,
+                                 bits_per_int8, elem_stride, s);
   return static_cast<int>(cudaErrorInvalidValue);
+}
+
+extern "C" int ozk_split_int8_strided(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch,
+                                      size_t rows, size_t len, const double *in, size_t ld, int col_major,
+                                      unsigned num_split, unsigned bits_per_int8, unsigned elem_stride,
+                                      void *stream) {
+  return ozk_split_int8_block(out, pitch, rows, 0, max_exp, scratch, rows, len, in, ld, col_major, num_split,
+                              bits_per_int8, elem_stride, stream);
 }
 
 extern "C" int ozk_split_int8(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch,

@@ -153,7 +153,9 @@ template <int S, bool CACHED>
 __global__ void __launch_bounds__(kSplitThreads)
 split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
                   const size_t rows, const uint32_t len, const double *__restrict__ in,
-                  const size_t ld, const unsigned L, const uint32_t es) {
+                  const size_t ld, const unsigned L, const uint32_t es, const size_t slice_stride) {
+  // slice_stride: bytes between consecutive slices of the destination plane (the plane may hold more rows than
+  // this launch cuts: row-block calls of the host-operand pipeline).
   // es: distance between consecutive elements in doubles (1 = real matrix, 2 = one plane of an
   // interleaved complex matrix; `in` then points at the plane's first double, ld counts complex elements)
   extern __shared__ double s_row[];
@@ -172,7 +174,6 @@ split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
   const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
   if (threadIdx.x == 0) max_exp[row] = mx;
 
-  const size_t slice_stride = slice_row_tiles(rows) * kTileRows * pitch;
   const size_t kblocks = pitch / kTileK;
   const uint32_t ngroups = static_cast<uint32_t>(pitch / 16);
   for (uint32_t g = threadIdx.x; g < ngroups; g += kSplitThreads) {
@@ -207,7 +208,7 @@ template <int S, int THREADS, int GROUPS>
 __global__ void __launch_bounds__(THREADS)
 split_rows_reg_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
                       const size_t rows, const uint32_t len, const double *__restrict__ in,
-                      const size_t ld, const unsigned L) {
+                      const size_t ld, const unsigned L, const size_t slice_stride) {
   __shared__ uint32_t s_red[THREADS / 32];
   __shared__ uint32_t s_max;
   const size_t row = blockIdx.x;
@@ -248,7 +249,6 @@ split_rows_reg_kernel(int8_t *__restrict__ out, const size_t pitch, double *__re
   const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
   if (threadIdx.x == 0) max_exp[row] = mx;
 
-  const size_t slice_stride = slice_row_tiles(rows) * kTileRows * pitch;
   const size_t kblocks = pitch / kTileK;
   const uint32_t ngroups = static_cast<uint32_t>(pitch / 16);
 #pragma unroll
@@ -294,7 +294,8 @@ template <int S>
 __global__ void __launch_bounds__(256)
 split_cols_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
                   const uint32_t *__restrict__ emax, const size_t rows, const uint32_t len,
-                  const double *__restrict__ in, const size_t ld, const unsigned L, const uint32_t es) {
+                  const double *__restrict__ in, const size_t ld, const unsigned L, const uint32_t es,
+                  const size_t slice_stride) {
   extern __shared__ uint4 s_out[];  // [S][32 rows][8 chunks of 16 B], chunk index ^ (row & 7)
   const uint32_t rl = threadIdx.x & 31, cg = threadIdx.x >> 5;
   const size_t r = static_cast<size_t>(blockIdx.x) * kColsRows + rl;
@@ -322,7 +323,6 @@ split_cols_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
   const size_t gr = static_cast<size_t>(blockIdx.x) * kColsRows + orow;
   const uint32_t gk = kbase + chunk * 16;
   if (gr < rows && gk < pitch) {
-    const size_t slice_stride = slice_row_tiles(rows) * kTileRows * pitch;
     int8_t *__restrict__ dst = out + slice_chunk_offset(gr, gk >> 4, pitch / kTileK);
 #pragma unroll
     for (int t = 0; t < S; t++)
@@ -402,9 +402,12 @@ loss_cols_kernel(unsigned long long *__restrict__ counters, const uint32_t *__re
 }
 
 template <int S>
-int launch_split(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, size_t rows,
+int launch_split(int8_t *out, size_t pitch, size_t plane_rows, double *max_exp, uint32_t *scratch, size_t rows,
                  size_t len, const double *in, size_t ld, int col_major, unsigned L, uint32_t es,
                  cudaStream_t stream) {
+  // `out` points at this call's first row tile inside a plane of plane_rows rows (plane_rows == rows for a
+  // whole-matrix call)
+  const size_t slice_stride = slice_row_tiles(plane_rows) * kTileRows * pitch;
   if (col_major) {
     OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), stream));
     dim3 g1(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk));
@@ -415,20 +418,20 @@ int launch_split(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, 
       OZ_CUDA_TRY(cudaFuncSetAttribute(split_cols_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_cols)));
     split_cols_kernel<S><<<g2, 256, smem_cols, stream>>>(out, pitch, max_exp, scratch, rows,
-                                                         static_cast<uint32_t>(len), in, ld, L, es);
+                                                         static_cast<uint32_t>(len), in, ld, L, es, slice_stride);
     count_launch(2);
   } else if (es == 1 && len <= 16384) {
     // register-resident rows: (threads, 16-element groups per thread) sized to the row
     const unsigned nrows = static_cast<unsigned>(rows);
     const uint32_t len32 = static_cast<uint32_t>(len);
     if (len <= 2048)
-      split_rows_reg_kernel<S, 128, 1><<<nrows, 128, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L);
+      split_rows_reg_kernel<S, 128, 1><<<nrows, 128, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride);
     else if (len <= 4096)
-      split_rows_reg_kernel<S, 256, 1><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L);
+      split_rows_reg_kernel<S, 256, 1><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride);
     else if (len <= 8192)
-      split_rows_reg_kernel<S, 256, 2><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L);
+      split_rows_reg_kernel<S, 256, 2><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride);
     else
-      split_rows_reg_kernel<S, 512, 2><<<nrows, 512, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L);
+      split_rows_reg_kernel<S, 512, 2><<<nrows, 512, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride);
     count_launch(1);
   } else {
     if (len <= static_cast<size_t>(kMaxCachedLen)) {
@@ -439,10 +442,10 @@ int launch_split(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch, 
                                          static_cast<int>(smem)));
       }
       split_rows_kernel<S, true><<<static_cast<unsigned>(rows), kSplitThreads, smem, stream>>>(
-          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es);
+          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es, slice_stride);
     } else {
       split_rows_kernel<S, false><<<static_cast<unsigned>(rows), kSplitThreads, 0, stream>>>(
-          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es);
+          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es, slice_stride);
     }
     count_launch(1);
   }

@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-python -c "import torch; torch.zeros(1).cuda()"
-for rep in 1 2; do
-for ns in 0 32 100 500; do
-  echo -n "rep$rep IDLE_SLEEP=$ns: "
-  OZIMMU_B200_IDLE_SLEEP=$ns timeout 200 python tools/perf_probe.py 8192 9 --iters 20 2>&1 | head -1
-done
-done 2>&1 | tee gpurun_out/sweep6.log
+(timeout 600 python -m pytest tests/test_gpu_host_blocks.py "tests/test_gpu_gemm.py::test_gemm_host_equals_device_path" -x -q) > gpurun_out/t_blocks.log 2>&1; echo "pytest blocks rc=$?"; tail -15 gpurun_out/t_blocks.log
+(timeout 300 python -c "import __graft_entry__ as g; g.smoke()") 2>&1 | tail -2
+(timeout 600 python tools/e2e_probe.py 8192) > gpurun_out/e2e_probe.log 2>&1; echo "probe rc=$?"; cat gpurun_out/e2e_probe.log
+(timeout 600 python bench.py --steps 10 --warmup 3) > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "bench ours rc=$?"; python -c "
+import json
+d=json.loads(open('gpurun_out/bench_ours.json').read().strip().splitlines()[-1])
+print('OURS', round(d['value'],2), 'TFLOP/s', round(d['ms_per_step'],2),'ms; e2e', round(d['e2e']['value'],2), d['e2e']['ms_per_step'], 'roof', d['roofline']['frac'], 'clocks', d['clocks'])"
