@@ -77,6 +77,17 @@ int gemm(handle_t handle, const operation_t op_A, const operation_t op_B, const 
          void *const c_ptr, std::size_t ldc, const compute_mode_t compute_mode,
          const element_kind_t element_kind);
 
+// Extension (not in the reference header, whose strided-batched interposers loop over gemm(),
+// reference src/cublas.cu:380-406): a strided batch of real DGEMMs, C_e = alpha*op(A_e)*op(B_e) + beta*C_e with
+// X_e = X + e*stride_x (strides in elements), multiplied by one grouped launch.  Each entry is bit-identical to
+// a separate gemm() call.  Returns 0, or 1 for an invalid argument.
+int gemm_strided_batched(handle_t handle, const operation_t op_A, const operation_t op_B, const std::size_t m,
+                         const std::size_t n, const std::size_t k, const double *alpha, const double *const a_ptr,
+                         const std::size_t lda, const long long stride_a, const double *const b_ptr,
+                         const std::size_t ldb, const long long stride_b, const double *beta, double *const c_ptr,
+                         const std::size_t ldc, const long long stride_c, const std::size_t batch_count,
+                         const compute_mode_t compute_mode);
+
 compute_mode_t auto_mode_select(handle_t handle, const operation_t op_A, const operation_t op_B,
                                 const std::size_t m, const std::size_t n, const std::size_t k,
                                 const void *const a_ptr, const std::size_t lda,

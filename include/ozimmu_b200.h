@@ -116,6 +116,16 @@ int ozk_gemm_i8_fused_block(size_t m, size_t n, size_t k, const int8_t *a_slices
                             unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
                             unsigned flags, void *stream);
 
+/* Grouped launch for a strided batch (reference src/cublas.cu:315-472 loops one GEMM per entry, :380-406):
+ * `batch` independent m x n x k products in ONE persistent launch, tiles of all entries in one queue so that
+ * small entries fill the GPU together.  Entry e uses a_slices + e*a_batch_bytes, b_slices + e*b_batch_bytes,
+ * amax + e*amax_batch, bmax + e*bmax_batch and c + e*c_batch (the last three counted in doubles). */
+int ozk_gemm_i8_fused_batched(size_t m, size_t n, size_t k, size_t batch, const int8_t *a_slices,
+                              size_t a_batch_bytes, const int8_t *b_slices, size_t b_batch_bytes, size_t pitch,
+                              const double *amax, size_t amax_batch, const double *bmax, size_t bmax_batch,
+                              unsigned num_split, unsigned bits_per_int8, double alpha, double beta, double *c,
+                              size_t ldc, size_t c_batch, void *stream);
+
 /* One of the four real products of a complex GEMM (reference src/gemm.cu:479-518 loop body +
  * :160-186 axy_complex + :188-239 init_c_complex): x = the fp64_int8 product of the given planes,
  * C[i,j] = fma(x, (coef_re, coef_im), C'[i,j]) with C' = beta*C if apply_beta (first launch of the
@@ -175,6 +185,16 @@ size_t ozimmu_reallocate_working_memory_bytes(ozimmu_handle_t handle, size_t siz
 int ozimmu_gemm(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
                 const void *alpha, const void *a, size_t lda, const void *b, size_t ldb,
                 const void *beta, void *c, size_t ldc, int compute_mode, int element_kind);
+
+/* Strided batch of real DGEMMs (what the reference's cublasGemmStridedBatchedEx / cublasDgemmStridedBatched
+ * interposers compute entry by entry, src/cublas.cu:315-492): C_e = alpha*op(A_e)*op(B_e) + beta*C_e with
+ * X_e = X + e*stride_x (strides in doubles).  compute_mode: fp64_int8_3..18, fp64_int8_auto (decided per
+ * entry) or dgemm.  Entries are split on two streams and multiplied by one grouped launch; every entry is
+ * bit-identical to a separate ozimmu_gemm call. */
+int ozimmu_gemm_strided_batched(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                                const double *alpha, const double *a, size_t lda, long long stride_a,
+                                const double *b, size_t ldb, long long stride_b, const double *beta, double *c,
+                                size_t ldc, long long stride_c, size_t batch, int compute_mode);
 
 /* :85-94 -- returns the selected compute mode (OZIMMU_FP64_INT8_3.. or OZIMMU_DGEMM);
  * negative on failure.  counters16 (host, optional) receives the 16 loss totals. */

@@ -176,6 +176,19 @@ def gemm(handle: handle_t, op_A: operation_t, op_B: operation_t, m: int, n: int,
     return _check(rc, "gemm")
 
 
+def gemm_strided_batched(handle: handle_t, op_A: operation_t, op_B: operation_t, m: int, n: int, k: int, alpha: float,
+                         a_ptr, lda: int, stride_a: int, b_ptr, ldb: int, stride_b: int, beta: float, c_ptr, ldc: int,
+                         stride_c: int, batch_count: int, compute_mode: compute_mode_t) -> int:
+    """Strided batch of real DGEMMs (X_e = X + e*stride_x elements) through one grouped launch; what the
+    reference's cublasDgemmStridedBatched / cublasGemmStridedBatchedEx interposers loop over
+    (reference src/cublas.cu:315-492).  Asynchronous on the handle's stream."""
+    al, be = C.c_double(alpha), C.c_double(beta)
+    rc = _lib.lib().ozimmu_gemm_strided_batched(handle.raw, int(op_A), int(op_B), m, n, k, C.addressof(al), _ptr(a_ptr),
+                                                lda, stride_a, _ptr(b_ptr), ldb, stride_b, C.addressof(be),
+                                                _ptr(c_ptr), ldc, stride_c, batch_count, int(compute_mode))
+    return _check(rc, "gemm_strided_batched")
+
+
 def gemm_host(handle: handle_t, op_A: operation_t, op_B: operation_t, m: int, n: int, k: int, alpha: float, a_host,
               lda: int, b_host, ldb: int, beta: float, c_host, ldc: int, compute_mode: compute_mode_t) -> int:
     """Same product with HOST operands (numpy arrays / pinned CPU tensors); returns when C is complete."""

@@ -128,6 +128,72 @@ void gemm_int8_real(handle_t h, operation_t op_a, operation_t op_b, std::size_t 
   mark_done(h, s);
 }
 
+// Strided batch of real fp64_int8 products: the reference's interposers run one gemm_int8<double> per entry
+// (src/cublas.cu:380-406); here the entries are split on two streams and multiplied by ONE grouped launch
+// whose tile queue spans all entries, so that small entries fill the GPU together.  Entries are processed in
+// chunks that keep the workspace below OZIMMU_B200_BATCH_WORKSPACE_MB (default 8192).
+void gemm_int8_real_batched(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n,
+                            std::size_t k, double alpha, const double *a, std::size_t lda, long long stride_a,
+                            const double *b, std::size_t ldb, long long stride_b, double beta, double *c,
+                            std::size_t ldc, long long stride_c, std::size_t batch, unsigned num_split) {
+  if (m == 0 || n == 0 || batch == 0) return;
+  if (k == 0) {
+    for (std::size_t e = 0; e < batch; e++)
+      OZ_KERNEL_CHECK(ozk_scale_c(m, n, beta, c + static_cast<long long>(e) * stride_c, ldc, h->cuda_stream));
+    return;
+  }
+  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
+  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split);
+  const std::size_t limit = std::stoull(H::env_or("OZIMMU_B200_BATCH_WORKSPACE_MB", "8192")) << 20;
+  const std::size_t chunk = std::max<std::size_t>(1, std::min(batch, limit / w.total));
+  reallocate_working_memory(h, w.total * chunk);
+  ensure_streams(h);
+  char *ws = static_cast<char *>(h->working_memory_ptr);
+  cudaStream_t s = h->cuda_stream;
+  wait_previous(h, s);
+  const int a_col_major = (op_a == op_n), b_col_major = (op_b != op_n);
+  const bool overlap = !h->profiler.enabled;
+  cudaStream_t sb = overlap ? h->aux_stream : s;
+  for (std::size_t e0 = 0; e0 < batch; e0 += chunk) {
+    const std::size_t ne = std::min(chunk, batch - e0);
+    if (overlap) {
+      OZ_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));   // also: the previous chunk's products are done with the slices
+      OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, h->ev_fork, 0));
+    }
+    h->profiler.start("split_A", s);
+    for (std::size_t e = 0; e < ne; e++) {
+      char *we = ws + e * w.total;
+      OZ_KERNEL_CHECK(ozk_split_int8(reinterpret_cast<std::int8_t *>(we + w.off_a_slices), w.pitch,
+                                     reinterpret_cast<double *>(we + w.off_amax),
+                                     reinterpret_cast<std::uint32_t *>(we + w.off_scr_a), m, k,
+                                     a + static_cast<long long>(e0 + e) * stride_a, lda, a_col_major, num_split, bits, s));
+    }
+    h->profiler.stop("split_A", s);
+    h->profiler.start("split_B", sb);
+    for (std::size_t e = 0; e < ne; e++) {
+      char *we = ws + e * w.total;
+      OZ_KERNEL_CHECK(ozk_split_int8(reinterpret_cast<std::int8_t *>(we + w.off_b_slices), w.pitch,
+                                     reinterpret_cast<double *>(we + w.off_bmax),
+                                     reinterpret_cast<std::uint32_t *>(we + w.off_scr_b), n, k,
+                                     b + static_cast<long long>(e0 + e) * stride_b, ldb, b_col_major, num_split, bits, sb));
+    }
+    h->profiler.stop("split_B", sb);
+    if (overlap) {
+      OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, sb));
+      OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    }
+    h->profiler.start("int8tc_accumulate_fused", s);
+    OZ_KERNEL_CHECK(ozk_gemm_i8_fused_batched(
+        m, n, k, ne, reinterpret_cast<const std::int8_t *>(ws + w.off_a_slices), w.total,
+        reinterpret_cast<const std::int8_t *>(ws + w.off_b_slices), w.total, w.pitch,
+        reinterpret_cast<const double *>(ws + w.off_amax), w.total / sizeof(double),
+        reinterpret_cast<const double *>(ws + w.off_bmax), w.total / sizeof(double), num_split, bits, alpha, beta,
+        c + static_cast<long long>(e0) * stride_c, ldc, static_cast<std::size_t>(stride_c), s));
+    h->profiler.stop("int8tc_accumulate_fused", s);
+  }
+  mark_done(h, s);
+}
+
 // reference src/gemm.cu:412-521 gemm_int8<cuDoubleComplex>: real and imaginary planes are split
 // independently, then four real fp64_int8 products are added into C in the order
 // (im,im) -> -alpha, (re,re) -> +alpha, (im,re) and (re,im) -> i*alpha, after C = beta*C.
@@ -428,6 +494,43 @@ int mtk::ozimmu::gemm(handle_t h, const operation_t op_A, const operation_t op_B
                            " is not implemented");
 }
 
+// Not in the reference's header: its strided-batched interposers loop over gemm() (src/cublas.cu:380-406).
+int mtk::ozimmu::gemm_strided_batched(handle_t h, const operation_t op_A, const operation_t op_B, const std::size_t m,
+                                      const std::size_t n, const std::size_t k, const double *alpha,
+                                      const double *const a_ptr, const std::size_t lda, const long long stride_a,
+                                      const double *const b_ptr, const std::size_t ldb, const long long stride_b,
+                                      const double *beta, double *const c_ptr, const std::size_t ldc,
+                                      const long long stride_c, const std::size_t batch_count,
+                                      const compute_mode_t compute_mode) {
+  int arg_error = 0;
+  arg_error |= check_shape(op_A, m, k, lda, "A");
+  arg_error |= check_shape(op_B, k, n, ldb, "B");
+  arg_error |= check_shape(op_n, m, n, ldc, "C");
+  arg_error |= check_alignment(a_ptr, sizeof(double), "A");
+  arg_error |= check_alignment(b_ptr, sizeof(double), "B");
+  arg_error |= check_alignment(c_ptr, sizeof(double), "C");
+  // entries of C must not overlap (they are written concurrently); stride 0 is fine for the inputs
+  if (batch_count > 1 && m > 0 && n > 0 &&
+      static_cast<unsigned long long>(stride_c < 0 ? -stride_c : stride_c) < ldc * (n - 1) + m) {
+    H::log_error("gemm_strided_batched: entries of C overlap (|stride_c| < ldc*(n-1)+m)");
+    arg_error |= 1;
+  }
+  if (arg_error) return 1;
+  if (H::is_int8_mode(compute_mode) && stride_c >= 0) {
+    gemm_int8_real_batched(h, op_A, op_B, m, n, k, *alpha, a_ptr, lda, stride_a, b_ptr, ldb, stride_b, *beta, c_ptr,
+                           ldc, stride_c, batch_count, H::num_split_of(compute_mode));
+    return 0;
+  }
+  // auto mode decides per entry (a blocking counter read each), dgemm goes to cuBLAS: entry by entry
+  for (std::size_t e = 0; e < batch_count; e++) {
+    const int rc = gemm(h, op_A, op_B, m, n, k, alpha, a_ptr + static_cast<long long>(e) * stride_a, lda,
+                        b_ptr + static_cast<long long>(e) * stride_b, ldb, beta,
+                        c_ptr + static_cast<long long>(e) * stride_c, ldc, compute_mode, real);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 // ===============================================================================================
 // C spelling
 // ===============================================================================================
@@ -500,6 +603,20 @@ int ozimmu_gemm(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, 
     return gemm(reinterpret_cast<handle_t>(handle), static_cast<operation_t>(op_a != 0),
                 static_cast<operation_t>(op_b != 0), m, n, k, alpha, a, lda, b, ldb, beta, c, ldc,
                 static_cast<compute_mode_t>(compute_mode), static_cast<element_kind_t>(element_kind));
+  });
+}
+
+int ozimmu_gemm_strided_batched(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                                const double *alpha, const double *a, size_t lda, long long stride_a,
+                                const double *b, size_t ldb, long long stride_b, const double *beta, double *c,
+                                size_t ldc, long long stride_c, size_t batch, int compute_mode) {
+  if (handle == nullptr || alpha == nullptr || beta == nullptr || compute_mode < 0 ||
+      compute_mode > OZIMMU_FP64_INT8_AUTO)
+    return 1;
+  return guarded([&] {
+    return gemm_strided_batched(reinterpret_cast<handle_t>(handle), static_cast<operation_t>(op_a != 0),
+                                static_cast<operation_t>(op_b != 0), m, n, k, alpha, a, lda, stride_a, b, ldb, stride_b,
+                                beta, c, ldc, stride_c, batch, static_cast<compute_mode_t>(compute_mode));
   });
 }
 

@@ -71,6 +71,10 @@ struct FusedParams {
   uint32_t sync_len;           // counters available
   uint32_t prefetch_ahead;     // k-steps of L2 prefetch lead (OZIMMU_B200_PREFETCH, 0 = off)
   uint32_t no_lockstep;        // host only: never pace this launch (it shares the GPU with other launches)
+  // strided batch (grouped launch): tile index = entry * tiles_m * tiles_n + tile inside the entry; every entry
+  // has its own slices / row scales / C at these distances (bytes for the slices, doubles for the rest)
+  uint32_t batch;
+  unsigned long long a_batch_bytes, b_batch_bytes, amax_batch, bmax_batch, c_batch;
 };
 
 // reference src/config.cu:85-92: for sum = 2..s+1, for j = 1..sum-1: (A_id=j, B_id=sum-j)
@@ -113,7 +117,11 @@ struct PairIter {
 
 // tile index -> (tile row, tile column): bands of group_m tile rows, column-major inside a band, so the tiles
 // that run concurrently cover a compact block of C and share their A / B panels through L2
-__device__ __forceinline__ void tile_coords(const FusedParams &p, uint32_t t, uint32_t &tm, uint32_t &tn) {
+__device__ __forceinline__ void tile_coords(const FusedParams &p, uint32_t t, uint32_t &tm, uint32_t &tn,
+                                            uint32_t &entry) {
+  const uint32_t per_entry = p.tiles_m * p.tiles_n;
+  entry = t / per_entry;
+  t -= entry * per_entry;
   const uint32_t group_size = p.group_m * p.tiles_n;
   const uint32_t g = t / group_size;
   const uint32_t first = g * p.group_m;
@@ -169,7 +177,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
   const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0) & 1u;  // 0 = leader (issues the MMAs)
   const uint32_t pair_id = blockIdx.x >> 1;
   const uint32_t num_pairs = gridDim.x >> 1;
-  const uint32_t num_tiles = p.tiles_m * p.tiles_n;
+  const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const uint32_t steps_per_tile = (p.single_a != 0 ? 1u : p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
 
   if (threadIdx.x == 0) {
@@ -207,23 +215,25 @@ oz_gemm_pair_kernel(const FusedParams p) {
       bool lockstep = p.sync_ctr != nullptr && rank == 0;
       uint32_t g = 0;
       for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
-        uint32_t tm, tn;
-        tile_coords(p, t, tm, tn);
+        uint32_t tm, tn, entry;
+        tile_coords(p, t, tm, tn, entry);
+        const int8_t *a_base = p.a_slices + static_cast<size_t>(entry) * p.a_batch_bytes;
+        const int8_t *b_base = p.b_slices + static_cast<size_t>(entry) * p.b_batch_bytes;
         // this CTA's 128 rows of A; its BN/2 rows of B (BN=256: one whole 128-row tile; BN=128: half a tile)
         const size_t a_tile = static_cast<size_t>(tm) * 2 + rank;
         const size_t b_tile = (BN_ == 256) ? static_cast<size_t>(tn) * 2 + rank : static_cast<size_t>(tn);
         const size_t b_sub = (BN_ == 256) ? 0 : static_cast<size_t>(rank) * Cfg::kBBytes;
         for (PairIter it(p); it.valid(); it.next()) {
-          const int8_t *a_src = p.a_slices + ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
+          const int8_t *a_src = a_base + ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
           const int8_t *b_src =
-              p.b_slices + ((it.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
+              b_base + ((it.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
           // optional L2 prefetch `prefetch_ahead` k-steps ahead (into the next product of this tile if needed)
           PairIter nx = it;
           nx.next();
           const int8_t *a_nx = nullptr, *b_nx = nullptr;
           if (p.prefetch_ahead && nx.valid()) {
-            a_nx = p.a_slices + ((nx.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
-            b_nx = p.b_slices + ((nx.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
+            a_nx = a_base + ((nx.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
+            b_nx = b_base + ((nx.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
           }
           for (uint32_t kb = 0; kb < p.k_blocks; kb++, g++) {
             if (p.prefetch_ahead && issuer) {
@@ -322,8 +332,8 @@ oz_gemm_pair_kernel(const FusedParams p) {
     const bool raw = p.single_a != 0;
     uint32_t pc = 0;
     for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
-      uint32_t tm, tn;
-      tile_coords(p, t, tm, tn);
+      uint32_t tm, tn, entry;
+      tile_coords(p, t, tm, tn, entry);
       const uint32_t row = tm * 2 * BM + rank * BM + q * 32u + lane;
       const uint32_t col0 = tn * BN_ + half * kCols;
       double acc[kRegCols];
@@ -371,7 +381,8 @@ oz_gemm_pair_kernel(const FusedParams p) {
 #pragma unroll
             for (uint32_t j = 0; j < 16; j++) {
               const uint32_t col = col0 + c * 16 + j;
-              if (col < p.n) p.c_i32[static_cast<size_t>(col) * p.m + row] = static_cast<int32_t>(v[j]);
+              if (col < p.n)
+                p.c_i32[(static_cast<size_t>(entry) * p.n + col) * p.m + row] = static_cast<int32_t>(v[j]);
             }
           }
         }
@@ -385,8 +396,10 @@ oz_gemm_pair_kernel(const FusedParams p) {
       }
       if (!raw && row < p.m) {
         // reference src/gemm.cu:124-148: x = acc / 2^44 * amax[mi] * bmax[ni]
-        const double am = p.amax[row];
-        double *crow = p.c + row;
+        const double am = p.amax[static_cast<size_t>(entry) * p.amax_batch + row];
+        const double *bmax = p.bmax + static_cast<size_t>(entry) * p.bmax_batch;
+        double *cbase = p.c + static_cast<size_t>(entry) * p.c_batch * (p.cplx ? 2 : 1);
+        double *crow = cbase + row;
 #pragma unroll
         for (uint32_t j = 0; j < kCols; j++) {
           const uint32_t col = col0 + j;
@@ -394,9 +407,9 @@ oz_gemm_pair_kernel(const FusedParams p) {
             const double a_j = (j < kRegCols) ? acc[j % kRegCols] : spill[static_cast<size_t>(j - kRegCols) * BM];
             double x = __dmul_rn(a_j, 0x1p-44);
             x = __dmul_rn(x, am);
-            x = __dmul_rn(x, __ldg(p.bmax + col));
+            x = __dmul_rn(x, __ldg(bmax + col));
             if (p.cplx) {
-              double2 *dst = reinterpret_cast<double2 *>(p.c) + static_cast<size_t>(col) * p.ldc + row;
+              double2 *dst = reinterpret_cast<double2 *>(cbase) + static_cast<size_t>(col) * p.ldc + row;
               double2 y = make_double2(0.0, 0.0);
               if (p.cplx_init) {
                 if (p.beta != 0 || p.beta_im != 0) {
@@ -545,7 +558,8 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
     }
     max_pairs = once.value[dev];
   }
-  const uint32_t num_tiles = p.tiles_m * p.tiles_n;
+  if (p.batch == 0) p.batch = 1;
+  const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const uint32_t pairs = num_tiles < static_cast<uint32_t>(max_pairs) ? num_tiles : static_cast<uint32_t>(max_pairs);
   if (pairs == 0) return 0;
   cfg.gridDim = dim3(pairs * 2);
@@ -581,7 +595,8 @@ int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
     const uint64_t pairs = static_cast<uint64_t>(sms > 1 ? sms / 2 : 1);
     uint64_t best_cost = ~0ull;
     for (int cand : {256, 128}) {
-      const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 2 * BM)) * ceil_div_u32(p.n, cand);
+      const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 2 * BM)) * ceil_div_u32(p.n, cand) *
+                             (p.batch ? p.batch : 1);
       const uint64_t cost = ((tiles + pairs - 1) / pairs) * (128 + cand / 2);
       if (cost < best_cost) {
         best_cost = cost;
@@ -658,6 +673,34 @@ extern "C" int ozk_gemm_i8_fused_block(size_t m, size_t n, size_t k, const int8_
   p.rt_a = static_cast<uint32_t>(oz::slice_row_tiles(a_plane_rows));
   p.rt_b = static_cast<uint32_t>(oz::slice_row_tiles(b_plane_rows));
   p.no_lockstep = (flags & OZK_FUSED_NO_LOCKSTEP) ? 1u : 0u;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.c = c;
+  p.ldc = ldc;
+  p.amax = amax;
+  p.bmax = bmax;
+  return oz::dispatch_fused(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ozk_gemm_i8_fused_batched(size_t m, size_t n, size_t k, size_t batch, const int8_t *a_slices,
+                                         size_t a_batch_bytes, const int8_t *b_slices, size_t b_batch_bytes,
+                                         size_t pitch, const double *amax, size_t amax_batch, const double *bmax,
+                                         size_t bmax_batch, unsigned num_split, unsigned bits_per_int8,
+                                         double alpha, double beta, double *c, size_t ldc, size_t c_batch,
+                                         void *stream) {
+  if (m == 0 || n == 0 || batch == 0) return 0;
+  const size_t tiles = ((m + 255) / 256) * ((n + 127) / 128);  // upper bound (128-wide tiles)
+  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m || a_batch_bytes % 16 != 0 ||
+      b_batch_bytes % 16 != 0 || batch >= (1ull << 31) || tiles * batch >= (1ull << 31))
+    return static_cast<int>(cudaErrorInvalidValue);
+  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices, b_slices, num_split, bits_per_int8);
+  p.batch = static_cast<uint32_t>(batch);
+  p.a_batch_bytes = a_batch_bytes;
+  p.b_batch_bytes = b_batch_bytes;
+  p.amax_batch = amax_batch;
+  p.bmax_batch = bmax_batch;
+  p.c_batch = c_batch;
+  p.no_lockstep = 1;  // entries share no operands: nothing to gain from pacing the CTA pairs
   p.alpha = alpha;
   p.beta = beta;
   p.c = c;

@@ -137,9 +137,10 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
   // Block edges (multiples of 256, the kernel's tile): OZIMMU_B200_E2E_PANEL = columns of op(B) / C per block,
   // OZIMMU_B200_E2E_ROWBLOCK = rows of op(A) / C per block; 0 = the whole operand in one piece (ROWBLOCK=0:
-  // column panels only).  Read per call.
-  const std::size_t want_cols = env_size("OZIMMU_B200_E2E_PANEL", 1024);
-  const std::size_t want_rows = env_size("OZIMMU_B200_E2E_ROWBLOCK", 1024);
+  // column panels only).  Read per call.  768 measured best at 8192^3
+  // (profiles/r1_e2e_block_sweep.txt).
+  const std::size_t want_cols = env_size("OZIMMU_B200_E2E_PANEL", 768);
+  const std::size_t want_rows = env_size("OZIMMU_B200_E2E_ROWBLOCK", 768);
   const std::size_t cb = block_edge(n, want_cols == 0 ? n : want_cols), rb = block_edge(m, want_rows == 0 ? m : want_rows);
   const std::size_t nbb = (n + cb - 1) / cb, nab = (m + rb - 1) / rb;
 

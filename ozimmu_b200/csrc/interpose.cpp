@@ -141,6 +141,29 @@ cublasStatus_t ozaki_dgemm(cublasHandle_t handle, compute_mode_t mode, cublasOpe
   return ozaki_gemm(handle, mode, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mtk::ozimmu::real);
 }
 
+// the whole strided batch through one grouped launch (the reference loops: src/cublas.cu:380-406)
+cublasStatus_t ozaki_dgemm_batched(cublasHandle_t handle, compute_mode_t mode, cublasOperation_t ta, cublasOperation_t tb,
+                                   int m, int n, int k, const double *alpha, const double *A, int lda, long long strideA,
+                                   const double *B, int ldb, long long strideB, const double *beta, double *C, int ldc,
+                                   long long strideC, int batch) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  try {
+    handle_t h = global_handle();
+    cudaStream_t s = stream_of(handle);
+    set_cuda_stream(h, s);
+    CulipScope scope(s, std::string("D") + get_compute_mode_name_str(mode) + "-batched" + std::to_string(batch) + "-" +
+                            op_str(ta) + op_str(tb) + "-m" + std::to_string(m) + "-n" + std::to_string(n) + "-k" +
+                            std::to_string(k));
+    const int err = gemm_strided_batched(h, ta == CUBLAS_OP_N ? op_n : op_t, tb == CUBLAS_OP_N ? op_n : op_t, m, n, k,
+                                         alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
+                                         static_cast<std::size_t>(batch), mode);
+    return err ? CUBLAS_STATUS_INVALID_VALUE : CUBLAS_STATUS_SUCCESS;
+  } catch (const std::exception &e) {
+    H::log_error(e.what());
+    return CUBLAS_STATUS_INTERNAL_ERROR;
+  }
+}
+
 bool no_conj(cublasOperation_t ta, cublasOperation_t tb) { return ta != CUBLAS_OP_C && tb != CUBLAS_OP_C; }
 
 }  // namespace
@@ -253,7 +276,7 @@ cublasStatus_t cublasZgemm_v2(cublasHandle_t handle, cublasOperation_t transa, c
   return fn(handle, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
-// reference src/cublas.cu:315-472: one Ozaki GEMM per batch entry (:380-406)
+// reference src/cublas.cu:315-472 (one Ozaki GEMM per batch entry, :380-406): here one grouped launch
 cublasStatus_t cublasGemmStridedBatchedEx(cublasHandle_t handle, cublasOperation_t transa, cublasOperation_t transb, int m,
                                           int n, int k, const void *alpha, const void *A, cudaDataType_t Atype, int lda,
                                           long long strideA, const void *B, cudaDataType_t Btype, int ldb,
@@ -271,15 +294,23 @@ cublasStatus_t cublasGemmStridedBatchedEx(cublasHandle_t handle, cublasOperation
         H::log_error(e.what());
       }
     }
-    if (take) {
-      for (int i = 0; i < batchCount; i++) {
-        const cublasStatus_t st = ozaki_dgemm(
-            handle, mode, transa, transb, m, n, k, static_cast<const double *>(alpha),
-            static_cast<const double *>(A) + strideA * i, lda, static_cast<const double *>(B) + strideB * i, ldb,
-            static_cast<const double *>(beta), static_cast<double *>(C) + strideC * i, ldc);
-        if (st != CUBLAS_STATUS_SUCCESS) return st;
+    if (take && batchCount > 0) {
+      const auto *a = static_cast<const double *>(A);
+      const auto *b = static_cast<const double *>(B);
+      auto *c = static_cast<double *>(C);
+      // entries of C that overlap (or walk backwards) cannot run concurrently: entry by entry, as the reference
+      const unsigned long long span = static_cast<unsigned long long>(ldc) * (n > 0 ? n - 1 : 0) + m;
+      if (batchCount == 1 || strideC < 0 || static_cast<unsigned long long>(strideC) < span) {
+        for (int i = 0; i < batchCount; i++) {
+          const cublasStatus_t st =
+              ozaki_dgemm(handle, mode, transa, transb, m, n, k, static_cast<const double *>(alpha), a + strideA * i, lda,
+                          b + strideB * i, ldb, static_cast<const double *>(beta), c + strideC * i, ldc);
+          if (st != CUBLAS_STATUS_SUCCESS) return st;
+        }
+        return CUBLAS_STATUS_SUCCESS;
       }
-      return CUBLAS_STATUS_SUCCESS;
+      return ozaki_dgemm_batched(handle, mode, transa, transb, m, n, k, static_cast<const double *>(alpha), a, lda,
+                                 strideA, b, ldb, strideB, static_cast<const double *>(beta), c, ldc, strideC, batchCount);
     }
   }
   auto fn = real_fn<GemmStridedBatchedExFn>("cublasGemmStridedBatchedEx");

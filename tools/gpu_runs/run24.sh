@@ -1,3 +1,4 @@
-python -c "import torch; torch.zeros(1).cuda()"
-for n in 1024 2048; do timeout 200 python tools/perf_probe.py $n 9 --iters 50 --shapes 00,p128,p192,p256,11 2>&1 | head -12; done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 python tools/perf_probe.py 1024 9 --iters 1 2>&1 | grep -E "^\s+(void|oz)|gpu__time" | head -40
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests/test_gpu_batched.py tests/test_gpu_host_blocks.py tests/test_gpu_kernels.py tests/test_gpu_gemm.py -x -q) > gpurun_out/t_batched.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/t_batched.log
+(timeout 600 python tools/batched_probe.py) > gpurun_out/batched_probe.log 2>&1; echo "probe rc=$?"; cat gpurun_out/batched_probe.log
+(timeout 300 python tools/e2e_probe.py 8192 768:768 1024:1024) 2>&1 | tail -4
