@@ -70,6 +70,7 @@ struct FusedParams {
   uint32_t sync_window;        // a pair starts sync interval j only after interval j - window is complete
   uint32_t sync_len;           // counters available
   uint32_t prefetch_ahead;     // k-steps of L2 prefetch lead (OZIMMU_B200_PREFETCH, 0 = off)
+  uint32_t prefetch_coop;      // != 0: the pairs that share a panel split its prefetches among themselves
   uint32_t no_lockstep;        // host only: never pace this launch (it shares the GPU with other launches)
   // strided batch (grouped launch): tile index = entry * tiles_m * tiles_n + tile inside the entry; every entry
   // has its own slices / row scales / C at these distances (bytes for the slices, doubles for the rest)
@@ -237,13 +238,18 @@ oz_gemm_pair_kernel(const FusedParams p) {
           }
           for (uint32_t kb = 0; kb < p.k_blocks; kb++, g++) {
             if (p.prefetch_ahead && issuer) {
+              // Cooperative: the ~8 pairs of a wave that stream the same A panel (same tile row, consecutive
+              // tile columns) each prefetch every 8th k-block of it, likewise the 8 pairs of a band that share a B
+              // panel -- one request per panel chunk instead of one per pair.
               const uint32_t kf = kb + p.prefetch_ahead;
+              const bool do_a = !p.prefetch_coop || ((kf ^ tn) & 7u) == 0;
+              const bool do_b = !p.prefetch_coop || ((kf ^ tm) & 7u) == 0;
               if (kf < p.k_blocks) {
-                ptx::bulk_prefetch_l2(a_src + static_cast<size_t>(kf) * kTileBytes, BM * BK);
-                ptx::bulk_prefetch_l2(b_src + static_cast<size_t>(kf) * kTileBytes, Cfg::kBBytes);
+                if (do_a) ptx::bulk_prefetch_l2(a_src + static_cast<size_t>(kf) * kTileBytes, BM * BK);
+                if (do_b) ptx::bulk_prefetch_l2(b_src + static_cast<size_t>(kf) * kTileBytes, Cfg::kBBytes);
               } else if (a_nx != nullptr && kf - p.k_blocks < p.k_blocks) {
-                ptx::bulk_prefetch_l2(a_nx + static_cast<size_t>(kf - p.k_blocks) * kTileBytes, BM * BK);
-                ptx::bulk_prefetch_l2(b_nx + static_cast<size_t>(kf - p.k_blocks) * kTileBytes, Cfg::kBBytes);
+                if (do_a) ptx::bulk_prefetch_l2(a_nx + static_cast<size_t>(kf - p.k_blocks) * kTileBytes, BM * BK);
+                if (do_b) ptx::bulk_prefetch_l2(b_nx + static_cast<size_t>(kf - p.k_blocks) * kTileBytes, Cfg::kBBytes);
               }
             }
             if (lockstep && (g % kSyncEvery) == 0) {
@@ -488,6 +494,14 @@ uint32_t prefetch_ahead() {
   return v;
 }
 
+uint32_t prefetch_coop() {
+  static const uint32_t v = [] {
+    const char *e = std::getenv("OZIMMU_B200_PREFETCH_COOP");
+    return e ? static_cast<uint32_t>(std::atoi(e)) : 1u;
+  }();
+  return v;
+}
+
 constexpr uint32_t kSyncCounters = 1u << 16;  // per buffer: 64 Ki intervals = 1 Mi k-steps per CTA pair
 constexpr int kSyncBuffers = 8;               // launches that may be in flight at once without sharing
 uint32_t *next_sync_buffer() {
@@ -523,6 +537,7 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   if (p.rt_b == 0) p.rt_b = static_cast<uint32_t>(slice_row_tiles(p.n));
   p.sync_window = lockstep_window();
   p.prefetch_ahead = prefetch_ahead();
+  p.prefetch_coop = prefetch_coop();
 
   auto kern = oz_gemm_pair_kernel<BN_>;
   int dev = 0, sms = 0;

@@ -1,2 +1,10 @@
-python -c "import torch; torch.zeros(1).cuda()"
-for ls in 2 0; do for n in 1024 2048; do echo -n "LOCKSTEP=$ls "; OZIMMU_B200_LOCKSTEP=$ls timeout 200 python tools/perf_probe.py $n 9 --iters 50 --shapes 00,p128,p192,p256 2>&1 | head -4; done; done
+mkdir -p gpurun_out
+: > gpurun_out/prefetch_coop.log
+for rep in 1 2; do
+for cfg in "0 1" "8 1" "16 1" "32 1" "48 1" "16 0"; do
+  set -- $cfg
+  echo -n "rep$rep PREFETCH=$1 COOP=$2: " >> gpurun_out/prefetch_coop.log
+  OZIMMU_B200_PREFETCH=$1 OZIMMU_B200_PREFETCH_COOP=$2 timeout 300 python tools/perf_probe.py 8192 9 --iters 10 2>&1 | grep "^ozimmu_b200" >> gpurun_out/prefetch_coop.log
+done
+done
+cat gpurun_out/prefetch_coop.log
