@@ -271,8 +271,12 @@ def run_ours(args) -> dict:
     h = oz.create()
     L = oz.lib()
 
+    # B travels in column panels and every panel of C starts as soon as its columns have landed
+    # (OZIMMU_B200_BENCH_PIPELINE=0: one broadcast, then one product launch)
+    pipeline = os.environ.get("OZIMMU_B200_BENCH_PIPELINE", "1") != "0"
+
     def step():
-        rc = oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0)
+        rc = oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0, pipeline=pipeline)
         assert rc == 0
 
     sampler = ClockSampler(local)
@@ -298,7 +302,8 @@ def run_ours(args) -> dict:
             da.copy_(ha, non_blocking=True)
             if rank == 0:
                 db.copy_(hb, non_blocking=True)
-            assert oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, da, n, db, n, 0.0, dc, n, mode, src=0) == 0
+            assert oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, da, n, db, n, 0.0, dc, n, mode, src=0,
+                                   pipeline=pipeline) == 0
             hc.copy_(dc, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         h2d, d2h = (world + 1) * n * n * 8, world * n * n * 8

@@ -88,6 +88,16 @@ int gemm_strided_batched(handle_t handle, const operation_t op_A, const operatio
                          const std::size_t ldc, const long long stride_c, const std::size_t batch_count,
                          const compute_mode_t compute_mode);
 
+// Extension: the same real GEMM when B arrives column panel by column panel (e.g. as a broadcast from another
+// GPU delivers it): panel p = columns [col_edges[p], col_edges[p+1]) of op(B) and C (inner edges multiples of 256,
+// col_edges[0] = 0, col_edges[num_panels] = n, at most 16 panels) may be read once ready[p] -- an event the caller
+// records on any stream -- has fired.  Bit-identical to gemm().  Asynchronous on the handle's stream.
+int gemm_streamed_b(handle_t handle, const operation_t op_A, const operation_t op_B, const std::size_t m,
+                    const std::size_t n, const std::size_t k, const double *alpha, const double *const a_ptr,
+                    const std::size_t lda, const double *const b_ptr, const std::size_t ldb, const double *beta,
+                    double *const c_ptr, const std::size_t ldc, const compute_mode_t compute_mode,
+                    const std::size_t num_panels, const std::size_t *col_edges, const cudaEvent_t *ready);
+
 compute_mode_t auto_mode_select(handle_t handle, const operation_t op_A, const operation_t op_B,
                                 const std::size_t m, const std::size_t n, const std::size_t k,
                                 const void *const a_ptr, const std::size_t lda,

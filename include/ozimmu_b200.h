@@ -196,6 +196,17 @@ int ozimmu_gemm_strided_batched(ozimmu_handle_t handle, int op_a, int op_b, size
                                 const double *b, size_t ldb, long long stride_b, const double *beta, double *c,
                                 size_t ldc, long long stride_c, size_t batch, int compute_mode);
 
+/* ozimmu_gemm (real) when B becomes valid column panel by column panel -- the multi-GPU path broadcasts B that
+ * way -- so that split(A) and the products of the panels that have landed overlap the rest of the
+ * transfer.  Panel p = columns [col_edges[p], col_edges[p+1]) of op(B) and C: col_edges has num_panels + 1
+ * entries, col_edges[0] = 0, col_edges[num_panels] = n, inner edges multiples of 256, num_panels <= 16;
+ * ready_events[p] is a cudaEvent_t the caller recorded (on any stream) after panel p was written.
+ * Bit-identical to ozimmu_gemm; asynchronous on the handle's stream. */
+int ozimmu_gemm_streamed_b(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                           const double *alpha, const double *a, size_t lda, const double *b, size_t ldb,
+                           const double *beta, double *c, size_t ldc, int compute_mode, size_t num_panels,
+                           const size_t *col_edges, void *const *ready_events);
+
 /* :85-94 -- returns the selected compute mode (OZIMMU_FP64_INT8_3.. or OZIMMU_DGEMM);
  * negative on failure.  counters16 (host, optional) receives the 16 loss totals. */
 int ozimmu_auto_mode_select(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n,

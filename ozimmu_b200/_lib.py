@@ -37,6 +37,9 @@ PROTOTYPES = {
     "ozimmu_gemm_strided_batched": (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p,
                                             c_size_t, C.c_longlong, c_void_p, c_size_t, C.c_longlong, c_void_p, c_void_p,
                                             c_size_t, C.c_longlong, c_size_t, c_int]),
+    "ozimmu_gemm_streamed_b": (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t,
+                                       c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_size_t, c_void_p,
+                                       c_void_p]),
     "ozk_mantissa_loss_strided": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int, c_uint,
                                           c_uint, c_void_p]),
     "ozk_gemm_i8_fused_complex": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p,

@@ -189,6 +189,23 @@ def gemm_strided_batched(handle: handle_t, op_A: operation_t, op_B: operation_t,
     return _check(rc, "gemm_strided_batched")
 
 
+def gemm_streamed_b(handle: handle_t, op_A: operation_t, op_B: operation_t, m: int, n: int, k: int, alpha: float, a_ptr,
+                    lda: int, b_ptr, ldb: int, beta: float, c_ptr, ldc: int, compute_mode: compute_mode_t,
+                    col_edges: Sequence[int], ready_events: Sequence[int]) -> int:
+    """gemm() when B becomes valid column panel by column panel: panel p = columns [col_edges[p], col_edges[p+1])
+    may be read once the CUDA event ready_events[p] (raw cudaEvent_t handles, e.g. torch.cuda.Event.cuda_event) has
+    fired.  Inner edges must be multiples of 256.  Asynchronous on the handle's stream."""
+    al, be = C.c_double(alpha), C.c_double(beta)
+    npan = len(ready_events)
+    assert len(col_edges) == npan + 1
+    edges = (C.c_size_t * (npan + 1))(*[int(x) for x in col_edges])
+    evs = (C.c_void_p * npan)(*[int(e) for e in ready_events])
+    rc = _lib.lib().ozimmu_gemm_streamed_b(handle.raw, int(op_A), int(op_B), m, n, k, C.addressof(al), _ptr(a_ptr), lda,
+                                           _ptr(b_ptr), ldb, C.addressof(be), _ptr(c_ptr), ldc, int(compute_mode), npan,
+                                           C.addressof(edges), C.addressof(evs))
+    return _check(rc, "gemm_streamed_b")
+
+
 def gemm_host(handle: handle_t, op_A: operation_t, op_B: operation_t, m: int, n: int, k: int, alpha: float, a_host,
               lda: int, b_host, ldb: int, beta: float, c_host, ldc: int, compute_mode: compute_mode_t) -> int:
     """Same product with HOST operands (numpy arrays / pinned CPU tensors); returns when C is complete."""

@@ -494,6 +494,89 @@ int mtk::ozimmu::gemm(handle_t h, const operation_t op_A, const operation_t op_B
                            " is not implemented");
 }
 
+// Not in the reference: B becomes valid column panel by column panel (the multi-GPU path broadcasts it that way,
+// SURVEY 8e), and every panel of C is computed as soon as its columns of B are there.  split(A) and the products of
+// the panels that have landed run while the rest of B is still on the wire; the launches rotate over the product
+// streams so that each back-fills the SMs its predecessor leaves idle in its last round of tiles.
+int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const operation_t op_B, const std::size_t m,
+                                 const std::size_t n, const std::size_t k, const double *alpha, const double *const a_ptr,
+                                 const std::size_t lda, const double *const b_ptr, const std::size_t ldb,
+                                 const double *beta, double *const c_ptr, const std::size_t ldc,
+                                 const compute_mode_t compute_mode, const std::size_t num_panels,
+                                 const std::size_t *col_edges, const cudaEvent_t *ready) {
+  int arg_error = 0;
+  arg_error |= check_shape(op_A, m, k, lda, "A");
+  arg_error |= check_shape(op_B, k, n, ldb, "B");
+  arg_error |= check_shape(op_n, m, n, ldc, "C");
+  arg_error |= check_alignment(a_ptr, sizeof(double), "A");
+  arg_error |= check_alignment(b_ptr, sizeof(double), "B");
+  arg_error |= check_alignment(c_ptr, sizeof(double), "C");
+  if (num_panels == 0 || num_panels > static_cast<std::size_t>(handle::kMaxBlocks) || col_edges == nullptr ||
+      ready == nullptr || col_edges[0] != 0 || col_edges[num_panels] != n) {
+    H::log_error("gemm_streamed_b: 1.." + std::to_string(handle::kMaxBlocks) +
+                 " panels, col_edges[0] = 0, col_edges[num_panels] = n");
+    arg_error |= 1;
+  } else {
+    for (std::size_t p = 0; p < num_panels; p++)
+      if (col_edges[p] > col_edges[p + 1] || (p + 1 < num_panels && col_edges[p + 1] % 256 != 0)) {
+        H::log_error("gemm_streamed_b: inner panel edges must be ascending multiples of 256");
+        arg_error |= 1;
+        break;
+      }
+  }
+  if (arg_error) return 1;
+  cudaStream_t s = h->cuda_stream;
+  if (!H::is_int8_mode(compute_mode) || k == 0 || m == 0 || n == 0 || h->profiler.enabled) {
+    // auto mode looks at all of B first, dgemm is cuBLAS: wait for every panel, then the plain call
+    for (std::size_t p = 0; p < num_panels; p++) OZ_CUDA_CHECK(cudaStreamWaitEvent(s, ready[p], 0));
+    return gemm(h, op_A, op_B, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc, compute_mode, real);
+  }
+  const unsigned num_split = H::num_split_of(compute_mode);
+  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
+  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split);
+  reallocate_working_memory(h, w.total);
+  ensure_streams(h);
+  H::ensure_pipeline_streams(h);
+  char *ws = static_cast<char *>(h->working_memory_ptr);
+  double *amax = reinterpret_cast<double *>(ws + w.off_amax);
+  double *bmax = reinterpret_cast<double *>(ws + w.off_bmax);
+  auto *scr_a = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_a);
+  auto *scr_b = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_b);
+  auto *a_sl = reinterpret_cast<std::int8_t *>(ws + w.off_a_slices);
+  auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
+  wait_previous(h, s);
+  cudaStream_t sb = h->aux_stream;
+  OZ_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));
+  OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, h->ev_fork, 0));
+  OZ_KERNEL_CHECK(ozk_split_int8(a_sl, w.pitch, amax, scr_a, m, k, a_ptr, lda, op_A == op_n, num_split, bits, s));
+  cudaEvent_t ev_a = h->ev_block_split[0][0];
+  OZ_CUDA_CHECK(cudaEventRecord(ev_a, s));  // also orders the products after everything queued on s before this call
+  bool used[handle::kProductStreams] = {};
+  for (std::size_t p = 0; p < num_panels; p++) {
+    const std::size_t j0 = col_edges[p], nj = col_edges[p + 1] - j0;
+    if (nj == 0) continue;
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, ready[p], 0));
+    const double *src = (op_B == op_n) ? b_ptr + j0 * ldb : b_ptr + j0;
+    OZ_KERNEL_CHECK(ozk_split_int8_block(b_sl, w.pitch, n, j0, bmax + j0, scr_b + j0, nj, k, src, ldb, op_B != op_n,
+                                         num_split, bits, 1, sb));
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[1][p], sb));
+    const int r = static_cast<int>(p % handle::kProductStreams);
+    cudaStream_t sp = h->product_stream[r];
+    used[r] = true;
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_a, 0));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, h->ev_block_split[1][p], 0));
+    OZ_KERNEL_CHECK(ozk_gemm_i8_fused_block(m, nj, k, a_sl, m, 0, b_sl, n, j0, w.pitch, amax, bmax + j0, num_split, bits,
+                                            *alpha, *beta, c_ptr + j0 * ldc, ldc, OZK_FUSED_NO_LOCKSTEP, sp));
+  }
+  for (int r = 0; r < handle::kProductStreams; r++) {
+    if (!used[r]) continue;
+    OZ_CUDA_CHECK(cudaEventRecord(h->ev_product_tail[r], h->product_stream[r]));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_product_tail[r], 0));
+  }
+  mark_done(h, s);
+  return 0;
+}
+
 // Not in the reference's header: its strided-batched interposers loop over gemm() (src/cublas.cu:380-406).
 int mtk::ozimmu::gemm_strided_batched(handle_t h, const operation_t op_A, const operation_t op_B, const std::size_t m,
                                       const std::size_t n, const std::size_t k, const double *alpha,
@@ -617,6 +700,21 @@ int ozimmu_gemm_strided_batched(ozimmu_handle_t handle, int op_a, int op_b, size
     return gemm_strided_batched(reinterpret_cast<handle_t>(handle), static_cast<operation_t>(op_a != 0),
                                 static_cast<operation_t>(op_b != 0), m, n, k, alpha, a, lda, stride_a, b, ldb, stride_b,
                                 beta, c, ldc, stride_c, batch, static_cast<compute_mode_t>(compute_mode));
+  });
+}
+
+int ozimmu_gemm_streamed_b(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                           const double *alpha, const double *a, size_t lda, const double *b, size_t ldb,
+                           const double *beta, double *c, size_t ldc, int compute_mode, size_t num_panels,
+                           const size_t *col_edges, void *const *ready_events) {
+  if (handle == nullptr || alpha == nullptr || beta == nullptr || compute_mode < 0 ||
+      compute_mode > OZIMMU_FP64_INT8_AUTO)
+    return 1;
+  return guarded([&] {
+    return gemm_streamed_b(reinterpret_cast<handle_t>(handle), static_cast<operation_t>(op_a != 0),
+                           static_cast<operation_t>(op_b != 0), m, n, k, alpha, a, lda, b, ldb, beta, c, ldc,
+                           static_cast<compute_mode_t>(compute_mode), num_panels, col_edges,
+                           reinterpret_cast<const cudaEvent_t *>(ready_events));
   });
 }
 

@@ -75,6 +75,8 @@ inline mtk::ozimmu::compute_mode_t mode_of_num_split(unsigned s) {
 
 // lazily created aux stream + ordering events of a handle
 void ensure_streams(mtk::ozimmu::handle *h);
+// lazily created copy / split / product streams and per-block events (host_e2e.cu)
+void ensure_pipeline_streams(mtk::ozimmu::handle *h);
 
 // reference src/config.cu:85-92: the ordered (A_id, B_id) list of one fp64_int8_S product sweep
 std::vector<std::pair<int, int>> pair_list(unsigned num_split);

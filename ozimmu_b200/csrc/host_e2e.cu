@@ -45,7 +45,10 @@ void ensure_stage(void **ptr, std::size_t *have, std::size_t need) {
   *have = need;
 }
 
-void ensure_e2e_streams(handle_t h) {
+}  // namespace
+
+// copy / split / product streams and events shared by the host-operand pipeline and gemm_streamed_b
+void oz::host::ensure_pipeline_streams(mtk::ozimmu::handle *h) {
   if (h->h2d_stream) return;
   int lo = 0, hi = 0;
   OZ_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -62,6 +65,8 @@ void ensure_e2e_streams(handle_t h) {
   for (auto &e : h->ev_rect_out) make(e);
   for (auto &e : h->ev_product_tail) make(e);
 }
+
+namespace {
 
 // block edge: `want` rounded up to the kernel's 256-row tile, grown until `extent` needs at most kMaxBlocks
 std::size_t block_edge(std::size_t extent, std::size_t want) {
@@ -99,7 +104,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     return 1;
   }
   if (m == 0 || n == 0) return 0;
-  ensure_e2e_streams(h);
+  H::ensure_pipeline_streams(h);
   H::ensure_streams(h);
   const std::size_t a_rows = (op_a == op_n) ? m : k, a_cols = (op_a == op_n) ? k : m;
   const std::size_t b_rows = (op_b == op_n) ? k : n, b_cols = (op_b == op_n) ? n : k;

@@ -4,11 +4,11 @@
 on its block.  Bit-identical to the one-GPU result: the split scales A per row and B per column and
 K is never partitioned, so no cross-shard reduction exists.
 
-By default B travels as ONE broadcast followed by one product over the whole row block (the fused
-kernel then runs a single persistent launch, 14 full rounds of tiles at 8192^2).  `pipeline=True` sends B
-in column panels (contiguous for op_n B) and runs split + product per panel while the next panel is on the
-wire; on NVLink 5 the broadcast (512 MiB in < 1 ms) is too short to repay the ragged last round that each
-per-panel launch adds, so it is off unless B is very large relative to the product.
+`pipeline=True` (op_n B) sends B in contiguous column panels and hands the panels' arrival events to
+`gemm_streamed_b`: split(A) runs while the first panel is on the wire, and every panel of C is computed as soon
+as its columns of B have landed (the fused launches rotate over several streams, so a launch back-fills the SMs
+its predecessor leaves idle in its last round of tiles).  `pipeline=False` is one broadcast followed by one
+product launch.
 """
 from __future__ import annotations
 
@@ -27,10 +27,11 @@ def row_block(m: int, world_size: int, rank: int) -> Tuple[int, int]:
 
 
 def column_panels(n: int, max_panels: int = 4, min_width: int = 1024) -> List[Tuple[int, int]]:
-    """(first column, width) of the broadcast panels: equal widths, multiples of 128, at least min_width."""
+    """(first column, width) of the broadcast panels: equal widths, multiples of 256 (the kernel's tile and the
+    block-wise split's granularity), at least min_width."""
     panels = max(1, min(max_panels, n // max(1, min_width)))
     w = -(-n // panels)
-    w = -(-w // 128) * 128
+    w = -(-w // 256) * 256
     out = []
     j = 0
     while j < n:
@@ -55,22 +56,47 @@ def sharded_gemm(handle: api.handle_t, op_A: int, op_B: int, m_local: int, n: in
         return api.gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
                         compute_mode)
     flat = b.view(-1)
-    if not pipeline or int(op_B) != int(api.op_n) or m_local == 0:
+    if not pipeline or int(op_B) != int(api.op_n) or m_local == 0 or n < 2 * _MIN_PANEL:
         dist.broadcast(flat, src=src, group=group)
         if m_local == 0:
             return 0
         return api.gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
                         compute_mode)
     # op_n B: k x n column-major, panel [j0, j0 + w) is the contiguous range [j0*ldb, (j0+w)*ldb)
-    panels = column_panels(n)
-    works = []
-    for (j0, w) in panels:
-        hi = min(flat.numel(), (j0 + w) * ldb)
-        works.append(dist.broadcast(flat[j0 * ldb:hi], src=src, group=group, async_op=True))
-    cflat = c_block.view(-1)
-    rc = 0
-    for (j0, w), work in zip(panels, works):
-        work.wait()  # orders the current stream after this panel's broadcast
-        rc |= api.gemm(handle, op_A, op_B, m_local, w, k, alpha, a_block, lda, flat[j0 * ldb:], ldb, beta,
-                       cflat[j0 * ldc:], ldc, compute_mode)
+    panels = column_panels(n, max_panels=8, min_width=_MIN_PANEL)
+    side = _side_stream()
+    side.wait_stream(torch.cuda.current_stream())     # whatever produced / last read `b` on this stream
+    events = []
+    with torch.cuda.stream(side):
+        for (j0, w) in panels:
+            hi = min(flat.numel(), (j0 + w) * ldb)
+            work = dist.broadcast(flat[j0 * ldb:hi], src=src, group=group, async_op=True)
+            work.wait()                               # orders `side` after this panel's broadcast
+            ev = torch.cuda.Event()
+            ev.record(side)
+            events.append(ev)
+    edges = [j0 for (j0, _) in panels] + [n]
+    rc = api.gemm_streamed_b(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
+                             compute_mode, edges, [ev.cuda_event for ev in events])
+    _keep_alive(events)
     return rc
+
+
+_MIN_PANEL = 1024
+_side = {}
+_live_events: list = []
+
+
+def _side_stream():
+    """one broadcast-ordering stream per device"""
+    import torch
+    dev = torch.cuda.current_device()
+    if dev not in _side:
+        _side[dev] = torch.cuda.Stream(device=dev)
+    return _side[dev]
+
+
+def _keep_alive(events) -> None:
+    """the library's streams still wait on these events after this call returns: keep the last two calls' events"""
+    _live_events.append(events)
+    del _live_events[:-2]

@@ -150,3 +150,47 @@ def test_gemm_host_many_blocks_is_capped(handle, monkeypatch):
     hc = np.zeros(m * n)
     assert oz.gemm_host(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, hc, m, oz.fp64_int8(6)) == 0
     assert np.array_equal(bits(hc), bits(dc))
+
+
+@pytest.mark.parametrize("op_a,op_b,beta", [(0, 0, 0.0), (1, 0, -1.5), (0, 1, 0.5)])
+def test_gemm_streamed_b_equals_gemm(handle, op_a, op_b, beta):
+    """B filled panel by panel on a side stream (as the multi-GPU broadcast does), each panel guarded by an event:
+    the result is the plain call's, bit for bit -- also when the panels are completed in reverse order."""
+    m, n, k = 700, 1900, 900
+    lda = m if op_a == 0 else k
+    ldb = k if op_b == 0 else n
+    a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 61))
+    b_full = to_dev(oracle_lib.gen_matrix("exp_rand-1", k * n, 62))
+    c0 = oracle_lib.gen_matrix("normal01", m * n, 63)
+    want = to_dev(c0)
+    assert oz.gemm(handle, op_a, op_b, m, n, k, 2.0, a, lda, b_full, ldb, beta, want, m, oz.fp64_int8(10)) == 0
+    torch.cuda.synchronize()
+    edges = [0, 512, 1280, n]
+    b = torch.zeros_like(b_full)
+    got = to_dev(c0)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    events = [torch.cuda.Event() for _ in range(3)]
+    bv, bfv = (b.view(n, k), b_full.view(n, k)) if op_b == 0 else (b.view(k, n), b_full.view(k, n))
+    with torch.cuda.stream(side):
+        for p in (2, 1, 0):
+            torch.cuda._sleep(2_000_000)          # the panels really are late
+            j0, j1 = edges[p], edges[p + 1]
+            if op_b == 0:
+                bv[j0:j1].copy_(bfv[j0:j1])       # k x n column-major: columns j0..j1 are contiguous rows of the view
+            else:
+                bv[:, j0:j1].copy_(bfv[:, j0:j1])  # n x k column-major: rows j0..j1 of every column
+            events[p].record(side)
+    assert oz.gemm_streamed_b(handle, op_a, op_b, m, n, k, 2.0, a, lda, b, ldb, beta, got, m, oz.fp64_int8(10), edges,
+                              [e.cuda_event for e in events]) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int64), want.view(torch.int64))
+    # invalid panel edges are rejected
+    assert oz.gemm_streamed_b(handle, op_a, op_b, m, n, k, 2.0, a, lda, b, ldb, beta, got, m, oz.fp64_int8(10),
+                              [0, 500, n], [events[0].cuda_event, events[1].cuda_event]) == 1
+    # dgemm / auto fall back to the plain call after waiting for every panel
+    got_d = to_dev(c0)
+    assert oz.gemm_streamed_b(handle, op_a, op_b, m, n, k, 2.0, a, lda, b, ldb, beta, got_d, m,
+                              oz.compute_mode_t.dgemm, edges, [e.cuda_event for e in events]) == 0
+    torch.cuda.synchronize()
+    assert torch.allclose(got_d, want, rtol=1e-11, atol=1e-11)
