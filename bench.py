@@ -271,9 +271,11 @@ def run_ours(args) -> dict:
     h = oz.create()
     L = oz.lib()
 
-    # B travels in column panels and every panel of C starts as soon as its columns have landed
-    # (OZIMMU_B200_BENCH_PIPELINE=0: one broadcast, then one product launch)
-    pipeline = os.environ.get("OZIMMU_B200_BENCH_PIPELINE", "1") != "0"
+    # one broadcast of B, then one product launch.  OZIMMU_B200_BENCH_PIPELINE=1: B travels in column panels and
+    # every panel of C starts as soon as its columns have landed (gemm_streamed_b) -- measured SLOWER on 2 x B200
+    # (21.1 vs 19.1 ms, profiles/r1_bench_2gpu_streamed_b.txt): NCCL's broadcast kernels need SMs, and the persistent
+    # product kernel holds all of them, so the later panels' broadcasts wait for whole rounds of tiles.
+    pipeline = os.environ.get("OZIMMU_B200_BENCH_PIPELINE", "0") == "1"
 
     def step():
         rc = oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0, pipeline=pipeline)

@@ -7,8 +7,11 @@ K is never partitioned, so no cross-shard reduction exists.
 `pipeline=True` (op_n B) sends B in contiguous column panels and hands the panels' arrival events to
 `gemm_streamed_b`: split(A) runs while the first panel is on the wire, and every panel of C is computed as soon
 as its columns of B have landed (the fused launches rotate over several streams, so a launch back-fills the SMs
-its predecessor leaves idle in its last round of tiles).  `pipeline=False` is one broadcast followed by one
-product launch.
+its predecessor leaves idle in its last round of tiles).  `pipeline=False` (default) is one broadcast followed
+by one product launch.  Measured on 2 x B200 at 8192 rows per rank the pipeline is SLOWER (21.1 vs 19.1 ms per step,
+profiles/r1_bench_2gpu_streamed_b.txt): NCCL's broadcast kernels need SMs of their own, the persistent product
+kernel occupies every SM, so each later panel's broadcast waits for a whole round of tiles to drain.  It pays only
+when the transport does not need SMs (copy-engine peer copies, host staging) -- kept for those callers.
 """
 from __future__ import annotations
 
