@@ -490,6 +490,13 @@ int mtk::ozimmu::gemm(handle_t h, const operation_t op_A, const operation_t op_B
       throw std::runtime_error("ozIMMU: cublasGemmEx passthrough failed with status " + std::to_string(st));
     return 0;
   }
+  if (compute_mode == sgemm) {
+    ensure_streams(h);
+    H::gemm_in_f32(h, private_cublas(h), op_A, op_B, m, n, k, static_cast<const double *>(alpha),
+                   static_cast<const double *>(a_ptr), lda, static_cast<const double *>(b_ptr), ldb,
+                   static_cast<const double *>(beta), static_cast<double *>(c_ptr), ldc, element_kind);
+    return 0;
+  }
   throw std::runtime_error("ozIMMU: compute mode " + get_compute_mode_name_str(compute_mode) +
                            " is not implemented");
 }

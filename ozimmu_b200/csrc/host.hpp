@@ -78,6 +78,13 @@ void ensure_streams(mtk::ozimmu::handle *h);
 // lazily created copy / split / product streams and per-block events (host_e2e.cu)
 void ensure_pipeline_streams(mtk::ozimmu::handle *h);
 
+// compute mode `sgemm` (reference src/cublas_helper.cu:84-134): the GEMM in FP32 through cuBLAS (sgemm_mode.cu).
+// `cublas` = a real cuBLAS handle bound to the handle's stream; alpha / beta: 1 (real) or 2 (complex) doubles.
+void gemm_in_f32(mtk::ozimmu::handle *h, cublasHandle_t cublas, mtk::ozimmu::operation_t op_a,
+                 mtk::ozimmu::operation_t op_b, std::size_t m, std::size_t n, std::size_t k, const double *alpha,
+                 const double *a, std::size_t lda, const double *b, std::size_t ldb, const double *beta, double *c,
+                 std::size_t ldc, mtk::ozimmu::element_kind_t kind);
+
 // reference src/config.cu:85-92: the ordered (A_id, B_id) list of one fp64_int8_S product sweep
 std::vector<std::pair<int, int>> pair_list(unsigned num_split);
 

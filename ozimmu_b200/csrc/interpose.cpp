@@ -86,7 +86,7 @@ cudaStream_t stream_of(cublasHandle_t handle) {
 // reference src/cublas.cu:143-148 (with the THRESHOLD_N fix)
 bool should_intercept(handle_t h, compute_mode_t mode, int m, int n, int k, cudaDataType_t a, cudaDataType_t b,
                       cudaDataType_t c) {
-  return mode != dgemm && mode != sgemm && m >= 0 && n >= 0 && k >= 0 &&
+  return mode != dgemm && m >= 0 && n >= 0 && k >= 0 &&
          static_cast<std::uint32_t>(m) >= h->intercept_threshold_m &&
          static_cast<std::uint32_t>(n) >= h->intercept_threshold_n &&
          static_cast<std::uint32_t>(k) >= h->intercept_threshold_k &&
@@ -203,7 +203,7 @@ cublasStatus_t cublasGemmEx(cublasHandle_t handle, cublasOperation_t transa, cub
   const compute_mode_t mode = env_compute_mode();
   const bool is_real = Atype == CUDA_R_64F && Btype == CUDA_R_64F && Ctype == CUDA_R_64F;
   const bool is_cplx = Atype == CUDA_C_64F && Btype == CUDA_C_64F && Ctype == CUDA_C_64F && no_conj(transa, transb);
-  if (mode != dgemm && mode != sgemm && (is_real || is_cplx)) {
+  if (mode != dgemm && (is_real || is_cplx)) {
     bool take = false;
     {
       std::lock_guard<std::mutex> lock(g_mu);
@@ -230,7 +230,7 @@ cublasStatus_t cublasDgemm_v2(cublasHandle_t handle, cublasOperation_t transa, c
                               int k, const double *alpha, const double *A, int lda, const double *B, int ldb,
                               const double *beta, double *C, int ldc) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm && mode != sgemm) {
+  if (mode != dgemm) {
     bool take = false;
     {
       std::lock_guard<std::mutex> lock(g_mu);
@@ -256,7 +256,7 @@ cublasStatus_t cublasZgemm_v2(cublasHandle_t handle, cublasOperation_t transa, c
                               const cuDoubleComplex *B, int ldb, const cuDoubleComplex *beta, cuDoubleComplex *C,
                               int ldc) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm && mode != sgemm && no_conj(transa, transb)) {
+  if (mode != dgemm && no_conj(transa, transb)) {
     bool take = false;
     {
       std::lock_guard<std::mutex> lock(g_mu);
@@ -284,7 +284,7 @@ cublasStatus_t cublasGemmStridedBatchedEx(cublasHandle_t handle, cublasOperation
                                           long long strideC, int batchCount, cublasComputeType_t computeType,
                                           cublasGemmAlgo_t algo) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm && mode != sgemm && Atype == CUDA_R_64F && Btype == CUDA_R_64F && Ctype == CUDA_R_64F) {
+  if (mode != dgemm && Atype == CUDA_R_64F && Btype == CUDA_R_64F && Ctype == CUDA_R_64F) {
     bool take = false;
     {
       std::lock_guard<std::mutex> lock(g_mu);
@@ -325,7 +325,7 @@ cublasStatus_t cublasDgemmStridedBatched(cublasHandle_t handle, cublasOperation_
                                          const double *B, int ldb, long long strideB, const double *beta, double *C,
                                          int ldc, long long strideC, int batchCount) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm && mode != sgemm)
+  if (mode != dgemm)
     return cublasGemmStridedBatchedEx(handle, transa, transb, m, n, k, alpha, A, CUDA_R_64F, lda, strideA, B, CUDA_R_64F,
                                       ldb, strideB, beta, C, CUDA_R_64F, ldc, strideC, batchCount, CUBLAS_COMPUTE_64F,
                                       CUBLAS_GEMM_DEFAULT);

@@ -151,3 +151,35 @@ def test_cuda_graph_capture(handle):
         torch.cuda.synchronize()
         assert torch.equal(c_graph.view(torch.int64), c_eager.view(torch.int64))
     oz.set_cuda_stream(handle, None)
+
+
+@pytest.mark.parametrize("op_a,op_b,beta", [(0, 0, 0.0), (1, 0, -0.5), (0, 1, 2.0), (1, 1, 0.0)])
+def test_sgemm_mode_real(handle, op_a, op_b, beta):
+    """compute mode `sgemm` (reference src/cublas_helper.cu:84-134): FP64 in / out, FP32 GEMM inside -- equal to an
+    FP32 matmul of the rounded operands up to FP32 summation order, padded leading dimensions untouched."""
+    m, n, k, pad = 300, 200, 500, 3
+    lda, ldb, ldc = (m if op_a == 0 else k) + pad, (k if op_b == 0 else n) + pad, m + pad
+    A = torch.randn(k if op_a == 0 else m, lda, dtype=torch.float64, device="cuda")     # [col][row]
+    B = torch.randn(n if op_b == 0 else k, ldb, dtype=torch.float64, device="cuda")
+    C0 = torch.randn(n, ldc, dtype=torch.float64, device="cuda")
+    C = C0.clone()
+    assert oz.gemm(handle, op_a, op_b, m, n, k, 1.5, A, lda, B, ldb, beta, C, ldc, oz.compute_mode_t.sgemm) == 0
+    torch.cuda.synchronize()
+    opA = (A[:, :m].T if op_a == 0 else A[:, :k]).float()      # m x k
+    opB = (B[:, :k].T if op_b == 0 else B[:, :n]).float()      # k x n
+    ref = 1.5 * (opA.double() @ opB.double()) + beta * C0[:, :m].T.float().double()
+    got = C[:, :m].T
+    assert (torch.linalg.norm(got - ref) / torch.linalg.norm(ref)).item() < 1e-5
+    assert torch.equal(got, got.float().double())               # every output is an FP32 value
+    assert torch.equal(C[:, m:], C0[:, m:])                     # ld padding untouched
+
+
+def test_sgemm_mode_complex(handle):
+    m, n, k = 128, 96, 200
+    A = torch.randn(k, m, dtype=torch.complex128, device="cuda")   # column-major m x k
+    B = torch.randn(n, k, dtype=torch.complex128, device="cuda")   # column-major k x n
+    C = torch.zeros(n, m, dtype=torch.complex128, device="cuda")
+    assert oz.gemm(handle, 0, 0, m, n, k, 1.0 + 0.5j, A, m, B, k, 0j, C, m, oz.compute_mode_t.sgemm, oz.complx) == 0
+    torch.cuda.synchronize()
+    ref = (1.0 + 0.5j) * (B @ A)
+    assert (torch.linalg.norm(C - ref) / torch.linalg.norm(ref)).item() < 1e-5

@@ -1,5 +1,11 @@
-(timeout 200 python -m pytest tests/test_gpu_kernels.py -q --maxfail=3 -x -k "pair_product") 2>&1 | tail -3
-(timeout 300 python -m pytest tests/test_gpu_gemm.py -q --maxfail=4 -k "oracle or 8192 or cluster") 2>&1 | tail -3
-(timeout 120 python tools/perf_probe.py 8192 9 --iters 10 --shapes 00,p128) 2>&1 | head -6
-(timeout 120 python tools/perf_probe.py 4096 9 --iters 10) 2>&1 | head -1
-(timeout 120 python tools/perf_probe.py 1024 9 --iters 30 --shapes 00,p256) 2>&1 | head -2
+mkdir -p gpurun_out
+: > gpurun_out/nccl_bcast.log
+run() { env "$@" timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29556 tools/ubench/nccl_bcast.py 2>&1 | grep "^world" >> gpurun_out/nccl_bcast.log; }
+run NCCL_DEBUG=WARN
+run NCCL_MIN_NCHANNELS=16
+run NCCL_MIN_NCHANNELS=32
+run NCCL_MIN_NCHANNELS=32 NCCL_NTHREADS=512
+run NCCL_PROTO=Simple NCCL_MIN_NCHANNELS=24
+run NCCL_ALGO=Ring NCCL_MIN_NCHANNELS=32
+run NCCL_P2P_USE_CUDA_MEMCPY=1
+cat gpurun_out/nccl_bcast.log
