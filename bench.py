@@ -276,9 +276,11 @@ def run_ours(args) -> dict:
     # (21.1 vs 19.1 ms, profiles/r1_bench_2gpu_streamed_b.txt): NCCL's broadcast kernels need SMs, and the persistent
     # product kernel holds all of them, so the later panels' broadcasts wait for whole rounds of tiles.
     pipeline = os.environ.get("OZIMMU_B200_BENCH_PIPELINE", "0") == "1"
+    transport = os.environ.get("OZIMMU_B200_BENCH_TRANSPORT", "nccl")
 
     def step():
-        rc = oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0, pipeline=pipeline)
+        rc = oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0, pipeline=pipeline,
+                             transport=transport)
         assert rc == 0
 
     sampler = ClockSampler(local)
@@ -305,7 +307,7 @@ def run_ours(args) -> dict:
             if rank == 0:
                 db.copy_(hb, non_blocking=True)
             assert oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, da, n, db, n, 0.0, dc, n, mode, src=0,
-                                   pipeline=pipeline) == 0
+                                   pipeline=pipeline, transport=transport) == 0
             hc.copy_(dc, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         h2d, d2h = (world + 1) * n * n * 8, world * n * n * 8

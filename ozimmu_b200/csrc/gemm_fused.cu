@@ -575,8 +575,14 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   }
   if (p.batch == 0) p.batch = 1;
   const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
-  const uint32_t pairs = num_tiles < static_cast<uint32_t>(max_pairs) ? num_tiles : static_cast<uint32_t>(max_pairs);
-  if (pairs == 0) return 0;
+  if (num_tiles == 0) return 0;
+  // Every CTA pair gets the same number of tiles (+-1): the launch needs `rounds` rounds either way, and a pair with a
+  // short tile list would only exit early when the launch's own grid is wider than needed.  Launching
+  // ceil(tiles / rounds) pairs instead leaves the other SMs to a concurrent launch for the WHOLE duration (the block
+  // pipelines rotate launches over several streams); with the full grid and 128 tiles, 20 pairs run one tile and 54
+  // run two, and whichever CTAs of the next launch start late still own two tiles -- 2 rounds per 1.73 rounds of work.
+  const uint32_t rounds = ceil_div_u32(num_tiles, static_cast<uint32_t>(max_pairs));
+  const uint32_t pairs = ceil_div_u32(num_tiles, rounds);
   cfg.gridDim = dim3(pairs * 2);
   // lockstep counters only pay off when several rounds of tiles stream through L2 (pairs cannot drift apart
   // within a single round, and the polling costs ~7 % there)

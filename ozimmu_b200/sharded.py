@@ -45,12 +45,18 @@ def column_panels(n: int, max_panels: int = 4, min_width: int = 1024) -> List[Tu
 
 def sharded_gemm(handle: api.handle_t, op_A: int, op_B: int, m_local: int, n: int, k: int, alpha: float, a_block,
                  lda: int, b, ldb: int, beta: float, c_block, ldc: int, compute_mode, *, src: int = 0, group=None,
-                 pipeline: bool = False) -> int:
+                 pipeline: bool = False, transport: str = "nccl") -> int:
     """C_block = alpha * op(A_block) * op(B) + beta * C_block on every rank.
 
     a_block / c_block: this rank's rows (device, column-major).  b: device buffer of the full B on every
     rank; its CONTENT is taken from rank `src` (the broadcast overwrites the other ranks' copies).
     Without an initialised process group (single GPU) this is a plain api.gemm.
+
+    transport="nccl": B is replicated by a NCCL broadcast (`pipeline` = in column panels feeding gemm_streamed_b).
+    transport="peer" (op_n B): every rank PULLS B's column panels from the owner's buffer over NVLink with the copy
+    engines (CUDA IPC mapping of the owner's allocation, established on first use of a buffer) and computes each
+    panel of C as it lands -- no SMs are needed for the transfer, so it overlaps the persistent product kernel.
+    The owner must not overwrite B before its next collective call on the same group.
     """
     import torch
     import torch.distributed as dist
@@ -59,6 +65,9 @@ def sharded_gemm(handle: api.handle_t, op_A: int, op_B: int, m_local: int, n: in
         return api.gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
                         compute_mode)
     flat = b.view(-1)
+    if transport == "peer" and int(op_B) == int(api.op_n) and n >= 2 * _MIN_PANEL:
+        return _peer_pull_gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
+                               compute_mode, src, group)
     if not pipeline or int(op_B) != int(api.op_n) or m_local == 0 or n < 2 * _MIN_PANEL:
         dist.broadcast(flat, src=src, group=group)
         if m_local == 0:
@@ -103,3 +112,68 @@ def _keep_alive(events) -> None:
     """the library's streams still wait on these events after this call returns: keep the last two calls' events"""
     _live_events.append(events)
     del _live_events[:-2]
+
+
+_peer_views: dict = {}
+
+
+def _peer_view(b, src: int, group):
+    """the owner's B buffer mapped into this process (CUDA IPC), established once per buffer; collective"""
+    import torch
+    import torch.distributed as dist
+    from torch.multiprocessing.reductions import reduce_tensor
+
+    key = (b.data_ptr(), b.numel(), src, id(group))
+    if key not in _peer_views:
+        rank = dist.get_rank(group)
+        payload = [reduce_tensor(b.view(-1)) if rank == src else None]
+        dist.broadcast_object_list(payload, src=src, group=group)
+        if rank == src:
+            view = b.view(-1)
+        else:
+            rebuild, args = payload[0]
+            view = rebuild(*args)          # a tensor on the owner's device, readable from here over NVLink
+        _peer_views[key] = view
+    return _peer_views[key]
+
+
+def _peer_pull_gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc, compute_mode,
+                    src, group) -> int:
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    flat = b.view(-1)
+    peer = _peer_view(b, src, group)
+    # the owner's B is final once every rank has passed this point in stream order (and the previous call's pulls
+    # have completed: each rank's stream waited for them before it got here)
+    dist.barrier(group=group)
+    panels = column_panels(n, max_panels=8, min_width=_MIN_PANEL)
+    cur = torch.cuda.current_stream()
+    events = []
+    if rank == src:
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        events = [ev] * len(panels)
+    else:
+        side = _side_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for (j0, w) in panels:
+                hi = min(flat.numel(), (j0 + w) * ldb)
+                flat[j0 * ldb:hi].copy_(peer[j0 * ldb:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                events.append(ev)
+    if m_local == 0:
+        rc = 0
+        for ev in events:
+            cur.wait_event(ev)
+    else:
+        edges = [j0 for (j0, _) in panels] + [n]
+        rc = api.gemm_streamed_b(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
+                                 compute_mode, edges, [ev.cuda_event for ev in events])
+        if rank != src:
+            cur.wait_event(events[-1])   # the next call's barrier is ordered after this call's last pull
+    _keep_alive(events)
+    return rc

@@ -33,6 +33,13 @@ if rank != 0:
 assert oz.sharded_gemm(h, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_pipe, rows, oz.fp64_int8(s), src=0, pipeline=True) == 0
 torch.cuda.synchronize()
 assert torch.equal(c_pipe.view(torch.int64), c_blk.view(torch.int64)), "panel-pipelined broadcast differs"
+for rep in range(2):   # second call reuses the cached IPC mapping of B
+    c_peer = torch.zeros_like(c_blk)
+    if rank != 0:
+        b.zero_()
+    assert oz.sharded_gemm(h, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_peer, rows, oz.fp64_int8(s), src=0, transport="peer") == 0
+    torch.cuda.synchronize()
+    assert torch.equal(c_peer.view(torch.int64), c_blk.view(torch.int64)), "peer-pull transport differs"
 torch.save(c_blk.cpu(), os.environ["OZ_OUT"] + f"/c_{rank}.pt")
 dist.barrier(); oz.destroy(h); dist.destroy_process_group()
 """

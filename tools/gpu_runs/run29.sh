@@ -1,8 +1,3 @@
-python -c "import torch; torch.zeros(1).cuda()"
-for rep in 1 2; do
-for cfg in "0 2" "8 2" "16 2" "32 2" "0 1" "0 4" "0 0" "16 4"; do
-  set -- $cfg
-  echo -n "rep$rep PREFETCH=$1 LOCKSTEP=$2: "
-  OZIMMU_B200_PREFETCH=$1 OZIMMU_B200_LOCKSTEP=$2 timeout 200 python tools/perf_probe.py 8192 9 --iters 20 2>&1 | head -1
-done
-done 2>&1 | tee gpurun_out/sweep7.log
+mkdir -p gpurun_out
+(timeout 600 python -m pytest tests/test_gpu_sharded.py -x -q) 2>&1 | tail -12
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29557 tools/ubench/sharded_breakdown.py 2>&1 | grep "^world\|Error\|error" | tee gpurun_out/sharded_breakdown2.log

@@ -22,16 +22,23 @@ def timed(fn, reps=10):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-t_gemm = timed(lambda: oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode))
-t_bc = timed(lambda: dist.broadcast(b, src=0))
-t_step = timed(lambda: oz.sharded_gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0))
-t_pipe = timed(lambda: oz.sharded_gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0, pipeline=True))
-t_gemm2 = timed(lambda: oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode))
+variants = {
+    "product alone": lambda: oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode),
+    "broadcast alone": lambda: dist.broadcast(b, src=0),
+    "broadcast+product": lambda: oz.sharded_gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0),
+    "streamed-B (NCCL panels)": lambda: oz.sharded_gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0, pipeline=True),
+    "peer-pull pipeline": lambda: oz.sharded_gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0, transport="peer"),
+}
+# the GPUs slow down by ~6 % as they heat up over such a run: interleave the variants instead of timing them in turn
+acc = {k: [] for k in variants}
+for cycle in range(4):
+    for name, fn in variants.items():
+        acc[name].append(timed(fn, 5))
+mine = {k: (sum(v[1:]) / len(v[1:])) for k, v in acc.items()}   # first cycle = warm-up
 out = [None] * world
-dist.all_gather_object(out, (rank, t_gemm, t_bc, t_step, t_pipe, t_gemm2))
+dist.all_gather_object(out, (rank, mine))
 if rank == 0:
-    for r, tg, tb, ts, tp, tg2 in out:
-        print(f"world={world} rank {r}: product alone {tg:.3f} ms, broadcast alone {tb:.3f} ms, broadcast+product {ts:.3f} ms, "
-              f"streamed-B pipeline {tp:.3f} ms, product alone again {tg2:.3f} ms", flush=True)
+    for r, d in out:
+        print(f"world={world} rank {r}: " + ", ".join(f"{k} {v:.3f} ms" for k, v in d.items()), flush=True)
 oz.destroy(h)
 dist.destroy_process_group()
