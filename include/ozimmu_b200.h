@@ -93,6 +93,14 @@ int ozk_split_int8_block(int8_t *out, size_t pitch, size_t plane_rows, size_t ro
                          int col_major, unsigned num_split, unsigned bits_per_int8, unsigned elem_stride,
                          void *stream);
 
+/* ozk_split_int8 for `batch` operands of the same shape in ONE launch (strided-batched GEMMs): entry e reads
+ * in + e*in_stride (doubles) and writes its slices at out + e*out_stride (bytes), its row scales at
+ * max_exp + e*max_stride (doubles) and uses scratch + e*scr_stride (uint32).  batch <= 65535. */
+int ozk_split_int8_batched(int8_t *out, size_t out_stride, size_t pitch, double *max_exp, size_t max_stride,
+                           uint32_t *scratch, size_t scr_stride, size_t rows, size_t len, const double *in,
+                           size_t ld, size_t in_stride, int col_major, unsigned num_split,
+                           unsigned bits_per_int8, size_t batch, void *stream);
+
 /* reference src/gemm.cu:266-334 (matmul_core -> cublasGemmEx int8) + :77-102
  * (accumulate_in_f64) + :104-122 (init_accumulator_buffer) + :124-158 (axby), fused:
  * for every (i,j) of the reference pair order (src/config.cu:85-92) an exact

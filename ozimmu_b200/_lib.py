@@ -40,6 +40,9 @@ PROTOTYPES = {
     "ozimmu_gemm_streamed_b": (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t,
                                        c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_size_t, c_void_p,
                                        c_void_p]),
+    "ozk_split_int8_batched": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t,
+                                       c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_uint, c_uint, c_size_t,
+                                       c_void_p]),
     "ozk_mantissa_loss_strided": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int, c_uint,
                                           c_uint, c_void_p]),
     "ozk_gemm_i8_fused_complex": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p,

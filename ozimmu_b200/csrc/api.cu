@@ -145,7 +145,7 @@ void gemm_int8_real_batched(handle_t h, operation_t op_a, operation_t op_b, std:
   const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
   const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split);
   const std::size_t limit = std::stoull(H::env_or("OZIMMU_B200_BATCH_WORKSPACE_MB", "8192")) << 20;
-  const std::size_t chunk = std::max<std::size_t>(1, std::min(batch, limit / w.total));
+  const std::size_t chunk = std::max<std::size_t>(1, std::min<std::size_t>({batch, limit / w.total, 65535}));
   reallocate_working_memory(h, w.total * chunk);
   ensure_streams(h);
   char *ws = static_cast<char *>(h->working_memory_ptr);
@@ -160,23 +160,32 @@ void gemm_int8_real_batched(handle_t h, operation_t op_a, operation_t op_b, std:
       OZ_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));   // also: the previous chunk's products are done with the slices
       OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, h->ev_fork, 0));
     }
+    // one split launch per operand for the whole chunk (entry e's workspace is ws + e * w.total)
+    auto split_chunk = [&](const double *x, long long stride, std::size_t ld, std::size_t rows, int col_major,
+                           std::size_t off_slices, std::size_t off_max, std::size_t off_scr, cudaStream_t st) {
+      if (stride >= 0) {
+        // stride 0: one operand shared by every entry -- split once, the grouped launch reads it with stride 0
+        const std::size_t count = stride == 0 ? 1 : ne;
+        OZ_KERNEL_CHECK(ozk_split_int8_batched(reinterpret_cast<std::int8_t *>(ws + off_slices), w.total, w.pitch,
+                                               reinterpret_cast<double *>(ws + off_max), w.total / sizeof(double),
+                                               reinterpret_cast<std::uint32_t *>(ws + off_scr),
+                                               w.total / sizeof(std::uint32_t), rows, k, x + static_cast<long long>(e0) * stride,
+                                               ld, static_cast<std::size_t>(stride), col_major, num_split, bits, count, st));
+        return;
+      }
+      for (std::size_t e = 0; e < ne; e++) {   // backward-strided input: entry by entry
+        char *we = ws + e * w.total;
+        OZ_KERNEL_CHECK(ozk_split_int8(reinterpret_cast<std::int8_t *>(we + off_slices), w.pitch,
+                                       reinterpret_cast<double *>(we + off_max),
+                                       reinterpret_cast<std::uint32_t *>(we + off_scr), rows, k,
+                                       x + static_cast<long long>(e0 + e) * stride, ld, col_major, num_split, bits, st));
+      }
+    };
     h->profiler.start("split_A", s);
-    for (std::size_t e = 0; e < ne; e++) {
-      char *we = ws + e * w.total;
-      OZ_KERNEL_CHECK(ozk_split_int8(reinterpret_cast<std::int8_t *>(we + w.off_a_slices), w.pitch,
-                                     reinterpret_cast<double *>(we + w.off_amax),
-                                     reinterpret_cast<std::uint32_t *>(we + w.off_scr_a), m, k,
-                                     a + static_cast<long long>(e0 + e) * stride_a, lda, a_col_major, num_split, bits, s));
-    }
+    split_chunk(a, stride_a, lda, m, a_col_major, w.off_a_slices, w.off_amax, w.off_scr_a, s);
     h->profiler.stop("split_A", s);
     h->profiler.start("split_B", sb);
-    for (std::size_t e = 0; e < ne; e++) {
-      char *we = ws + e * w.total;
-      OZ_KERNEL_CHECK(ozk_split_int8(reinterpret_cast<std::int8_t *>(we + w.off_b_slices), w.pitch,
-                                     reinterpret_cast<double *>(we + w.off_bmax),
-                                     reinterpret_cast<std::uint32_t *>(we + w.off_scr_b), n, k,
-                                     b + static_cast<long long>(e0 + e) * stride_b, ldb, b_col_major, num_split, bits, sb));
-    }
+    split_chunk(b, stride_b, ldb, n, b_col_major, w.off_b_slices, w.off_bmax, w.off_scr_b, sb);
     h->profiler.stop("split_B", sb);
     if (overlap) {
       OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, sb));
@@ -184,10 +193,11 @@ void gemm_int8_real_batched(handle_t h, operation_t op_a, operation_t op_b, std:
     }
     h->profiler.start("int8tc_accumulate_fused", s);
     OZ_KERNEL_CHECK(ozk_gemm_i8_fused_batched(
-        m, n, k, ne, reinterpret_cast<const std::int8_t *>(ws + w.off_a_slices), w.total,
-        reinterpret_cast<const std::int8_t *>(ws + w.off_b_slices), w.total, w.pitch,
-        reinterpret_cast<const double *>(ws + w.off_amax), w.total / sizeof(double),
-        reinterpret_cast<const double *>(ws + w.off_bmax), w.total / sizeof(double), num_split, bits, alpha, beta,
+        m, n, k, ne, reinterpret_cast<const std::int8_t *>(ws + w.off_a_slices), stride_a == 0 ? 0 : w.total,
+        reinterpret_cast<const std::int8_t *>(ws + w.off_b_slices), stride_b == 0 ? 0 : w.total, w.pitch,
+        reinterpret_cast<const double *>(ws + w.off_amax), stride_a == 0 ? 0 : w.total / sizeof(double),
+        reinterpret_cast<const double *>(ws + w.off_bmax), stride_b == 0 ? 0 : w.total / sizeof(double), num_split, bits,
+        alpha, beta,
         c + static_cast<long long>(e0) * stride_c, ldc, static_cast<std::size_t>(stride_c), s));
     h->profiler.stop("int8tc_accumulate_fused", s);
   }

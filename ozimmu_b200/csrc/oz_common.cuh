@@ -31,6 +31,14 @@ __host__ __device__ inline size_t slice_chunk_offset(size_t r, size_t g, size_t 
   return ((r >> 7) * k_blocks + (g >> 3)) * kTileBytes + (r & 127) * kTileK + (((g & 7) ^ (r & 7)) << 4);
 }
 
+// Strided batch of operands split by one launch (grid.y for the row kernels, grid.z for the column kernels):
+// entry e reads in + e*in_stride (doubles) and writes out + e*out_stride (bytes), max_exp + e*max_stride,
+// scratch + e*scr_stride.  count = 1 with zero strides for a plain call.
+struct SplitBatch {
+  uint32_t count;
+  size_t in_stride, out_stride, max_stride, scr_stride;
+};
+
 __host__ __device__ inline uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 #define OZ_CUDA_TRY(expr)                                                                    \

@@ -151,9 +151,13 @@ __device__ __forceinline__ uint32_t swz(uint32_t i) { return (i & ~15u) | ((i ^ 
 // ---------------------------------------------------------------------------------------------
 template <int S, bool CACHED>
 __global__ void __launch_bounds__(kSplitThreads)
-split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
-                  const size_t rows, const uint32_t len, const double *__restrict__ in,
-                  const size_t ld, const unsigned L, const uint32_t es, const size_t slice_stride) {
+split_rows_kernel(int8_t *__restrict__ out_, const size_t pitch, double *__restrict__ max_exp_,
+                  const size_t rows, const uint32_t len, const double *__restrict__ in_,
+                  const size_t ld, const unsigned L, const uint32_t es, const size_t slice_stride,
+                  const SplitBatch bt) {
+  int8_t *__restrict__ out = out_ + blockIdx.y * bt.out_stride;
+  double *__restrict__ max_exp = max_exp_ + blockIdx.y * bt.max_stride;
+  const double *__restrict__ in = in_ + blockIdx.y * bt.in_stride;
   // slice_stride: bytes between consecutive slices of the destination plane (the plane may hold more rows than
   // this launch cuts: row-block calls of the host-operand pipeline).
   // es: distance between consecutive elements in doubles (1 = real matrix, 2 = one plane of an
@@ -206,9 +210,12 @@ split_rows_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restri
 // ---------------------------------------------------------------------------------------------
 template <int S, int THREADS, int GROUPS>
 __global__ void __launch_bounds__(THREADS)
-split_rows_reg_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
-                      const size_t rows, const uint32_t len, const double *__restrict__ in,
-                      const size_t ld, const unsigned L, const size_t slice_stride) {
+split_rows_reg_kernel(int8_t *__restrict__ out_, const size_t pitch, double *__restrict__ max_exp_,
+                      const size_t rows, const uint32_t len, const double *__restrict__ in_,
+                      const size_t ld, const unsigned L, const size_t slice_stride, const SplitBatch bt) {
+  int8_t *__restrict__ out = out_ + blockIdx.y * bt.out_stride;
+  double *__restrict__ max_exp = max_exp_ + blockIdx.y * bt.max_stride;
+  const double *__restrict__ in = in_ + blockIdx.y * bt.in_stride;
   __shared__ uint32_t s_red[THREADS / 32];
   __shared__ uint32_t s_max;
   const size_t row = blockIdx.x;
@@ -271,8 +278,10 @@ split_rows_reg_kernel(int8_t *__restrict__ out, const size_t pitch, double *__re
 constexpr int kColChunk = 64;  // columns per CTA in the row-max pass
 
 __global__ void __launch_bounds__(256)
-rowmax_cols_kernel(uint32_t *__restrict__ emax, const size_t rows, const uint32_t len,
-                   const double *__restrict__ in, const size_t ld, const uint32_t es) {
+rowmax_cols_kernel(uint32_t *__restrict__ emax_, const size_t rows, const uint32_t len,
+                   const double *__restrict__ in_, const size_t ld, const uint32_t es, const SplitBatch bt) {
+  uint32_t *__restrict__ emax = emax_ + blockIdx.z * bt.scr_stride;
+  const double *__restrict__ in = in_ + blockIdx.z * bt.in_stride;
   const size_t r = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
   if (r >= rows) return;
   const uint32_t c0 = blockIdx.y * kColChunk;
@@ -292,10 +301,14 @@ constexpr int kColsRows = 32, kColsK = 128;
 
 template <int S>
 __global__ void __launch_bounds__(256)
-split_cols_kernel(int8_t *__restrict__ out, const size_t pitch, double *__restrict__ max_exp,
-                  const uint32_t *__restrict__ emax, const size_t rows, const uint32_t len,
-                  const double *__restrict__ in, const size_t ld, const unsigned L, const uint32_t es,
-                  const size_t slice_stride) {
+split_cols_kernel(int8_t *__restrict__ out_, const size_t pitch, double *__restrict__ max_exp_,
+                  const uint32_t *__restrict__ emax_, const size_t rows, const uint32_t len,
+                  const double *__restrict__ in_, const size_t ld, const unsigned L, const uint32_t es,
+                  const size_t slice_stride, const SplitBatch bt) {
+  int8_t *__restrict__ out = out_ + blockIdx.z * bt.out_stride;
+  double *__restrict__ max_exp = max_exp_ + blockIdx.z * bt.max_stride;
+  const uint32_t *__restrict__ emax = emax_ + blockIdx.z * bt.scr_stride;
+  const double *__restrict__ in = in_ + blockIdx.z * bt.in_stride;
   extern __shared__ uint4 s_out[];  // [S][32 rows][8 chunks of 16 B], chunk index ^ (row & 7)
   const uint32_t rl = threadIdx.x & 31, cg = threadIdx.x >> 5;
   const size_t r = static_cast<size_t>(blockIdx.x) * kColsRows + rl;
@@ -404,34 +417,39 @@ loss_cols_kernel(unsigned long long *__restrict__ counters, const uint32_t *__re
 template <int S>
 int launch_split(int8_t *out, size_t pitch, size_t plane_rows, double *max_exp, uint32_t *scratch, size_t rows,
                  size_t len, const double *in, size_t ld, int col_major, unsigned L, uint32_t es,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const SplitBatch bt = SplitBatch{1, 0, 0, 0, 0}) {
+  if (bt.count == 0 || bt.count > 65535) return static_cast<int>(cudaErrorInvalidValue);
   // `out` points at this call's first row tile inside a plane of plane_rows rows (plane_rows == rows for a
   // whole-matrix call)
   const size_t slice_stride = slice_row_tiles(plane_rows) * kTileRows * pitch;
   if (col_major) {
-    OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), stream));
-    dim3 g1(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk));
-    rowmax_cols_kernel<<<g1, 256, 0, stream>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es);
-    dim3 g2(static_cast<unsigned>((rows + kColsRows - 1) / kColsRows), static_cast<unsigned>((pitch + kColsK - 1) / kColsK));
+    if (bt.count == 1)
+      OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), stream));
+    else
+      OZ_CUDA_TRY(cudaMemset2DAsync(scratch, bt.scr_stride * sizeof(uint32_t), 0, rows * sizeof(uint32_t), bt.count, stream));
+    dim3 g1(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk), bt.count);
+    rowmax_cols_kernel<<<g1, 256, 0, stream>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es, bt);
+    dim3 g2(static_cast<unsigned>((rows + kColsRows - 1) / kColsRows), static_cast<unsigned>((pitch + kColsK - 1) / kColsK),
+            bt.count);
     const size_t smem_cols = static_cast<size_t>(S) * kColsRows * kColsK;
     if (smem_cols > 48 * 1024)  // per device and cheap: no caching
       OZ_CUDA_TRY(cudaFuncSetAttribute(split_cols_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_cols)));
     split_cols_kernel<S><<<g2, 256, smem_cols, stream>>>(out, pitch, max_exp, scratch, rows,
-                                                         static_cast<uint32_t>(len), in, ld, L, es, slice_stride);
+                                                         static_cast<uint32_t>(len), in, ld, L, es, slice_stride, bt);
     count_launch(2);
   } else if (es == 1 && len <= 16384) {
     // register-resident rows: (threads, 16-element groups per thread) sized to the row
-    const unsigned nrows = static_cast<unsigned>(rows);
+    const dim3 nrows(static_cast<unsigned>(rows), bt.count);
     const uint32_t len32 = static_cast<uint32_t>(len);
     if (len <= 2048)
-      split_rows_reg_kernel<S, 128, 1><<<nrows, 128, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride);
+      split_rows_reg_kernel<S, 128, 1><<<nrows, 128, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride, bt);
     else if (len <= 4096)
-      split_rows_reg_kernel<S, 256, 1><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride);
+      split_rows_reg_kernel<S, 256, 1><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride, bt);
     else if (len <= 8192)
-      split_rows_reg_kernel<S, 256, 2><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride);
+      split_rows_reg_kernel<S, 256, 2><<<nrows, 256, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride, bt);
     else
-      split_rows_reg_kernel<S, 512, 2><<<nrows, 512, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride);
+      split_rows_reg_kernel<S, 512, 2><<<nrows, 512, 0, stream>>>(out, pitch, max_exp, rows, len32, in, ld, L, slice_stride, bt);
     count_launch(1);
   } else {
     if (len <= static_cast<size_t>(kMaxCachedLen)) {
@@ -441,11 +459,11 @@ int launch_split(int8_t *out, size_t pitch, size_t plane_rows, double *max_exp, 
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
       }
-      split_rows_kernel<S, true><<<static_cast<unsigned>(rows), kSplitThreads, smem, stream>>>(
-          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es, slice_stride);
+      split_rows_kernel<S, true><<<dim3(static_cast<unsigned>(rows), bt.count), kSplitThreads, smem, stream>>>(
+          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es, slice_stride, bt);
     } else {
-      split_rows_kernel<S, false><<<static_cast<unsigned>(rows), kSplitThreads, 0, stream>>>(
-          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es, slice_stride);
+      split_rows_kernel<S, false><<<dim3(static_cast<unsigned>(rows), bt.count), kSplitThreads, 0, stream>>>(
+          out, pitch, max_exp, rows, static_cast<uint32_t>(len), in, ld, L, es, slice_stride, bt);
     }
     count_launch(1);
   }
