@@ -68,12 +68,30 @@ void oz::host::ensure_pipeline_streams(mtk::ozimmu::handle *h) {
 
 namespace {
 
-// block edge: `want` rounded up to the kernel's 256-row tile, grown until `extent` needs at most kMaxBlocks
-std::size_t block_edge(std::size_t extent, std::size_t want) {
+// Block boundaries of one operand: blocks of `want` rows (rounded up to the kernel's 256-row tile, grown until at
+// most kMaxBlocks are needed); with `taper` the last ~1.5 blocks are cut into halves, quarters, ... so that the
+// blocks that arrive LAST -- nothing overlaps the products they enable -- carry little work.
+std::vector<std::size_t> block_edges(std::size_t extent, std::size_t want, bool taper) {
   const std::size_t kmax = handle::kMaxBlocks;
   std::size_t e = (std::max<std::size_t>(want, 256) + 255) / 256 * 256;
-  if ((extent + e - 1) / e > kmax) e = ((extent + kmax - 1) / kmax + 255) / 256 * 256;
-  return e;
+  const std::size_t room = taper ? kmax - 2 : kmax;
+  if ((extent + e - 1) / e > room) e = ((extent + room - 1) / room + 255) / 256 * 256;
+  std::vector<std::size_t> edges{0};
+  std::size_t at = 0;
+  if (taper && e >= 512) {
+    while (extent - at > e + e / 2) edges.push_back(at += e);
+    // the rest (between e/2 and 1.5 e): halve until 256
+    while (extent - at > 256 && edges.size() < kmax) {
+      const std::size_t rest = extent - at;
+      const std::size_t piece = std::max<std::size_t>(256, (rest / 2 + 255) / 256 * 256);
+      if (piece >= rest) break;
+      edges.push_back(at += piece);
+    }
+  } else {
+    while (extent - at > e) edges.push_back(at += e);
+  }
+  edges.push_back(extent);
+  return edges;
 }
 
 std::size_t env_size(const char *name, std::size_t fallback) {
@@ -146,8 +164,12 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   // (profiles/r1_e2e_block_sweep.txt).
   const std::size_t want_cols = env_size("OZIMMU_B200_E2E_PANEL", 768);
   const std::size_t want_rows = env_size("OZIMMU_B200_E2E_ROWBLOCK", 768);
-  const std::size_t cb = block_edge(n, want_cols == 0 ? n : want_cols), rb = block_edge(m, want_rows == 0 ? m : want_rows);
-  const std::size_t nbb = (n + cb - 1) / cb, nab = (m + rb - 1) / rb;
+  // OZIMMU_B200_E2E_TAPER=1 halves the last blocks (less work behind the last byte); measured +-0 at the default
+  // edge of 768, +0.5 ms better at 1024 (profiles/r1_e2e_block_sweep.txt): off by default.
+  const bool taper = env_size("OZIMMU_B200_E2E_TAPER", 0) != 0;
+  const std::vector<std::size_t> be = block_edges(n, want_cols == 0 ? n : want_cols, taper && want_cols != 0);
+  const std::vector<std::size_t> ae = block_edges(m, want_rows == 0 ? m : want_rows, taper && want_rows != 0);
+  const std::size_t nbb = be.size() - 1, nab = ae.size() - 1;
 
   const H::WorkspaceLayout w = H::workspace_layout(m, n, k, s);
   reallocate_working_memory(h, w.total);
@@ -161,7 +183,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
 
   auto copy_a_block = [&](std::size_t i) {
-    const std::size_t i0 = i * rb, mi = std::min(rb, m - i0);
+    const std::size_t i0 = ae[i], mi = ae[i + 1] - i0;
     if (op_a == op_n) {  // m x k column-major: rows i0..i0+mi of every column
       copy_matrix(da + i0, a + i0, lda, mi, k, cudaMemcpyHostToDevice, sin);
     } else {             // k x m column-major: a row block of op(A) is a contiguous column panel
@@ -170,7 +192,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[0][i], sin));
   };
   auto copy_b_block = [&](std::size_t j) {
-    const std::size_t j0 = j * cb, nj = std::min(cb, n - j0);
+    const std::size_t j0 = be[j], nj = be[j + 1] - j0;
     if (op_b == op_n) {  // k x n column-major: a column panel is contiguous
       copy_matrix(db + j0 * ldb, b + j0 * ldb, ldb, k, nj, cudaMemcpyHostToDevice, sin);
     } else {             // n x k column-major: rows j0..j0+nj of every column
@@ -180,7 +202,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[1][j], sin));
   };
   auto split_a_block = [&](std::size_t i) {
-    const std::size_t i0 = i * rb, mi = std::min(rb, m - i0);
+    const std::size_t i0 = ae[i], mi = ae[i + 1] - i0;
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_block_in[0][i], 0));
     const double *src = (op_a == op_n) ? da + i0 : da + i0 * lda;
     OZ_KERNEL_CHECK(ozk_split_int8_block(a_sl, w.pitch, m, i0, amax + i0, scr_a + i0, mi, k, src, lda, op_a == op_n, s,
@@ -188,7 +210,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[0][i], sc));
   };
   auto split_b_block = [&](std::size_t j) {
-    const std::size_t j0 = j * cb, nj = std::min(cb, n - j0);
+    const std::size_t j0 = be[j], nj = be[j + 1] - j0;
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_block_in[1][j], 0));
     const double *src = (op_b == op_n) ? db + j0 * ldb : db + j0;
     OZ_KERNEL_CHECK(ozk_split_int8_block(b_sl, w.pitch, n, j0, bmax + j0, scr_b + j0, nj, k, src, ldb, op_b != op_n, s,
@@ -228,13 +250,11 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   for (const Arrival &x : order) {
     if (x.which) {
       split_b_block(x.idx);
-      const std::size_t j0 = x.idx * cb;
-      product_rect(0, std::min(m, have_a * rb), j0, std::min(cb, n - j0), h->ev_block_split[1][x.idx]);
+      product_rect(0, ae[have_a], be[x.idx], be[x.idx + 1] - be[x.idx], h->ev_block_split[1][x.idx]);
       have_b++;
     } else {
       split_a_block(x.idx);
-      const std::size_t i0 = x.idx * rb;
-      product_rect(i0, std::min(rb, m - i0), 0, std::min(n, have_b * cb), h->ev_block_split[0][x.idx]);
+      product_rect(ae[x.idx], ae[x.idx + 1] - ae[x.idx], 0, be[have_b], h->ev_block_split[0][x.idx]);
       have_a++;
     }
   }

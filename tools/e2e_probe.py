@@ -1,5 +1,5 @@
 """Times ozimmu_gemm_host (host operands, pinned) at n^3 for a list of block schedules:
-python tools/e2e_probe.py [n] [panel:rowblock ...]   (0 = whole operand in one piece; default sweep below)"""
+python tools/e2e_probe.py [n] [panel:rowblock[:taper] ...]   (0 = whole operand in one piece; default sweep below)"""
 import os, sys, time
 from pathlib import Path
 import torch
@@ -13,8 +13,9 @@ b = torch.rand(n * n, dtype=torch.float64).pin_memory()
 c = torch.zeros(n * n, dtype=torch.float64).pin_memory()
 h = oz.create()
 for combo in combos:
-    panel, rowblock = combo.split(":")
+    panel, rowblock, taper = (combo.split(":") + ["1"])[:3]
     os.environ["OZIMMU_B200_E2E_PANEL"], os.environ["OZIMMU_B200_E2E_ROWBLOCK"] = panel, rowblock
+    os.environ["OZIMMU_B200_E2E_TAPER"] = taper
     for _ in range(2):
         oz.gemm_host(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(9))
     it = 5
@@ -24,7 +25,7 @@ for combo in combos:
         oz.gemm_host(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(9))
         best = min(best, time.perf_counter() - t0)
     dt = (time.perf_counter() - t_all) / it
-    print(f"gemm_host n={n} panel={panel} rowblock={rowblock}: mean {dt*1e3:.2f} ms best {best*1e3:.2f} ms  "
+    print(f"gemm_host n={n} panel={panel} rowblock={rowblock} taper={taper}: mean {dt*1e3:.2f} ms best {best*1e3:.2f} ms  "
           f"{2*n**3/dt/1e12:.2f} TFLOP/s-equiv", flush=True)
 # raw PCIe numbers for context
 d = torch.empty(n * n, dtype=torch.float64, device="cuda")
