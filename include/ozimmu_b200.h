@@ -232,6 +232,11 @@ int ozimmu_gemm_host(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_
                      const double *alpha, const double *a, size_t lda, const double *b, size_t ldb,
                      const double *beta, double *c, size_t ldc, int compute_mode);
 
+/* Diagnostic: the block boundaries ozimmu_gemm_host cuts an operand of `extent` rows into for a requested block
+ * edge `want` (0 = one block) -- ascending, edges[0] = 0, last = extent, inner edges multiples of 256, at most 17
+ * entries.  Writes min(count, capacity) entries, returns count. */
+size_t ozimmu_host_block_edges(size_t extent, size_t want, int taper, size_t *edges, size_t capacity);
+
 /* Number of kernels this library launched since load (bench.py's gpu_launches). */
 unsigned long long ozimmu_launch_count(void);
 

@@ -76,6 +76,7 @@ PROTOTYPES = {
     "ozimmu_get_bits_per_int8": (C.c_uint32, [C.c_uint32]),
     "ozimmu_gemm_host": (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t,
                                  c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int]),
+    "ozimmu_host_block_edges": (c_size_t, [c_size_t, c_size_t, c_int, c_void_p, c_size_t]),
     "ozimmu_launch_count": (C.c_ulonglong, []),
 }
 

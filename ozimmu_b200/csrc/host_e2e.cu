@@ -274,6 +274,14 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
 
 }  // namespace
 
+// Diagnostic: the block boundaries ozimmu_gemm_host uses for one operand (CPU-testable host logic).
+extern "C" size_t ozimmu_host_block_edges(size_t extent, size_t want, int taper, size_t *edges, size_t capacity) {
+  if (extent == 0) return 0;
+  const std::vector<std::size_t> e = block_edges(extent, want == 0 ? extent : want, taper != 0 && want != 0);
+  for (std::size_t i = 0; i < e.size() && i < capacity; i++) edges[i] = e[i];
+  return e.size();
+}
+
 extern "C" int ozimmu_gemm_host(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
                                 const double *alpha, const double *a, size_t lda, const double *b, size_t ldb,
                                 const double *beta, double *c, size_t ldc, int compute_mode) {

@@ -313,6 +313,12 @@ cublasStatus_t cublasGemmStridedBatchedEx(cublasHandle_t handle, cublasOperation
                                  strideA, b, ldb, strideB, static_cast<const double *>(beta), c, ldc, strideC, batchCount);
     }
   }
+  if (mode != dgemm && Atype == CUDA_C_64F && Btype == CUDA_C_64F && Ctype == CUDA_C_64F)
+    return cublasZgemmStridedBatched(handle, transa, transb, m, n, k, static_cast<const cuDoubleComplex *>(alpha),
+                                     static_cast<const cuDoubleComplex *>(A), lda, strideA,
+                                     static_cast<const cuDoubleComplex *>(B), ldb, strideB,
+                                     static_cast<const cuDoubleComplex *>(beta), static_cast<cuDoubleComplex *>(C), ldc,
+                                     strideC, batchCount);
   auto fn = real_fn<GemmStridedBatchedExFn>("cublasGemmStridedBatchedEx");
   if (fn == nullptr) return CUBLAS_STATUS_NOT_INITIALIZED;
   return fn(handle, transa, transb, m, n, k, alpha, A, Atype, lda, strideA, B, Btype, ldb, strideB, beta, C, Ctype, ldc,
@@ -336,12 +342,33 @@ cublasStatus_t cublasDgemmStridedBatched(cublasHandle_t handle, cublasOperation_
   return fn(handle, transa, transb, m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC, batchCount);
 }
 
-// reference src/cublas.cu:494-512 -- complex path: passthrough
+// reference src/cublas.cu:494-512 (-> :315-472 with C_64F: one complex Ozaki GEMM per batch entry, :380-406)
 cublasStatus_t cublasZgemmStridedBatched(cublasHandle_t handle, cublasOperation_t transa, cublasOperation_t transb, int m,
                                          int n, int k, const cuDoubleComplex *alpha, const cuDoubleComplex *A, int lda,
                                          long long strideA, const cuDoubleComplex *B, int ldb, long long strideB,
                                          const cuDoubleComplex *beta, cuDoubleComplex *C, int ldc, long long strideC,
                                          int batchCount) {
+  const compute_mode_t mode = env_compute_mode();
+  if (mode != dgemm && no_conj(transa, transb)) {
+    bool take = false;
+    {
+      std::lock_guard<std::mutex> lock(g_mu);
+      try {
+        take = should_intercept(global_handle(), mode, m, n, k, CUDA_C_64F, CUDA_C_64F, CUDA_C_64F) &&
+               host_pointer_mode(handle);
+      } catch (const std::exception &e) {
+        H::log_error(e.what());
+      }
+    }
+    if (take) {
+      for (int i = 0; i < batchCount; i++) {
+        const cublasStatus_t st = ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A + strideA * i, lda,
+                                             B + strideB * i, ldb, beta, C + strideC * i, ldc, complx);
+        if (st != CUBLAS_STATUS_SUCCESS) return st;
+      }
+      return CUBLAS_STATUS_SUCCESS;
+    }
+  }
   auto fn = real_fn<cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int,
                                     const cuDoubleComplex *, const cuDoubleComplex *, int, long long,
                                     const cuDoubleComplex *, int, long long, const cuDoubleComplex *, cuDoubleComplex *,

@@ -84,3 +84,24 @@ def test_invalid_arguments_rejected_without_gpu():
     assert lib.ozk_gemm_i8_fused(8, 8, 8, None, None, 16, None, None, 9, 7, 1.0, 0.0, None, 8, None) != 0   # pitch % 128
     assert lib.ozk_gemm_i8_fused(0, 8, 8, None, None, 128, None, None, 9, 7, 1.0, 0.0, None, 1, None) == 0  # empty
     assert lib.ozimmu_launch_count() == 0
+
+
+@pytest.mark.parametrize("taper", [0, 1])
+@pytest.mark.parametrize("want", [0, 1, 256, 300, 512, 768, 1024, 4096, 100000])
+@pytest.mark.parametrize("extent", [1, 100, 256, 257, 700, 1300, 4362, 8192, 16384, 40000, 131072])
+def test_host_block_edges(extent, want, taper):
+    """Block schedule of the host-operand pipeline (csrc/host_e2e.cu): a partition of [0, extent) into at most 16
+    blocks whose inner boundaries sit on the kernel's 256-row tiles (the block-wise split requires it)."""
+    lib = oz.lib()
+    buf = (C.c_size_t * 32)()
+    cnt = lib.ozimmu_host_block_edges(extent, want, taper, C.addressof(buf), 32)
+    e = list(buf[:cnt])
+    assert 2 <= cnt <= 17
+    assert e[0] == 0 and e[-1] == extent
+    assert all(a < b for a, b in zip(e, e[1:]))
+    assert all(x % 256 == 0 for x in e[1:-1])
+    if want == 0:
+        assert e == [0, extent]
+    if taper and want and cnt > 3:
+        sizes = [b - a for a, b in zip(e, e[1:])]
+        assert sizes[-1] <= sizes[0] and sizes[-2] <= sizes[0]     # the blocks that arrive last are not the big ones

@@ -127,7 +127,12 @@ a = torch.rand(6, 1024, 1152, dtype=torch.float64, device="cuda")
 b = torch.rand(6, 1152, 1280, dtype=torch.float64, device="cuda")
 c = torch.bmm(a, b)
 torch.cuda.synchronize()
-torch.save({"a": a.cpu(), "b": b.cpu(), "c": c.cpu()}, os.environ["OZ_DROPIN_OUT"])
+za = torch.randn(3, 1024, 1024, dtype=torch.complex128, device="cuda")
+zb = torch.randn(3, 1024, 1024, dtype=torch.complex128, device="cuda")
+zc = torch.bmm(za, zb)
+torch.cuda.synchronize()
+torch.save({"a": a.cpu(), "b": b.cpu(), "c": c.cpu(), "za": za.cpu(), "zb": zb.cpu(), "zc": zc.cpu()},
+           os.environ["OZ_DROPIN_OUT"])
 """
 
 
@@ -152,3 +157,14 @@ def test_ld_preload_bmm(tmp_path, handle):
     assert np.array_equal(bits(c), bits(d["c"]))
     ref = d["a"] @ d["b"]
     assert (torch.linalg.norm(d["c"] - ref) / torch.linalg.norm(ref)).item() < 1e-15
+    # complex128 bmm -> cublasZgemmStridedBatched / GemmStridedBatchedEx(C_64F): one complex Ozaki GEMM per entry
+    # (reference src/cublas.cu:380-406,494-512)
+    assert "[CULiP Result][Zfp64_int8_9-" in p.stdout, p.stdout[-2000:]
+    za, zb = d["za"].cuda(), d["zb"].cuda()
+    zc = torch.zeros_like(za)
+    nz = za.shape[1]
+    for e in range(za.shape[0]):
+        assert oz.gemm(handle, 0, 0, nz, nz, nz, 1.0 + 0j, zb[e], nz, za[e], nz, 0j, zc[e], nz, oz.fp64_int8(9),
+                       oz.complx) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(torch.view_as_real(zc).cpu().view(torch.int64), torch.view_as_real(d["zc"]).view(torch.int64))
