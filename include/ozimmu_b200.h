@@ -134,6 +134,23 @@ int ozk_gemm_i8_fused_batched(size_t m, size_t n, size_t k, size_t batch, const 
                               unsigned num_split, unsigned bits_per_int8, double alpha, double beta, double *c,
                               size_t ldc, size_t c_batch, void *stream);
 
+/* EXPERIMENTAL (not used by any default path; untested on hardware at the end of round 1 -- see DESIGN.md 10):
+ * ozk_gemm_i8_fused as ONE persistent launch that pops tiles from a device-side queue.  items[i] names a 256 x 256
+ * tile of C (tile = tile_row | tile_col << 16) in the order the host wants them started; a tile starts only when
+ * flags[a_flag] == epoch and flags[b_flag] == epoch (the host makes a block of A / B "ready" by writing epoch there
+ * after its split has finished, e.g. with cuStreamWriteValue32), and every finished tile adds 16 to done[items[i].done]
+ * (the host's copy-out stream waits for 16 x tiles of a block of C).  reserve_sms SMs are left free for the kernels
+ * that produce the operands while this launch waits.  scratch: ozk_queue_scratch_words(num_items, reserve_sms)
+ * uint32 of device memory, cleared by the launch; after completion scratch[1] != 0 means a readiness wait timed out. */
+typedef struct { uint32_t tile, a_flag, b_flag, done; } ozk_queue_item_t;
+size_t ozk_queue_scratch_words(size_t num_items, unsigned reserve_sms);
+int ozk_gemm_i8_fused_queue(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
+                            size_t pitch, const double *amax, const double *bmax, unsigned num_split,
+                            unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
+                            const ozk_queue_item_t *items, size_t num_items, const uint32_t *flags, uint32_t epoch,
+                            uint32_t *done, uint32_t *scratch, size_t scratch_words, unsigned reserve_sms,
+                            void *stream);
+
 /* One of the four real products of a complex GEMM (reference src/gemm.cu:479-518 loop body +
  * :160-186 axy_complex + :188-239 init_c_complex): x = the fp64_int8 product of the given planes,
  * C[i,j] = fma(x, (coef_re, coef_im), C'[i,j]) with C' = beta*C if apply_beta (first launch of the

@@ -303,6 +303,8 @@ int mtk::ozimmu::destroy(handle_t h) {
   cudaFree(h->stage_a);
   cudaFree(h->stage_b);
   cudaFree(h->stage_c);
+  cudaFree(h->queue_dev);
+  cudaFreeHost(h->queue_host);
   for (cudaStream_t s : {h->aux_stream, h->h2d_stream, h->d2h_stream, h->compute_stream})
     if (s) cudaStreamDestroy(s);
   for (cudaStream_t s : h->product_stream)

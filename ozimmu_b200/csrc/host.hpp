@@ -131,5 +131,13 @@ struct mtk::ozimmu::handle {
   cudaEvent_t ev_block_in[2][kMaxBlocks] = {}, ev_block_split[2][kMaxBlocks] = {};  // [0] = A, [1] = B
   cudaEvent_t ev_rect_out[2 * kMaxBlocks] = {};                                     // one per fused launch
   cudaEvent_t ev_product_tail[kProductStreams] = {};
+  // experimental queue mode of ozimmu_gemm_host (OZIMMU_B200_E2E_QUEUE=1): device block [flags | done | items |
+  // kernel scratch], pinned staging for the items, the epoch that marks a flag as "ready in this call"
+  void *queue_dev = nullptr, *queue_host = nullptr;
+  std::size_t queue_dev_bytes = 0, queue_host_bytes = 0;
+  std::uint32_t queue_epoch = 0;
+  std::uint64_t queue_warm_key = 0;
+  bool queue_warm = false;  // every kernel of the path has been launched once (lazy module loading must not happen
+                            // while the persistent kernel spins)
   int device = 0;
 };

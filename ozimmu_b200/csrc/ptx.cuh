@@ -107,6 +107,20 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders this thread's earlier generic-proxy observations (an acquire load of a "data is ready" flag) before its later
+// async-proxy operations (bulk copies of that data)
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 // same without the release fence (the ERRBAR/MEMBAR of a .release arrive costs ~1 us): for hand-offs whose
 // payload was written by the async proxy and already observed complete through an mbarrier (the relay of the
 // pair kernel), so there is no generic-proxy write of this thread to publish
