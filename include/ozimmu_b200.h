@@ -255,6 +255,13 @@ int ozimmu_gemm_host(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_
  * entries.  Writes min(count, capacity) entries, returns count. */
 size_t ozimmu_host_block_edges(size_t extent, size_t want, int taper, size_t *edges, size_t capacity);
 
+/* Diagnostic: the work-item list of the experimental queue mode (ozk_gemm_i8_fused_queue) for an m x n product whose
+ * operands are cut into blocks of want_rows / want_cols: items in start order, expected[a] = the done count arrival a's
+ * part of C must reach (32 entries), *num_arrivals = blocks of A + blocks of B.  Flag indices: blocks of A first, then
+ * blocks of B.  Writes min(count, capacity) items, returns count. */
+size_t ozimmu_host_queue_plan(size_t m, size_t n, size_t want_rows, size_t want_cols, int taper,
+                              ozk_queue_item_t *items, size_t capacity, uint32_t *expected, size_t *num_arrivals);
+
 /* Number of kernels this library launched since load (bench.py's gpu_launches). */
 unsigned long long ozimmu_launch_count(void);
 

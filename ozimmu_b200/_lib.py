@@ -81,6 +81,8 @@ PROTOTYPES = {
     "ozimmu_gemm_host": (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t,
                                  c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int]),
     "ozimmu_host_block_edges": (c_size_t, [c_size_t, c_size_t, c_int, c_void_p, c_size_t]),
+    "ozimmu_host_queue_plan": (c_size_t, [c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_void_p, c_size_t, c_void_p,
+                                          c_void_p]),
     "ozimmu_launch_count": (C.c_ulonglong, []),
 }
 

@@ -443,6 +443,29 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
 
 }  // namespace
 
+// Diagnostic: the work-item list of the experimental queue mode for an m x n product cut at the given block edges
+// (CPU-testable host logic).  Writes min(count, capacity) items and, per arrival, the done count its rectangle must
+// reach (expected[], capacity 2 * 16); returns the item count.
+extern "C" size_t ozimmu_host_queue_plan(size_t m, size_t n, size_t want_rows, size_t want_cols, int taper,
+                                         ozk_queue_item_t *items, size_t capacity, uint32_t *expected,
+                                         size_t *num_arrivals) {
+  if (m == 0 || n == 0) return 0;
+  const std::vector<std::size_t> ae = block_edges(m, want_rows == 0 ? m : want_rows, taper != 0 && want_rows != 0);
+  const std::vector<std::size_t> be = block_edges(n, want_cols == 0 ? n : want_cols, taper != 0 && want_cols != 0);
+  const std::size_t nab = ae.size() - 1, nbb = be.size() - 1;
+  std::vector<std::pair<int, std::size_t>> order;
+  for (std::size_t ia = 0, ib = 0; ia < nab || ib < nbb;) {
+    if (ib < nbb && (ib <= ia || ia >= nab)) order.emplace_back(1, ib++);
+    else order.emplace_back(0, ia++);
+  }
+  const QueuePlan plan = plan_queue(ae, be, order);
+  for (std::size_t i = 0; i < plan.items.size() && i < capacity; i++) items[i] = plan.items[i];
+  if (expected)
+    for (std::size_t i = 0; i < plan.expected.size(); i++) expected[i] = plan.expected[i];
+  if (num_arrivals) *num_arrivals = plan.expected.size();
+  return plan.items.size();
+}
+
 // Diagnostic: the block boundaries ozimmu_gemm_host uses for one operand (CPU-testable host logic).
 extern "C" size_t ozimmu_host_block_edges(size_t extent, size_t want, int taper, size_t *edges, size_t capacity) {
   if (extent == 0) return 0;
