@@ -485,6 +485,9 @@ extern "C" int ozimmu_gemm_host(ozimmu_handle_t handle, int op_a, int op_b, size
                           static_cast<operation_t>(op_b != 0), m, n, k, *alpha, a, lda, b, ldb, *beta, c, ldc,
                           static_cast<compute_mode_t>(compute_mode));
   } catch (const std::exception &e) {
+    // copies that reference the caller's host buffers may still be queued on the internal streams: drain them before
+    // the caller gets its buffers back
+    cudaDeviceSynchronize();
     H::log_error(e.what());
     return -1;
   }
