@@ -134,8 +134,8 @@ int ozk_gemm_i8_fused_batched(size_t m, size_t n, size_t k, size_t batch, const 
                               unsigned num_split, unsigned bits_per_int8, double alpha, double beta, double *c,
                               size_t ldc, size_t c_batch, void *stream);
 
-/* EXPERIMENTAL (not used by any default path; one hardware run at the end of round 1 -- DESIGN.md 10,
- * profiles/r1_queue_experiment.txt: bit-identical to ozk_gemm_i8_fused with the flags preset, late flags not yet verified):
+/* EXPERIMENTAL (not used by any default path; parity verified on hardware at the end of round 1 --
+ * tests/test_gpu_queue.py, opt-in; performance work open -- DESIGN.md 10, profiles/r1_queue_experiment.txt):
  * ozk_gemm_i8_fused as ONE persistent launch that pops tiles from a device-side queue.  items[i] names a 256 x 256
  * tile of C (tile = tile_row | tile_col << 16) in the order the host wants them started; a tile starts only when
  * flags[a_flag] == epoch and flags[b_flag] == epoch (the host makes a block of A / B "ready" by writing epoch there

@@ -117,7 +117,7 @@ void copy_matrix(double *dst, const double *src, std::size_t ld, std::size_t row
 }
 
 // ---- experimental: one persistent product launch fed by a device-side tile queue ---------------------------------
-// (OZIMMU_B200_E2E_QUEUE=1; one hardware run at the end of round 1 -- it completes, but slower than the multi-launch
+// (OZIMMU_B200_E2E_QUEUE=1; parity verified on hardware at the end of round 1, but slower than the multi-launch
 // pipeline: the block splits crawl on the few reserved SMs; DESIGN.md 10, profiles/r1_queue_experiment.txt.)  The schedule is the same
 // as below -- blocks of A and B travel alternately, each is split as it lands -- but instead of one product launch
 // per arrival there is ONE launch (ozk_gemm_i8_fused_queue) whose CTA pairs pop 256 x 256 tiles from a queue in

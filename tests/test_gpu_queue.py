@@ -1,9 +1,10 @@
 """-m gpu, OPT-IN (OZIMMU_B200_TEST_QUEUE=1): the experimental device-side tile queue (ozk_gemm_i8_fused_queue and
-OZIMMU_B200_E2E_QUEUE=1 for ozimmu_gemm_host).  The path was written at the end of round 1 with GPU time left for ONE
-run (profiles/r1_queue_experiment.txt): the queue launch is bit-identical to the static launch when the flags are set
-beforehand (3 shapes); the late-flags case failed on a harness bug (fixed below, not re-run); the e2e queue mode
-completes but is slower than the multi-launch pipeline because the split kernels crawl on the 4 reserved SMs.  It is
-off by default everywhere and these tests are skipped unless asked for; run them under a short `timeout`."""
+OZIMMU_B200_E2E_QUEUE=1 for ozimmu_gemm_host).  Written at the end of round 1; its two hardware runs
+(profiles/r1_queue_experiment.txt): all 7 tests below pass -- the queue launch is bit-identical to the static launch
+with the flags preset and with flags that arrive while the launch is already spinning, and the host entry's queue mode
+is bit-identical to the device entry.  Performance is not there yet (the block splits crawl on the few SMs the
+persistent launch leaves free), so the mode stays off by default and these tests stay opt-in; run them under a short
+`timeout`."""
 import os
 
 import numpy as np
