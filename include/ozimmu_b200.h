@@ -152,6 +152,16 @@ int ozk_gemm_i8_fused_queue(size_t m, size_t n, size_t k, const int8_t *a_slices
                             uint32_t *done, uint32_t *scratch, size_t scratch_words, unsigned reserve_sms,
                             void *stream);
 
+/* EXPERIMENTAL, not yet run on hardware: a second launch that JOINS the queue of a running ozk_gemm_i8_fused_queue
+ * launch (same arguments, same scratch -- not cleared), with num_pairs CTA pairs that record their items in the slot
+ * rows first_pair ...: for the SMs that were kept free for the operand-producing kernels, once those are done. */
+int ozk_gemm_i8_fused_queue_join(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
+                                 size_t pitch, const double *amax, const double *bmax, unsigned num_split,
+                                 unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
+                                 const ozk_queue_item_t *items, size_t num_items, const uint32_t *flags,
+                                 uint32_t epoch, uint32_t *done, uint32_t *scratch, size_t scratch_words,
+                                 unsigned first_pair, unsigned num_pairs, void *stream);
+
 /* One of the four real products of a complex GEMM (reference src/gemm.cu:479-518 loop body +
  * :160-186 axy_complex + :188-239 init_c_complex): x = the fp64_int8 product of the given planes,
  * C[i,j] = fma(x, (coef_re, coef_im), C'[i,j]) with C' = beta*C if apply_beta (first launch of the

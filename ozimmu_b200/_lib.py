@@ -47,6 +47,10 @@ PROTOTYPES = {
     "ozk_gemm_i8_fused_queue": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
                                         c_uint, c_uint, c_double, c_double, c_void_p, c_size_t, c_void_p, c_size_t,
                                         c_void_p, C.c_uint32, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
+    "ozk_gemm_i8_fused_queue_join": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p,
+                                             c_void_p, c_uint, c_uint, c_double, c_double, c_void_p, c_size_t, c_void_p,
+                                             c_size_t, c_void_p, C.c_uint32, c_void_p, c_void_p, c_size_t, c_uint,
+                                             c_uint, c_void_p]),
     "ozk_mantissa_loss_strided": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int, c_uint,
                                           c_uint, c_void_p]),
     "ozk_gemm_i8_fused_complex": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p,

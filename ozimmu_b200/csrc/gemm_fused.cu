@@ -88,6 +88,7 @@ struct FusedParams {
   uint32_t *q_slots;           // [pairs][q_cap]: the items each pair took, in order (zeroed before launch)
   uint32_t q_cap;
   long long q_timeout;         // clocks a readiness wait may take
+  uint32_t q_pair0;            // slot row of this launch's first pair (a second launch may join a running queue)
 };
 
 constexpr uint32_t kQueueEnd = 0xFFFFFFFFu;
@@ -252,7 +253,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0) & 1u;  // 0 = leader (issues the MMAs)
-  const uint32_t pair_id = blockIdx.x >> 1;
+  const uint32_t pair_id = (blockIdx.x >> 1) + (kQueue ? p.q_pair0 : 0u);
   const uint32_t num_pairs = gridDim.x >> 1;
   const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const uint32_t steps_per_tile = (p.single_a != 0 ? 1u : p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
@@ -718,8 +719,10 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
 
 // Queue-mode launch: 256-wide tiles, grid = the resident pairs minus the SMs kept free for the kernels that make the
 // operands ready (the split kernels run WHILE this kernel waits for them).
+// join_first_pair >= 0: a second launch on the SAME queue (scratch is not cleared, its pairs use the slot rows
+// join_first_pair ...): started once the SMs that were left to the operand-producing kernels are free again.
 int launch_pair_queue(const FusedParams &p0, unsigned reserve_sms, uint32_t *scratch, size_t scratch_words,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int join_first_pair = -1, unsigned join_pairs = 0) {
   using Cfg = PairCfg<256>;
   FusedParams p = p0;
   p.tiles_m = ceil_div_u32(p.m, 2 * BM);
@@ -747,12 +750,14 @@ int launch_pair_queue(const FusedParams &p0, unsigned reserve_sms, uint32_t *scr
   const uint32_t usable = static_cast<uint32_t>(sms) > reserve_sms + 2 ? static_cast<uint32_t>(sms) - reserve_sms : 2u;
   uint32_t pairs = usable / 2;
   if (pairs > p.q_num_items) pairs = p.q_num_items;
+  if (join_first_pair >= 0) pairs = join_pairs;
   if (pairs == 0) return 0;
-  // scratch: [0] queue head, [1] error flag, [2...] slots[pairs][num_items + 1]
+  // scratch: [0] queue head, [1] error flag, [2...] slots[pairs of all launches][num_items + 1]
   p.q_cap = p.q_num_items + 1;
-  const size_t need = 2 + static_cast<size_t>(pairs) * p.q_cap;
+  p.q_pair0 = join_first_pair >= 0 ? static_cast<uint32_t>(join_first_pair) : 0u;
+  const size_t need = 2 + static_cast<size_t>(p.q_pair0 + pairs) * p.q_cap;
   if (scratch == nullptr || scratch_words < need) return static_cast<int>(cudaErrorInvalidValue);
-  OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, need * sizeof(uint32_t), stream));
+  if (join_first_pair < 0) OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, scratch_words * sizeof(uint32_t), stream));
   p.q_next = scratch;
   p.q_error = scratch + 1;
   p.q_slots = scratch + 2;
@@ -933,6 +938,32 @@ extern "C" int ozk_gemm_i8_fused_queue(size_t m, size_t n, size_t k, const int8_
   p.q_epoch = epoch;
   p.q_done = done;
   return oz::launch_pair_queue(p, reserve_sms, scratch, scratch_words, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ozk_gemm_i8_fused_queue_join(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
+                                            size_t pitch, const double *amax, const double *bmax, unsigned num_split,
+                                            unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
+                                            const ozk_queue_item_t *items, size_t num_items, const uint32_t *flags,
+                                            uint32_t epoch, uint32_t *done, uint32_t *scratch, size_t scratch_words,
+                                            unsigned first_pair, unsigned num_pairs, void *stream) {
+  if (m == 0 || n == 0 || num_items == 0 || num_pairs == 0) return 0;
+  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m || items == nullptr || flags == nullptr ||
+      done == nullptr || num_items >= (1ull << 31) || first_pair > 4096 || num_pairs > 4096)
+    return static_cast<int>(cudaErrorInvalidValue);
+  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices, b_slices, num_split, bits_per_int8);
+  p.alpha = alpha;
+  p.beta = beta;
+  p.c = c;
+  p.ldc = ldc;
+  p.amax = amax;
+  p.bmax = bmax;
+  p.q_items = reinterpret_cast<const uint4 *>(items);
+  p.q_num_items = static_cast<uint32_t>(num_items);
+  p.q_flags = flags;
+  p.q_epoch = epoch;
+  p.q_done = done;
+  return oz::launch_pair_queue(p, 0, scratch, scratch_words, static_cast<cudaStream_t>(stream),
+                               static_cast<int>(first_pair), num_pairs);
 }
 
 extern "C" int ozk_gemm_i8_fused_complex(size_t m, size_t n, size_t k, const int8_t *a_slices,

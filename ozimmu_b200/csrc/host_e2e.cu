@@ -398,6 +398,21 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
                    "cuStreamWaitValue32");
       copy_matrix(c + c0 * ldc + r0, dc + c0 * ldc + r0, ldc, r1 - r0, c1 - c0, cudaMemcpyDeviceToHost, sout);
     }
+    // OZIMMU_B200_E2E_QUEUE_JOIN=1 (not yet run on hardware): once the last split is done, a second launch takes the
+    // SMs that were kept free for the splits and pops from the same queue
+    if (env_size("OZIMMU_B200_E2E_QUEUE_JOIN", 0) != 0) {
+      int dev = 0, sms = 0;
+      OZ_CUDA_CHECK(cudaGetDevice(&dev));
+      OZ_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const std::size_t all_pairs = static_cast<std::size_t>(sms) / 2;
+      const std::size_t main_pairs =
+          std::min<std::size_t>(static_cast<std::size_t>(sms) > reserve + 2 ? (sms - reserve) / 2 : 1, nitems);
+      if (all_pairs > main_pairs)
+        OZ_KERNEL_CHECK(ozk_gemm_i8_fused_queue_join(m, n, k, a_sl, b_sl, w.pitch, amax, bmax, s, bits, alpha, beta, dc, ldc,
+                                                     items_dev, nitems, flags_dev, epoch, done_dev, scratch_dev,
+                                                     scratch_words, static_cast<unsigned>(main_pairs),
+                                                     static_cast<unsigned>(all_pairs - main_pairs), sc));
+    }
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_product_tail[0], sp));
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_product_tail[0], 0));
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_done, sc));

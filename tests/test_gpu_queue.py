@@ -97,7 +97,12 @@ def test_queue_launch_equals_static_launch(m, n, k, order, late_flags):
     assert np.array_equal(done.cpu().numpy().astype(np.int64), 16 * tiles_per_block)
 
 
-def test_gemm_host_queue_mode(monkeypatch):
+@pytest.mark.parametrize("join", ["0", "1"])
+def test_gemm_host_queue_mode(monkeypatch, join):
+    """join=1 (a second launch takes the reserved SMs after the last split; 16 SMs reserved) has not run on hardware"""
+    monkeypatch.setenv("OZIMMU_B200_E2E_QUEUE_JOIN", join)
+    if join == "1":
+        monkeypatch.setenv("OZIMMU_B200_E2E_QUEUE_RESERVE_SMS", "16")
     h = oz.create()
     try:
         m, n, k = 2300, 2000, 900
