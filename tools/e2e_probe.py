@@ -1,5 +1,7 @@
-"""Times ozimmu_gemm_host (host operands, pinned) at n^3 for a list of block schedules:
-python tools/e2e_probe.py [n] [panel:rowblock[:taper] ...]   (0 = whole operand in one piece; default sweep below)"""
+"""Times ozimmu_gemm_host (host operands, pinned) at n^3 for a list of block schedules and checks every result
+against the device entry bit for bit:
+python tools/e2e_probe.py [n] [panel:rowblock[:taper[:ENV=V,ENV=V...]] ...]   (0 = whole operand in one piece)
+e.g.  python tools/e2e_probe.py 8192 768:768 768:768:0:OZIMMU_B200_E2E_QUEUE=1,OZIMMU_B200_E2E_QUEUE_RESERVE_SMS=16"""
 import os, sys, time
 from pathlib import Path
 import torch
@@ -12,21 +14,37 @@ a = torch.rand(n * n, dtype=torch.float64).pin_memory()
 b = torch.rand(n * n, dtype=torch.float64).pin_memory()
 c = torch.zeros(n * n, dtype=torch.float64).pin_memory()
 h = oz.create()
+want = torch.zeros(n * n, dtype=torch.float64, device="cuda")
+oz.gemm(h, 0, 0, n, n, n, 1.0, a.cuda(), n, b.cuda(), n, 0.0, want, n, oz.fp64_int8(9))
+torch.cuda.synchronize()
+want = want.cpu()
+touched = set()
 for combo in combos:
-    panel, rowblock, taper = (combo.split(":") + ["1"])[:3]
+    parts = combo.split(":", 3)
+    panel, rowblock = parts[0], parts[1]
+    taper = parts[2] if len(parts) > 2 else "0"
+    extra = parts[3] if len(parts) > 3 else ""
+    for key in touched:
+        os.environ.pop(key, None)
+    touched.clear()
     os.environ["OZIMMU_B200_E2E_PANEL"], os.environ["OZIMMU_B200_E2E_ROWBLOCK"] = panel, rowblock
     os.environ["OZIMMU_B200_E2E_TAPER"] = taper
+    for kv in filter(None, extra.split(",")):
+        key, val = kv.split("=", 1)
+        os.environ[key] = val
+        touched.add(key)
     for _ in range(2):
         oz.gemm_host(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(9))
     it = 5
-    best, t_all = 1e9, time.perf_counter()
+    times = []
     for _ in range(it):
         t0 = time.perf_counter()
         oz.gemm_host(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(9))
-        best = min(best, time.perf_counter() - t0)
-    dt = (time.perf_counter() - t_all) / it
-    print(f"gemm_host n={n} panel={panel} rowblock={rowblock} taper={taper}: mean {dt*1e3:.2f} ms best {best*1e3:.2f} ms  "
-          f"{2*n**3/dt/1e12:.2f} TFLOP/s-equiv", flush=True)
+        times.append(time.perf_counter() - t0)
+    ok = torch.equal(c.view(torch.int64), want.view(torch.int64))
+    dt = sum(times) / it
+    print(f"gemm_host n={n} panel={panel} rowblock={rowblock} taper={taper} {extra}: mean {dt*1e3:.2f} ms best {min(times)*1e3:.2f} "
+          f"worst {max(times)*1e3:.2f} ms  {2*n**3/dt/1e12:.2f} TFLOP/s-equiv  bit-identical={ok}", flush=True)
 # raw PCIe numbers for context
 d = torch.empty(n * n, dtype=torch.float64, device="cuda")
 torch.cuda.synchronize(); t0 = time.perf_counter(); d.copy_(a, non_blocking=True); torch.cuda.synchronize()
