@@ -130,6 +130,8 @@ struct StreamMemOps {
   Fn write = nullptr, wait = nullptr;
 };
 
+void ensure_stage(void **ptr, std::size_t *have, std::size_t need);
+
 const StreamMemOps &stream_mem_ops() {
   static const StreamMemOps ops = [] {
     StreamMemOps o;
@@ -151,6 +153,59 @@ const StreamMemOps &stream_mem_ops() {
 void mem_op_check(CUresult r, const char *what) {
   if (r != CUDA_SUCCESS) throw std::runtime_error(std::string("ozIMMU: ") + what + " failed with CUresult " + std::to_string(r));
 }
+
+}  // namespace
+
+bool oz::host::stream_mem_ops_available() { return stream_mem_ops().write != nullptr && stream_mem_ops().wait != nullptr; }
+
+void oz::host::stream_write_value32(cudaStream_t s, std::uint32_t *dev_addr, std::uint32_t value) {
+  mem_op_check(stream_mem_ops().write(s, reinterpret_cast<CUdeviceptr>(dev_addr), value, CU_STREAM_WRITE_VALUE_DEFAULT),
+               "cuStreamWriteValue32");
+}
+
+void oz::host::stream_wait_value32_geq(cudaStream_t s, std::uint32_t *dev_addr, std::uint32_t value) {
+  mem_op_check(stream_mem_ops().wait(s, reinterpret_cast<CUdeviceptr>(dev_addr), value, CU_STREAM_WAIT_VALUE_GEQ),
+               "cuStreamWaitValue32");
+}
+
+// Device block of the tile queue, [flags 64 x u32][done 64 x u32][items][kernel scratch], plus the pinned staging the
+// items are uploaded from; grows on demand.  Copies `items` into the staging and opens a new epoch.
+oz::host::QueueBuffers oz::host::queue_buffers(mtk::ozimmu::handle *h, const ozk_queue_item_t *items, std::size_t nitems,
+                                               unsigned reserve_sms) {
+  QueueBuffers q;
+  q.scratch_words = ozk_queue_scratch_words(nitems, reserve_sms);
+  const std::size_t off_done = 256, off_items = 512;
+  const std::size_t off_scratch = (off_items + nitems * sizeof(ozk_queue_item_t) + 255) / 256 * 256;
+  const std::size_t total = off_scratch + q.scratch_words * sizeof(std::uint32_t);
+  if (total > h->queue_dev_bytes) {
+    ensure_stage(&h->queue_dev, &h->queue_dev_bytes, total);
+    OZ_CUDA_CHECK(cudaMemset(h->queue_dev, 0, total));  // flags start at 0; epochs start at 1
+    h->queue_epoch = 0;
+  }
+  if (nitems * sizeof(ozk_queue_item_t) > h->queue_host_bytes) {
+    if (h->queue_host) OZ_CUDA_CHECK(cudaFreeHost(h->queue_host));
+    h->queue_host = nullptr;
+    h->queue_host_bytes = 0;
+    OZ_CUDA_CHECK(cudaMallocHost(&h->queue_host, nitems * sizeof(ozk_queue_item_t)));
+    h->queue_host_bytes = nitems * sizeof(ozk_queue_item_t);
+  }
+  std::copy(items, items + nitems, static_cast<ozk_queue_item_t *>(h->queue_host));
+  if (++h->queue_epoch == 0) {  // wrapped: stale flags could match again
+    OZ_CUDA_CHECK(cudaDeviceSynchronize());
+    OZ_CUDA_CHECK(cudaMemset(h->queue_dev, 0, 512));
+    h->queue_epoch = 1;
+  }
+  q.epoch = h->queue_epoch;
+  char *qd = static_cast<char *>(h->queue_dev);
+  q.flags = reinterpret_cast<std::uint32_t *>(qd);
+  q.done = reinterpret_cast<std::uint32_t *>(qd + off_done);
+  q.items = reinterpret_cast<ozk_queue_item_t *>(qd + off_items);
+  q.scratch = reinterpret_cast<std::uint32_t *>(qd + off_scratch);
+  q.items_host = static_cast<const ozk_queue_item_t *>(h->queue_host);
+  return q;
+}
+
+namespace {
 
 struct QueuePlan {
   std::vector<ozk_queue_item_t> items;
@@ -332,43 +387,19 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   // its module lazily, which must not happen while the persistent kernel spins on the flags that kernel feeds.
   const std::uint64_t warm_key = (static_cast<std::uint64_t>(s) << 8) | (op_a == op_n ? 1u : 0u) | (op_b == op_n ? 2u : 0u) |
                                  (static_cast<std::uint64_t>(k <= 2048 ? 0 : k <= 4096 ? 1 : k <= 8192 ? 2 : k <= 16384 ? 3 : 4) << 4);
-  const StreamMemOps &ops = stream_mem_ops();
-  if (env_size("OZIMMU_B200_E2E_QUEUE", 0) != 0 && h->queue_warm && h->queue_warm_key == warm_key && ops.write && ops.wait &&
+  if (env_size("OZIMMU_B200_E2E_QUEUE", 0) != 0 && h->queue_warm && h->queue_warm_key == warm_key &&
+      H::stream_mem_ops_available() &&
       (m + 255) / 256 <= 0xFFFF && (n + 255) / 256 <= 0xFFFF) {
     std::vector<std::pair<int, std::size_t>> ord;
     for (const Arrival &x : order) ord.emplace_back(x.which, x.idx);
     const QueuePlan plan = plan_queue(ae, be, ord);
     const std::size_t nitems = plan.items.size();
     const unsigned reserve = static_cast<unsigned>(env_size("OZIMMU_B200_E2E_QUEUE_RESERVE_SMS", 4));
-    const std::size_t scratch_words = ozk_queue_scratch_words(nitems, reserve);
-    // device block: [flags 64 x u32][done 64 x u32][items][kernel scratch]
-    const std::size_t off_done = 256, off_items = 512;
-    const std::size_t off_scratch = (off_items + nitems * sizeof(ozk_queue_item_t) + 255) / 256 * 256;
-    const std::size_t total = off_scratch + scratch_words * sizeof(std::uint32_t);
-    if (total > h->queue_dev_bytes) {
-      ensure_stage(&h->queue_dev, &h->queue_dev_bytes, total);
-      OZ_CUDA_CHECK(cudaMemset(h->queue_dev, 0, total));  // flags start at 0; epochs start at 1
-      h->queue_epoch = 0;
-    }
-    if (nitems * sizeof(ozk_queue_item_t) > h->queue_host_bytes) {
-      if (h->queue_host) OZ_CUDA_CHECK(cudaFreeHost(h->queue_host));
-      h->queue_host = nullptr;
-      h->queue_host_bytes = 0;
-      OZ_CUDA_CHECK(cudaMallocHost(&h->queue_host, nitems * sizeof(ozk_queue_item_t)));
-      h->queue_host_bytes = nitems * sizeof(ozk_queue_item_t);
-    }
-    std::copy(plan.items.begin(), plan.items.end(), static_cast<ozk_queue_item_t *>(h->queue_host));
-    if (++h->queue_epoch == 0) {  // wrapped: stale flags could match again
-      OZ_CUDA_CHECK(cudaDeviceSynchronize());
-      OZ_CUDA_CHECK(cudaMemset(h->queue_dev, 0, 512));
-      h->queue_epoch = 1;
-    }
-    const std::uint32_t epoch = h->queue_epoch;
-    char *qd = static_cast<char *>(h->queue_dev);
-    auto *flags_dev = reinterpret_cast<std::uint32_t *>(qd);
-    auto *done_dev = reinterpret_cast<std::uint32_t *>(qd + off_done);
-    auto *items_dev = reinterpret_cast<ozk_queue_item_t *>(qd + off_items);
-    auto *scratch_dev = reinterpret_cast<std::uint32_t *>(qd + off_scratch);
+    const H::QueueBuffers qb_ = H::queue_buffers(h, plan.items.data(), nitems, reserve);
+    const std::size_t scratch_words = qb_.scratch_words;
+    const std::uint32_t epoch = qb_.epoch;
+    std::uint32_t *flags_dev = qb_.flags, *done_dev = qb_.done, *scratch_dev = qb_.scratch;
+    ozk_queue_item_t *items_dev = qb_.items;
     cudaStream_t sp = h->product_stream[0];
     if (h->has_pending) OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, h->ev_done, 0));
     OZ_CUDA_CHECK(cudaMemcpyAsync(items_dev, h->queue_host, nitems * sizeof(ozk_queue_item_t), cudaMemcpyHostToDevice, sp));
@@ -390,12 +421,9 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
         qa++;
       }
       // the block's slices and row scales are complete: publish it to the running product launch
-      mem_op_check(ops.write(sc, reinterpret_cast<CUdeviceptr>(flags_dev + flag), epoch, CU_STREAM_WRITE_VALUE_DEFAULT),
-                   "cuStreamWriteValue32");
+      H::stream_write_value32(sc, flags_dev + flag, epoch);
       if (plan.expected[arrival] == 0) continue;
-      mem_op_check(ops.wait(sout, reinterpret_cast<CUdeviceptr>(done_dev + arrival), plan.expected[arrival],
-                            CU_STREAM_WAIT_VALUE_GEQ),
-                   "cuStreamWaitValue32");
+      H::stream_wait_value32_geq(sout, done_dev + arrival, plan.expected[arrival]);
       copy_matrix(c + c0 * ldc + r0, dc + c0 * ldc + r0, ldc, r1 - r0, c1 - c0, cudaMemcpyDeviceToHost, sout);
     }
     // OZIMMU_B200_E2E_QUEUE_JOIN=1 (not yet run on hardware): once the last split is done, a second launch takes the

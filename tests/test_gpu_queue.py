@@ -126,3 +126,38 @@ def test_gemm_host_queue_mode(monkeypatch, join):
         assert (oz.launch_count() - before - first) / 2 < first
     finally:
         oz.destroy(h)
+
+
+def test_gemm_streamed_b_queue_mode(monkeypatch):
+    """NOT yet run on hardware: gemm_streamed_b with OZIMMU_B200_STREAMED_QUEUE=1 (one queue launch instead of one
+    launch per panel); panels completed late, in order, by copies on a side stream."""
+    monkeypatch.setenv("OZIMMU_B200_STREAMED_QUEUE", "1")
+    h = oz.create()
+    try:
+        m, n, k = 1800, 2300, 900
+        a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 91))
+        b_full = to_dev(oracle_lib.gen_matrix("exp_rand-1", k * n, 92))
+        c0 = oracle_lib.gen_matrix("normal01", m * n, 93)
+        want = to_dev(c0)
+        assert oz.gemm(h, 0, 0, m, n, k, 2.0, a, m, b_full, k, 0.5, want, m, oz.fp64_int8(9)) == 0
+        torch.cuda.synchronize()
+        edges = [0, 768, 1536, n]
+        side = torch.cuda.Stream()
+        bfv = b_full.view(n, k)
+        for call in range(3):   # the first call goes through the multi-launch path and warms every kernel
+            b = torch.zeros_like(b_full)
+            bv = b.view(n, k)
+            got = to_dev(c0)
+            events = [torch.cuda.Event() for _ in range(3)]
+            torch.cuda.synchronize()
+            with torch.cuda.stream(side):
+                for p in range(3):
+                    torch.cuda._sleep(2_000_000)
+                    bv[edges[p]:edges[p + 1]].copy_(bfv[edges[p]:edges[p + 1]])
+                    events[p].record(side)
+            assert oz.gemm_streamed_b(h, 0, 0, m, n, k, 2.0, a, m, b, k, 0.5, got, m, oz.fp64_int8(9), edges,
+                                      [e.cuda_event for e in events]) == 0
+            torch.cuda.synchronize()
+            assert torch.equal(got.view(torch.int64), want.view(torch.int64)), call
+    finally:
+        oz.destroy(h)
