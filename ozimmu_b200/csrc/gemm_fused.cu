@@ -24,6 +24,10 @@
 //    acc = fma(p, 2^(32-rshift), acc).  After the last pair: x = acc*2^-44*amax[r]*bmax[c]; C = alpha*x (+ beta*C).
 //  * Soft lockstep between CTA pairs keeps the pairs of one wave within a few k-steps of each other so that they
 //    share slice panels through L2.
+//  * Tile queue: entry x tiles_m x tiles_n (entry = index in a strided batch, ozk_gemm_i8_fused_batched), static
+//    round-robin over ceil(tiles / rounds) CTA pairs so that every pair owns the same number of tiles; block launches
+//    (ozk_gemm_i8_fused_block) address a rectangle of C inside the operands' slice planes.  A separate instantiation
+//    (kQueue, experimental, ozk_gemm_i8_fused_queue) takes its tiles from a device-side queue gated by ready flags.
 #include <cstdlib>
 #include <mutex>
 
