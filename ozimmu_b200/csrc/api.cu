@@ -571,7 +571,7 @@ int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const opera
   cudaEvent_t ev_a = h->ev_block_split[0][0];
   OZ_CUDA_CHECK(cudaEventRecord(ev_a, s));  // also orders the products after everything queued on s before this call
 
-  // ---- experimental (OZIMMU_B200_STREAMED_QUEUE=1; NOT yet run on hardware): ONE product launch fed by the tile
+  // ---- experimental (OZIMMU_B200_STREAMED_QUEUE=1; parity verified on hardware, not yet timed): ONE product launch fed by the tile
   // queue instead of one launch per panel.  split(A) and the first panel's split run on the idle GPU;
   // the queue launch then starts, and the later panels' splits run on the SMs it leaves free, each followed by a
   // stream memory operation that publishes the panel.  Only after a call of the same configuration has gone through
