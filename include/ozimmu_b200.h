@@ -118,6 +118,9 @@ int ozk_gemm_i8_fused(size_t m, size_t n, size_t k, const int8_t *a_slices, cons
  * point at the block's first entries.  flags: OZK_FUSED_NO_LOCKSTEP = do not pace the CTA pairs against
  * each other (for launches that share the GPU with another launch). */
 #define OZK_FUSED_NO_LOCKSTEP 1u
+/* one CTA pair per tile (non-persistent launch): concurrent launches fill the SMs tile by tile through the hardware
+ * CTA scheduler, and a higher-priority kernel gets SMs whenever a tile ends (the block pipelines use this) */
+#define OZK_FUSED_ONE_TILE_PER_PAIR 2u
 int ozk_gemm_i8_fused_block(size_t m, size_t n, size_t k, const int8_t *a_slices, size_t a_plane_rows,
                             size_t row0, const int8_t *b_slices, size_t b_plane_rows, size_t col0,
                             size_t pitch, const double *amax, const double *bmax, unsigned num_split,
@@ -175,8 +178,8 @@ int ozk_gemm_i8_fused_complex(size_t m, size_t n, size_t k, const int8_t *a_slic
  * src/gemm.cu:143-147 applied to an all-zero accumulator). */
 int ozk_scale_c(size_t m, size_t n, double beta, double *c, size_t ldc, void *stream);
 
-/* Test/tuning hook: force the tile width of the fused kernel: (0, 128) or (0, 256); anything else restores
- * the per-problem choice. */
+/* Test/tuning hook: force the tile width of the fused kernel: (0, w), w in {128, 192, 208, 224, 240, 256}; anything
+ * else restores the per-problem choice (256 or 128).  OZIMMU_B200_TILE_N=w does the same from the environment. */
 int ozk_set_cluster_shape(int cm, int cn);
 
 /* Debug/verification launcher: the raw int32 product of ONE slice pair (1-based ids), written

@@ -632,6 +632,10 @@ int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const opera
     return 0;
   }
   bool used[handle::kProductStreams] = {};
+  // one CTA pair per tile (OZIMMU_B200_STREAMED_ONE_TILE, default 1): the panels' launches interleave tile by tile and
+  // whatever carries the next panel (a NCCL broadcast kernel, the panel's split) gets SMs whenever a tile ends
+  const unsigned panel_flags =
+      OZK_FUSED_NO_LOCKSTEP | (H::env_or("OZIMMU_B200_STREAMED_ONE_TILE", "1") != "0" ? OZK_FUSED_ONE_TILE_PER_PAIR : 0u);
   for (std::size_t p = 0; p < num_panels; p++) {
     const std::size_t j0 = col_edges[p], nj = col_edges[p + 1] - j0;
     if (nj == 0) continue;
@@ -640,13 +644,13 @@ int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const opera
     OZ_KERNEL_CHECK(ozk_split_int8_block(b_sl, w.pitch, n, j0, bmax + j0, scr_b + j0, nj, k, src, ldb, op_B != op_n,
                                          num_split, bits, 1, sb));
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[1][p], sb));
-    const int r = static_cast<int>(p % handle::kProductStreams);
+    const int r = static_cast<int>(p % 3);
     cudaStream_t sp = h->product_stream[r];
     used[r] = true;
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_a, 0));
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, h->ev_block_split[1][p], 0));
     OZ_KERNEL_CHECK(ozk_gemm_i8_fused_block(m, nj, k, a_sl, m, 0, b_sl, n, j0, w.pitch, amax, bmax + j0, num_split, bits,
-                                            *alpha, *beta, c_ptr + j0 * ldc, ldc, OZK_FUSED_NO_LOCKSTEP, sp));
+                                            *alpha, *beta, c_ptr + j0 * ldc, ldc, panel_flags, sp));
   }
   for (int r = 0; r < handle::kProductStreams; r++) {
     if (!used[r]) continue;

@@ -9,7 +9,7 @@
 //
 // Design (B200 / sm_100a), see DESIGN.md 3.2 for the measurements behind each choice:
 //  * CTA pair = one 256 x BN tile of C (tcgen05.mma.cta_group::2.kind::i8, UMMA M=256, N=BN, K=32), BN = 256
-//    (default) or 128 (small problems).  Each CTA owns 128 x BN outputs for the whole pair list, so the FP64
+//    (default) or 128 (small problems); 192..240 are built for tuning (deeper operand ring, PairCfg).  Each CTA owns 128 x BN outputs for the whole pair list, so the FP64
 //    accumulators never leave the SM: 96 columns per epilogue thread in registers, the rest (BN=256: 32) in SMEM.
 //  * Operands: int8 slices in the blocked, pre-swizzled layout of oz_common.cuh -- every 128-row x 128-byte tile
 //    is 16 KB contiguous, so a stage is filled by two linear bulk copies (cp.async.bulk: 54-76 B/clk/SM) rather
@@ -73,9 +73,11 @@ struct FusedParams {
   uint32_t *sync_ctr;          // one arrival counter per kSyncEvery k-steps, zeroed before launch (or null)
   uint32_t sync_window;        // a pair starts sync interval j only after interval j - window is complete
   uint32_t sync_len;           // counters available
-  uint32_t prefetch_ahead;     // k-steps of L2 prefetch lead (OZIMMU_B200_PREFETCH, 0 = off)
-  uint32_t prefetch_coop;      // != 0: the pairs that share a panel split its prefetches among themselves
   uint32_t no_lockstep;        // host only: never pace this launch (it shares the GPU with other launches)
+  uint32_t one_tile_per_pair;  // host only: grid = one CTA pair per tile (non-persistent; the hardware CTA scheduler is
+                               // the tile queue, and higher-priority kernels get SMs whenever a tile ends)
+  uint32_t b_rows;             // rows of B's slice planes that exist from b_slices on (multiple of 128): a tile
+                               // column narrower than 256 may reach past the plane's end
   // strided batch (grouped launch): tile index = entry * tiles_m * tiles_n + tile inside the entry; every entry
   // has its own slices / row scales / C at these distances (bytes for the slices, doubles for the rest)
   uint32_t batch;
@@ -215,9 +217,10 @@ __device__ __forceinline__ void item_coords(const FusedParams &p, uint32_t item,
 
 template <uint32_t BN_>
 struct PairCfg {
-  static constexpr uint32_t kBBytes = (BN_ / 2) * BK;                // this CTA's half of the B tile
-  static constexpr uint32_t kStageBytes = BM * BK + kBBytes;         // per CTA
-  static constexpr uint32_t kStages = (BN_ == 128) ? 8 : 5;
+  static_assert(BN_ % 16 == 0 && BN_ >= 128 && BN_ <= 256, "UMMA M=256 needs N % 16 == 0, N <= 256");
+  static constexpr uint32_t kBRows = BN_ / 2;                        // this CTA's half of the B tile
+  static constexpr uint32_t kBBytes = kBRows * BK;
+  static constexpr uint32_t kStageBytes = BM * BK + kBBytes;         // per CTA (a multiple of 1 KB: SW128 atoms)
   static constexpr uint32_t kAccBufs = (BN_ == 128) ? 4 : 2;
   static constexpr uint32_t kBufStride = BN_;                        // TMEM columns between buffers
   static constexpr uint32_t kColsPerThread = BN_ / 2;                // epilogue: 2 column halves
@@ -226,8 +229,13 @@ struct PairCfg {
   static constexpr uint32_t kRegCols = kColsPerThread < 96 ? kColsPerThread : 96;
   static constexpr uint32_t kSpillCols = kColsPerThread - kRegCols;
   static constexpr uint32_t kSpillBytes = 2 * kSpillCols * BM * 8;
+  // the operand ring takes what is left of the 227 KB: BN=256 -> 5 stages, 240 -> 5, 224 -> 6, 208 -> 7, 192 / 128 -> 8
+  static constexpr uint32_t kSmemMax = 227 * 1024, kBarReserve = 320, kAlign = 1024;
+  static constexpr uint32_t kStagesFit = (kSmemMax - kSpillBytes - kBarReserve - kAlign) / kStageBytes;
+  static constexpr uint32_t kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr uint32_t kBarBytes = 8 * (3 * kStages + 2 * kAccBufs) + 16;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kSpillBytes + kBarBytes + 1024;
+  static_assert(kBarBytes <= kBarReserve, "barrier block");
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kSpillBytes + kBarBytes + kAlign;
   static constexpr uint32_t kRegsOther = (BN_ == 128) ? 56 : 40;
   static constexpr uint32_t kRegsEpi = (BN_ == 128) ? 224 : 232;
 };
@@ -308,38 +316,24 @@ oz_gemm_pair_kernel(const FusedParams p) {
         }
         const int8_t *a_base = p.a_slices + static_cast<size_t>(entry) * p.a_batch_bytes;
         const int8_t *b_base = p.b_slices + static_cast<size_t>(entry) * p.b_batch_bytes;
-        // this CTA's 128 rows of A; its BN/2 rows of B (BN=256: one whole 128-row tile; BN=128: half a tile)
+        // this CTA's 128 rows of A (one 16 KB tile per k-block) and its BN/2 rows of B: rows [b_row0, b_row0 + BN/2) of the
+        // plane, which lie in one 128-row tile (BN = 256, 128) or straddle two (other widths): up to two linear pieces,
+        // each a whole number of 8-row swizzle atoms; rows past the end of the plane are not fetched (their columns of
+        // C do not exist)
         const size_t a_tile = static_cast<size_t>(tm) * 2 + rank;
-        const size_t b_tile = (BN_ == 256) ? static_cast<size_t>(tn) * 2 + rank : static_cast<size_t>(tn);
-        const size_t b_sub = (BN_ == 256) ? 0 : static_cast<size_t>(rank) * Cfg::kBBytes;
+        const uint32_t b_row0 = tn * BN_ + rank * Cfg::kBRows;
+        const uint32_t b_avail = b_row0 < p.b_rows ? p.b_rows - b_row0 : 0u;
+        const uint32_t b_rows1 = min(min(Cfg::kBRows, 128u - (b_row0 & 127u)), b_avail);
+        const uint32_t b_rows2 = min(Cfg::kBRows - b_rows1, b_avail - b_rows1);
+        const size_t b_tile = b_row0 >> 7;
+        const size_t b_sub = static_cast<size_t>(b_row0 & 127u) * BK;
+        const uint32_t stage_tx = BM * BK + (b_rows1 + b_rows2) * BK;
         for (PairIter it(p); it.valid(); it.next()) {
           const int8_t *a_src = a_base + ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
           const int8_t *b_src =
               b_base + ((it.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
-          // optional L2 prefetch `prefetch_ahead` k-steps ahead (into the next product of this tile if needed)
-          PairIter nx = it;
-          nx.next();
-          const int8_t *a_nx = nullptr, *b_nx = nullptr;
-          if (p.prefetch_ahead && nx.valid()) {
-            a_nx = a_base + ((nx.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
-            b_nx = b_base + ((nx.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
-          }
+          const int8_t *b_src2 = b_src - b_sub + static_cast<size_t>(p.k_blocks) * kTileBytes;  // next row tile
           for (uint32_t kb = 0; kb < p.k_blocks; kb++, g++) {
-            if (p.prefetch_ahead && issuer) {
-              // Cooperative: the ~8 pairs of a wave that stream the same A panel (same tile row, consecutive
-              // tile columns) each prefetch every 8th k-block of it, likewise the 8 pairs of a band that share a B
-              // panel -- one request per panel chunk instead of one per pair.
-              const uint32_t kf = kb + p.prefetch_ahead;
-              const bool do_a = !p.prefetch_coop || ((kf ^ tn) & 7u) == 0;
-              const bool do_b = !p.prefetch_coop || ((kf ^ tm) & 7u) == 0;
-              if (kf < p.k_blocks) {
-                if (do_a) ptx::bulk_prefetch_l2(a_src + static_cast<size_t>(kf) * kTileBytes, BM * BK);
-                if (do_b) ptx::bulk_prefetch_l2(b_src + static_cast<size_t>(kf) * kTileBytes, Cfg::kBBytes);
-              } else if (a_nx != nullptr && kf - p.k_blocks < p.k_blocks) {
-                if (do_a) ptx::bulk_prefetch_l2(a_nx + static_cast<size_t>(kf - p.k_blocks) * kTileBytes, BM * BK);
-                if (do_b) ptx::bulk_prefetch_l2(b_nx + static_cast<size_t>(kf - p.k_blocks) * kTileBytes, Cfg::kBBytes);
-              }
-            }
             if (lockstep && (g % kSyncEvery) == 0) {
               const uint32_t j = g / kSyncEvery;
               if (j >= p.sync_len) {
@@ -366,9 +360,13 @@ oz_gemm_pair_kernel(const FusedParams p) {
             ptx::mbar_wait(empty_bar(stage), ph ^ 1u);
             const uint32_t dst = smem_base + stage * Cfg::kStageBytes;
             if (issuer) {
-              ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              ptx::mbar_expect_tx(full_bar(stage), stage_tx);
               ptx::bulk_load(dst, a_src + static_cast<size_t>(kb) * kTileBytes, BM * BK, full_bar(stage));
-              ptx::bulk_load(dst + BM * BK, b_src + static_cast<size_t>(kb) * kTileBytes, Cfg::kBBytes, full_bar(stage));
+              if (b_rows1)
+                ptx::bulk_load(dst + BM * BK, b_src + static_cast<size_t>(kb) * kTileBytes, b_rows1 * BK, full_bar(stage));
+              if (b_rows2)
+                ptx::bulk_load(dst + BM * BK + b_rows1 * BK, b_src2 + static_cast<size_t>(kb) * kTileBytes, b_rows2 * BK,
+                               full_bar(stage));
             }
             if (++stage == kStagesP) { stage = 0; ph ^= 1u; }
           }
@@ -458,22 +456,26 @@ oz_gemm_pair_kernel(const FusedParams p) {
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * Cfg::kBufStride + half * kCols;
         const double scale = it.scale(p.bits);
 #pragma unroll
-        for (uint32_t c = 0; c < kCols / 16; c++) {
+        for (uint32_t c = 0; c < (kCols + 15) / 16; c++) {
+          // 16 columns per TMEM load; a tile width that is not a multiple of 32 ends with one 8-column load
+          const bool wide = c * 16 + 16 <= kCols;
+          const uint32_t nv = wide ? 16u : 8u;
           uint32_t v[16];
-          ptx::tmem_ld_x16(taddr + c * 16, v);
+          if (wide) ptx::tmem_ld_x16(taddr + c * 16, v);
+          else ptx::tmem_ld_x8(taddr + c * 16, v);
           ptx::tmem_ld_wait();
           if (!raw) {
             // (double)p without I2F.F64 (a quarter-rate conversion, 15/clk/SM measured, that would make the
             // epilogue as slow as the MMAs): 2^52 + 2^31 + p is the bit pattern {0x43300000, p ^ 0x80000000};
             // subtracting 2^52 + 2^31 is exact.
 #pragma unroll
-            for (uint32_t g = 0; g < 16; g += 8) {
+            for (uint32_t g = 0; g < nv; g += 8) {
               double d[8];
 #pragma unroll
               for (uint32_t j = 0; j < 8; j++)
                 d[j] = __dadd_rn(__hiloint2double(0x43300000, static_cast<int>(v[g + j] ^ 0x80000000u)),
                                  -4503601774854144.0);
-              if (c * 16 < kRegCols) {
+              if (c * 16 + g < kRegCols) {
 #pragma unroll
                 for (uint32_t j = 0; j < 8; j++)
                   acc[(c * 16 + g + j) % kRegCols] = __fma_rn(d[j], scale, acc[(c * 16 + g + j) % kRegCols]);
@@ -487,7 +489,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
             }
           } else if (!kQueue && row < p.m) {
 #pragma unroll
-            for (uint32_t j = 0; j < 16; j++) {
+            for (uint32_t j = 0; j < nv; j++) {
               const uint32_t col = col0 + c * 16 + j;
               if (col < p.n)
                 p.c_i32[(static_cast<size_t>(entry) * p.n + col) * p.m + row] = static_cast<int32_t>(v[j]);
@@ -602,23 +604,6 @@ uint32_t lockstep_window() {
   return w;
 }
 
-uint32_t prefetch_ahead() {
-  static const uint32_t v = [] {
-    uint32_t x = 0;
-    if (const char *e = std::getenv("OZIMMU_B200_PREFETCH")) x = static_cast<uint32_t>(std::atoi(e));
-    return x > 64 ? 64u : x;
-  }();
-  return v;
-}
-
-uint32_t prefetch_coop() {
-  static const uint32_t v = [] {
-    const char *e = std::getenv("OZIMMU_B200_PREFETCH_COOP");
-    return e ? static_cast<uint32_t>(std::atoi(e)) : 1u;
-  }();
-  return v;
-}
-
 constexpr uint32_t kSyncCounters = 1u << 16;  // per buffer: 64 Ki intervals = 1 Mi k-steps per CTA pair
 constexpr int kSyncBuffers = 8;               // launches that may be in flight at once without sharing
 uint32_t *next_sync_buffer() {
@@ -652,9 +637,8 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   p.group_m = 8;
   if (p.rt_a == 0) p.rt_a = static_cast<uint32_t>(slice_row_tiles(p.m));  // != 0: block of a larger plane
   if (p.rt_b == 0) p.rt_b = static_cast<uint32_t>(slice_row_tiles(p.n));
+  if (p.b_rows == 0) p.b_rows = p.rt_b * static_cast<uint32_t>(kTileRows);
   p.sync_window = lockstep_window();
-  p.prefetch_ahead = prefetch_ahead();
-  p.prefetch_coop = prefetch_coop();
 
   auto kern = oz_gemm_pair_kernel<BN_>;
   int dev = 0, sms = 0;
@@ -699,7 +683,11 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   // pipelines rotate launches over several streams); with the full grid and 128 tiles, 20 pairs run one tile and 54
   // run two, and whichever CTAs of the next launch start late still own two tiles -- 2 rounds per 1.73 rounds of work.
   const uint32_t rounds = ceil_div_u32(num_tiles, static_cast<uint32_t>(max_pairs));
-  const uint32_t pairs = ceil_div_u32(num_tiles, rounds);
+  // one_tile_per_pair: a non-persistent launch, one CTA pair per tile.  The hardware CTA scheduler then is the tile
+  // queue: pairs of concurrent launches fill the SMs in launch order with no ragged last round per launch, and a
+  // higher-priority kernel (the split of the operand block that has just arrived) gets SMs whenever a tile ends
+  // instead of waiting for a persistent pair's whole tile list.
+  const uint32_t pairs = p.one_tile_per_pair ? num_tiles : ceil_div_u32(num_tiles, rounds);
   cfg.gridDim = dim3(pairs * 2);
   // lockstep counters only pay off when several rounds of tiles stream through L2 (pairs cannot drift apart
   // within a single round, and the polling costs ~7 % there)
@@ -736,7 +724,7 @@ int launch_pair_queue(const FusedParams &p0, unsigned reserve_sms, uint32_t *scr
   p.rt_b = static_cast<uint32_t>(slice_row_tiles(p.n));
   p.batch = 1;
   p.sync_ctr = nullptr;
-  p.prefetch_ahead = 0;
+  p.b_rows = p.rt_b * static_cast<uint32_t>(kTileRows);
   auto kern = oz_gemm_pair_kernel<256, true>;
   int dev = 0, sms = 0, clock_khz = 0;
   OZ_CUDA_TRY(cudaGetDevice(&dev));
@@ -783,12 +771,33 @@ int launch_pair_queue(const FusedParams &p0, unsigned reserve_sms, uint32_t *scr
   return 0;
 }
 
+// tile widths built into the library (UMMA N of the CTA pair): 256 and 128 are the defaults, the widths in between
+// trade MACs per delivered byte for a deeper operand ring (PairCfg) and a different tile count
+constexpr int kTileWidths[] = {256, 240, 224, 208, 192, 128};
+
+bool tile_width_ok(int bn) {
+  for (int w : kTileWidths)
+    if (w == bn) return true;
+  return false;
+}
+
+// OZIMMU_B200_TILE_N=<width>: force the tile width (read once); OZIMMU_B200_TILE_CANDIDATES=a,b,..: the widths the
+// per-problem choice considers (default 256,128)
+int env_tile_width() {
+  static const int v = [] {
+    const char *e = std::getenv("OZIMMU_B200_TILE_N");
+    const int w = e ? std::atoi(e) : 0;
+    return tile_width_ok(w) ? w : 0;
+  }();
+  return v;
+}
+
 int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
-  int bn = g_tile_override;
+  int bn = g_tile_override ? g_tile_override : env_tile_width();
   if (bn == 0) {
     // The kernel is bound by operand delivery into the SMs, so a launch costs about
     // rounds x bytes-per-k-block-per-SM = ceil(tiles / resident pairs) x (128 + BN/2).  BN=256 delivers the
-    // fewest bytes per MAC; the narrower tile wins when it fills more SMs.
+    // fewest bytes per MAC; a narrower tile wins when it fills more SMs.
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -806,6 +815,10 @@ int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
   }
   switch (bn) {
     case 256: return launch_pair<256>(p, stream);
+    case 240: return launch_pair<240>(p, stream);
+    case 224: return launch_pair<224>(p, stream);
+    case 208: return launch_pair<208>(p, stream);
+    case 192: return launch_pair<192>(p, stream);
     case 128: return launch_pair<128>(p, stream);
     default: return static_cast<int>(cudaErrorInvalidValue);
   }
@@ -835,7 +848,7 @@ FusedParams base_params(size_t m, size_t n, size_t pitch, const int8_t *a_slices
 // Test/tuning hook: force the tile width of the fused kernel: (0, 128) or (0, 256); anything else restores
 // the per-problem choice.
 extern "C" int ozk_set_cluster_shape(int cm, int cn) {
-  oz::g_tile_override = (cm == 0 && (cn == 128 || cn == 256)) ? cn : 0;
+  oz::g_tile_override = (cm == 0 && oz::tile_width_ok(cn)) ? cn : 0;
   return 0;
 }
 
@@ -872,7 +885,9 @@ extern "C" int ozk_gemm_i8_fused_block(size_t m, size_t n, size_t k, const int8_
                                       b_slices + (col0 / oz::kTileRows) * tile_row_bytes, num_split, bits_per_int8);
   p.rt_a = static_cast<uint32_t>(oz::slice_row_tiles(a_plane_rows));
   p.rt_b = static_cast<uint32_t>(oz::slice_row_tiles(b_plane_rows));
+  p.b_rows = p.rt_b * static_cast<uint32_t>(oz::kTileRows) - static_cast<uint32_t>(col0);
   p.no_lockstep = (flags & OZK_FUSED_NO_LOCKSTEP) ? 1u : 0u;
+  p.one_tile_per_pair = (flags & OZK_FUSED_ONE_TILE_PER_PAIR) ? 1u : 0u;
   p.alpha = alpha;
   p.beta = beta;
   p.c = c;

@@ -140,10 +140,10 @@ struct mtk::ozimmu::handle {
   // that a launch back-fills the SMs the previous one leaves idle in its last round of tiles
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, compute_stream = nullptr;
   static constexpr int kMaxBlocks = 16;        // row blocks of op(A) / column blocks of op(B)
-  static constexpr int kProductStreams = 3;
+  static constexpr int kProductStreams = 8;    // streams available; the pipelines rotate over the first 3 by default
   cudaStream_t product_stream[kProductStreams] = {};
   cudaEvent_t ev_block_in[2][kMaxBlocks] = {}, ev_block_split[2][kMaxBlocks] = {};  // [0] = A, [1] = B
-  cudaEvent_t ev_rect_out[2 * kMaxBlocks] = {};                                     // one per fused launch
+  std::vector<cudaEvent_t> ev_rect_out;                                             // one per fused launch, grown on demand
   cudaEvent_t ev_product_tail[kProductStreams] = {};
   // experimental queue mode of ozimmu_gemm_host (OZIMMU_B200_E2E_QUEUE=1): device block [flags | done | items |
   // kernel scratch], pinned staging for the items, the epoch that marks a flag as "ready in this call"

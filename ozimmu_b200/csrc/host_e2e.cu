@@ -64,7 +64,6 @@ void oz::host::ensure_pipeline_streams(mtk::ozimmu::handle *h) {
     for (auto &e : row) make(e);
   for (auto &row : h->ev_block_split)
     for (auto &e : row) make(e);
-  for (auto &e : h->ev_rect_out) make(e);
   for (auto &e : h->ev_product_tail) make(e);
 }
 
@@ -355,22 +354,48 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[1][j], sc));
   };
   // C[i0 : i0+mi, j0 : j0+nj] once `ready` (the split that completed its operands; the compute stream runs the
-  // splits in arrival order, so it implies every earlier one) has fired
+  // splits in arrival order, so it implies every earlier one) has fired.  OZIMMU_B200_E2E_ONE_TILE (default 1): the
+  // launches are non-persistent, one CTA pair per tile, so the hardware CTA scheduler interleaves the tiles of
+  // consecutive launches and the high-priority block splits get SMs whenever a tile ends.
+  // OZIMMU_B200_E2E_RECT_TILES=t (default 0 = off): a rectangle of more than t tiles is cut along its long side into
+  // launches of at most t tiles, each with its own copy-out, so that the D2H of a rectangle starts before its last
+  // tile is done.
+  const bool one_tile = env_size("OZIMMU_B200_E2E_ONE_TILE", 1) != 0;
+  const std::size_t rect_tiles = env_size("OZIMMU_B200_E2E_RECT_TILES", 0);
+  const unsigned nstreams = static_cast<unsigned>(
+      std::min<std::size_t>(std::max<std::size_t>(env_size("OZIMMU_B200_E2E_STREAMS", 3), 1), handle::kProductStreams));
+  const unsigned fused_flags = OZK_FUSED_NO_LOCKSTEP | (one_tile ? OZK_FUSED_ONE_TILE_PER_PAIR : 0u);
   unsigned rects = 0;
   bool used[handle::kProductStreams] = {};
-  auto product_rect = [&](std::size_t i0, std::size_t mi, std::size_t j0, std::size_t nj, cudaEvent_t ready) {
-    if (mi == 0 || nj == 0) return;
-    const unsigned r = rects % handle::kProductStreams;
+  auto product_piece = [&](std::size_t i0, std::size_t mi, std::size_t j0, std::size_t nj, cudaEvent_t ready) {
+    const unsigned r = rects % nstreams;
     cudaStream_t sp = h->product_stream[r];
     used[r] = true;
+    while (h->ev_rect_out.size() <= rects) {
+      cudaEvent_t e = nullptr;
+      OZ_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->ev_rect_out.push_back(e);
+    }
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, ready, 0));
     double *dblk = dc + j0 * ldc + i0;
     OZ_KERNEL_CHECK(ozk_gemm_i8_fused_block(mi, nj, k, a_sl, m, i0, b_sl, n, j0, w.pitch, amax + i0, bmax + j0, s, bits,
-                                            alpha, beta, dblk, ldc, OZK_FUSED_NO_LOCKSTEP, sp));
+                                            alpha, beta, dblk, ldc, fused_flags, sp));
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_rect_out[rects], sp));
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sout, h->ev_rect_out[rects], 0));
     copy_matrix(c + j0 * ldc + i0, dblk, ldc, mi, nj, cudaMemcpyDeviceToHost, sout);
     rects++;
+  };
+  auto product_rect = [&](std::size_t i0, std::size_t mi, std::size_t j0, std::size_t nj, cudaEvent_t ready) {
+    if (mi == 0 || nj == 0) return;
+    const std::size_t tm = (mi + 255) / 256, tn = (nj + 255) / 256;
+    if (rect_tiles == 0 || tm * tn <= rect_tiles) return product_piece(i0, mi, j0, nj, ready);
+    if (tn >= tm) {   // wide: pieces of whole tile columns
+      const std::size_t step = std::max<std::size_t>(1, rect_tiles / tm) * 256;
+      for (std::size_t j = 0; j < nj; j += step) product_piece(i0, mi, j0 + j, std::min(step, nj - j), ready);
+    } else {          // tall: pieces of whole tile rows
+      const std::size_t step = std::max<std::size_t>(1, rect_tiles / tn) * 256;
+      for (std::size_t i = 0; i < mi; i += step) product_piece(i0 + i, std::min(step, mi - i), j0, nj, ready);
+    }
   };
 
   // arrival order: B0, A0, B1, A1, ... (the longer operand's remaining blocks follow at the end); queue every

@@ -79,7 +79,10 @@ def test_split_block_rejects_misaligned_blocks():
     (900, 1100, 1030, [0, 768, 900], [0, 512, 1024, 1100]),
 ])
 @pytest.mark.parametrize("beta", [0.0, -0.75])
-def test_fused_blocks_equal_whole(m, n, k, row_edges, col_edges, beta):
+@pytest.mark.parametrize("width", [0, 240, 224, 208, 192])
+def test_fused_blocks_equal_whole(m, n, k, row_edges, col_edges, beta, width):
+    """block launches (all flag combinations, every tile width -- widths below 256 read B rows past the block and, at
+    the plane's end, must not read past the plane) == one whole launch"""
     L = oz.lib()
     s, nbits = 9, int(L.ozk_bits_per_int8(k))
     a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 31))   # op_t A: k x m column-major == rows contiguous
@@ -95,23 +98,29 @@ def test_fused_blocks_equal_whole(m, n, k, row_edges, col_edges, beta):
     streams = [torch.cuda.Stream() for _ in range(3)]
     torch.cuda.synchronize()
     i = 0
+    L.ozk_set_cluster_shape(0, width)
     for r0, r1 in zip(row_edges[:-1], row_edges[1:]):
         for q0, q1 in zip(col_edges[:-1], col_edges[1:]):
             st = streams[i % 3]   # concurrent launches on several streams, as the host pipeline issues them
             i += 1
             rc = L.ozk_gemm_i8_fused_block(r1 - r0, q1 - q0, k, a_sl.data_ptr(), m, r0, b_sl.data_ptr(), n, q0, pitch,
                                            amax.data_ptr() + 8 * r0, bmax.data_ptr() + 8 * q0, s, nbits, 1.25, beta,
-                                           got.data_ptr() + 8 * (q0 * ldc + r0), ldc, i & 1, int(st.cuda_stream))
+                                           got.data_ptr() + 8 * (q0 * ldc + r0), ldc, i & 3, int(st.cuda_stream))
             assert rc == 0
     torch.cuda.synchronize()
+    L.ozk_set_cluster_shape(0, 0)
     assert torch.equal(got.view(torch.int64), want.view(torch.int64))
 
 
-@pytest.mark.parametrize("panel,rowblock", [("256", "256"), ("512", "0"), ("0", "512"), ("768", "1024"), (None, None)])
-def test_gemm_host_block_schedules(handle, panel, rowblock, monkeypatch):
+@pytest.mark.parametrize("panel,rowblock,one_tile,rect_tiles", [
+    ("256", "256", None, None), ("512", "0", "0", None), ("0", "512", None, "2"), ("768", "1024", "0", "3"),
+    ("512", "512", "1", "1"), (None, None, None, None)])
+def test_gemm_host_block_schedules(handle, panel, rowblock, one_tile, rect_tiles, monkeypatch):
     """Every block schedule of the host-operand entry (square blocks, column panels only, row blocks only, the
-    default) gives the bits of the device entry; ragged sizes, padded leading dimensions, all op combinations."""
-    for name, v in (("OZIMMU_B200_E2E_PANEL", panel), ("OZIMMU_B200_E2E_ROWBLOCK", rowblock)):
+    default; persistent or one-tile-per-pair launches; rectangles cut into several launches) gives the bits of the
+    device entry; ragged sizes, padded leading dimensions, all op combinations."""
+    for name, v in (("OZIMMU_B200_E2E_PANEL", panel), ("OZIMMU_B200_E2E_ROWBLOCK", rowblock),
+                    ("OZIMMU_B200_E2E_ONE_TILE", one_tile), ("OZIMMU_B200_E2E_RECT_TILES", rect_tiles)):
         if v is None:
             monkeypatch.delenv(name, raising=False)
         else:
