@@ -88,6 +88,20 @@ int gemm_strided_batched(handle_t handle, const operation_t op_A, const operatio
                          const std::size_t ldc, const long long stride_c, const std::size_t batch_count,
                          const compute_mode_t compute_mode);
 
+// The same for real or complex data: alpha / beta as for gemm(), strides in (complex) elements.  fp64_int8_auto picks
+// the split count per entry from one counter pass over the whole batch.
+int gemm_strided_batched(handle_t handle, const operation_t op_A, const operation_t op_B, const std::size_t m,
+                         const std::size_t n, const std::size_t k, const void *alpha, const void *const a_ptr,
+                         const std::size_t lda, const long long stride_a, const void *const b_ptr,
+                         const std::size_t ldb, const long long stride_b, const void *beta, void *const c_ptr,
+                         const std::size_t ldc, const long long stride_c, const std::size_t batch_count,
+                         const compute_mode_t compute_mode, const element_kind_t element_kind);
+
+// Extension: alpha / beta of the following gemm() / gemm_strided_batched() calls are DEVICE pointers (cuBLAS device
+// pointer mode).  The fp64_int8_S modes read them on the device in stream order; the other modes fetch them with one
+// blocking read.  The reference always dereferences them on the host (src/gemm.cu:405).
+void set_scalar_pointer_mode(handle_t handle, const bool on_device);
+
 // Extension: the same real GEMM when B arrives column panel by column panel (e.g. as a broadcast from another
 // GPU delivers it): panel p = columns [col_edges[p], col_edges[p+1]) of op(B) and C (inner edges multiples of 256,
 // col_edges[0] = 0, col_edges[num_panels] = n, at most 16 panels) may be read once ready[p] -- an event the caller

@@ -100,6 +100,11 @@ int ozk_split_int8_batched(int8_t *out, size_t out_stride, size_t pitch, double 
                            uint32_t *scratch, size_t scr_stride, size_t rows, size_t len, const double *in,
                            size_t ld, size_t in_stride, int col_major, unsigned num_split,
                            unsigned bits_per_int8, size_t batch, void *stream);
+/* the same on one plane of interleaved complex matrices (elem_stride = 2; in_stride still counts doubles) */
+int ozk_split_int8_batched_strided(int8_t *out, size_t out_stride, size_t pitch, double *max_exp, size_t max_stride,
+                                   uint32_t *scratch, size_t scr_stride, size_t rows, size_t len, const double *in,
+                                   size_t ld, size_t in_stride, int col_major, unsigned num_split,
+                                   unsigned bits_per_int8, unsigned elem_stride, size_t batch, void *stream);
 
 /* reference src/gemm.cu:266-334 (matmul_core -> cublasGemmEx int8) + :77-102
  * (accumulate_in_f64) + :104-122 (init_accumulator_buffer) + :124-158 (axby), fused:
@@ -165,18 +170,43 @@ int ozk_gemm_i8_fused_queue_join(size_t m, size_t n, size_t k, const int8_t *a_s
                                  uint32_t epoch, uint32_t *done, uint32_t *scratch, size_t scratch_words,
                                  unsigned first_pair, unsigned num_pairs, void *stream);
 
-/* One of the four real products of a complex GEMM (reference src/gemm.cu:479-518 loop body +
- * :160-186 axy_complex + :188-239 init_c_complex): x = the fp64_int8 product of the given planes,
- * C[i,j] = fma(x, (coef_re, coef_im), C'[i,j]) with C' = beta*C if apply_beta (first launch of the
- * four; C not read when beta == 0) else C.  c: cuDoubleComplex*, ldc in complex elements. */
-int ozk_gemm_i8_fused_complex(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
-                              size_t pitch, const double *amax, const double *bmax, unsigned num_split,
-                              unsigned bits_per_int8, double coef_re, double coef_im, int apply_beta,
-                              double beta_re, double beta_im, void *c, size_t ldc, void *stream);
+/* The general form of the fused launch -- real or complex C, whole matrix or block, single or strided batch,
+ * scalars by value or in device memory; the ozk_gemm_i8_fused* functions above fill this struct.  Zero-initialise
+ * it and set what applies.
+ *   complex_c != 0: a complex GEMM (reference src/gemm.cu:412-521) in ONE launch.  a_slices / b_slices hold two planes
+ *   each (real part, imaginary part, split independently: src/split.cu:69-152) a_plane_bytes / b_plane_bytes apart,
+ *   amax / bmax two row-scale vectors amax_plane / bmax_plane doubles apart; c is cuDoubleComplex*, ldc / c_batch in
+ *   complex elements.  Every tile runs the reference's four real plane products in its order (im,im) -> -alpha,
+ *   (re,re) -> +alpha, (im,re), (re,im) -> i*alpha (:479-518), each folded into C with y = fma(x, coef, y)
+ *   (axy_complex, :160-186) after C = beta*C (init_c_complex, :188-239; SURVEY App. B.6 fixed: Im uses the original Re).
+ *   alpha_dev / beta_dev (both or neither): the scalars are read from device memory in stream order (cuBLAS device
+ *   pointer mode; 1 double each, 2 for complex) and alpha[] / beta[] are ignored. */
+typedef struct {
+  size_t m, n, k, pitch;
+  const int8_t *a_slices, *b_slices;   /* base of the operands' slices (entry 0, real plane) */
+  size_t a_plane_rows, b_plane_rows;   /* rows the slice planes were split for (0: m / n) */
+  size_t row0, col0;                   /* origin of the m x n block inside the planes, multiples of 256 */
+  const double *amax, *bmax;           /* row scales of the block's first row / column */
+  unsigned num_split, bits_per_int8;
+  int complex_c;
+  size_t a_plane_bytes, b_plane_bytes, amax_plane, bmax_plane;
+  double alpha[2], beta[2];
+  const double *alpha_dev, *beta_dev;
+  void *c;                             /* the block's first element */
+  size_t ldc;
+  size_t batch;                        /* 0 or 1: a single product */
+  size_t a_batch_bytes, b_batch_bytes, amax_batch, bmax_batch, c_batch;
+  unsigned flags;                      /* OZK_FUSED_* */
+} ozk_fused_args_t;
+int ozk_gemm_i8_fused_ex(const ozk_fused_args_t *args, void *stream);
 
 /* Degenerate k == 0 product: C = beta * C (C not read when beta == 0; reference
  * src/gemm.cu:143-147 applied to an all-zero accumulator). */
 int ozk_scale_c(size_t m, size_t n, double beta, double *c, size_t ldc, void *stream);
+/* the same for complex C (complex_c != 0: beta = {re, im}, c cuDoubleComplex*, ldc in complex elements: the beta
+ * pre-scale of the complex path) and / or beta read from device memory (beta_dev != NULL) */
+int ozk_scale_c_ex(size_t m, size_t n, const double beta[2], const double *beta_dev, int complex_c, void *c,
+                   size_t ldc, void *stream);
 
 /* Test/tuning hook: force the tile width of the fused kernel: (0, w), w in {128, 192, 208, 224, 240, 256}; anything
  * else restores the per-problem choice (256 or 128).  OZIMMU_B200_TILE_N=w does the same from the environment. */
@@ -200,6 +230,12 @@ int ozk_mantissa_loss(unsigned long long *counters16, uint32_t *scratch, size_t 
 int ozk_mantissa_loss_strided(unsigned long long *counters16, uint32_t *scratch, size_t rows, size_t len,
                               const double *in, size_t ld, int col_major, unsigned bits_per_int8,
                               unsigned elem_stride, void *stream);
+
+/* ozk_mantissa_loss_strided for `batch` operands of the same shape in one launch: counters16 is [batch][16], entry e
+ * reads in + e*in_stride (doubles) and uses scratch + e*scr_stride.  batch <= 65535. */
+int ozk_mantissa_loss_batched(unsigned long long *counters16, uint32_t *scratch, size_t scr_stride, size_t rows,
+                              size_t len, const double *in, size_t ld, size_t in_stride, int col_major,
+                              unsigned bits_per_int8, unsigned elem_stride, size_t batch, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * 2. Host API (C spelling of reference include/ozimmu/ozimmu.hpp)
@@ -234,6 +270,19 @@ int ozimmu_gemm_strided_batched(ozimmu_handle_t handle, int op_a, int op_b, size
                                 const double *alpha, const double *a, size_t lda, long long stride_a,
                                 const double *b, size_t ldb, long long stride_b, const double *beta, double *c,
                                 size_t ldc, long long stride_c, size_t batch, int compute_mode);
+
+/* The same for real or complex data (element_kind; alpha / beta as for ozimmu_gemm; strides in complex elements for
+ * complex data -- what cublasZgemmStridedBatched computes, reference src/cublas.cu:494-512).  A complex batch is one
+ * grouped launch as well: every tile runs its four plane products back to back. */
+int ozimmu_gemm_strided_batched_ex(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                                   const void *alpha, const void *a, size_t lda, long long stride_a, const void *b,
+                                   size_t ldb, long long stride_b, const void *beta, void *c, size_t ldc,
+                                   long long stride_c, size_t batch, int compute_mode, int element_kind);
+
+/* on_device != 0: alpha / beta of the following ozimmu_gemm / ozimmu_gemm_strided_batched* calls are DEVICE pointers
+ * (cuBLAS device pointer mode).  The fp64_int8_S modes read them on the device in stream order; the other modes
+ * fetch them with one blocking read.  The reference dereferences them on the host regardless (src/gemm.cu:405). */
+int ozimmu_set_scalar_pointer_mode(ozimmu_handle_t handle, int on_device);
 
 /* ozimmu_gemm (real) when B becomes valid column panel by column panel -- the multi-GPU path broadcasts B that
  * way -- so that split(A) and the products of the panels that have landed overlap the rest of the

@@ -202,11 +202,14 @@ int oz_gemm(int op_a, int op_b, size_t m, size_t n, size_t k, double alpha, cons
 
 /* src/gemm.cu:412-521 gemm_int8<cuDoubleComplex> with :160-186 axy_complex_kernel and :188-239
  * init_c_complex (FMA contraction as in the reference's sm_100 SASS: t = c.y*b.y; c.x = fma(c.x, b.x, -t);
- * t = c.x*b.y [the UPDATED c.x, the reference's aliasing bug]; c.y = fma(c.y, b.x, t)).
+ * t = c.x*b.y; c.y = fma(c.y, b.x, t)).  The reference reads the UPDATED c.x in the second product (an aliasing
+ * bug, SURVEY App. B.6: Im(beta*C) comes out wrong whenever Im(beta) != 0).  ref_beta_quirk != 0 reproduces that
+ * (used to pin this file against the reference's golden vectors); 0 is the corrected arithmetic the product ships
+ * (the two agree bit for bit when Im(beta) == 0).
  * a, b, c: interleaved (re, im) doubles; lda/ldb/ldc in complex elements; alpha/beta: {re, im}. */
-int oz_gemm_complex(int op_a, int op_b, size_t m, size_t n, size_t k, const double *alpha, const double *a,
-                    size_t lda, const double *b, size_t ldb, const double *beta, double *c, size_t ldc,
-                    unsigned num_split) {
+int oz_gemm_complex_q(int op_a, int op_b, size_t m, size_t n, size_t k, const double *alpha, const double *a,
+                      size_t lda, const double *b, size_t ldb, const double *beta, double *c, size_t ldc,
+                      unsigned num_split, int ref_beta_quirk) {
   const unsigned L = oz_bits_per_int8((uint32_t)k);
   const uint32_t k4 = oz_slice_ld((uint32_t)k);
   const size_t a_plane = (size_t)num_split * m * k4, b_plane = (size_t)num_split * n * k4;
@@ -230,8 +233,9 @@ int oz_gemm_complex(int op_a, int op_b, size_t m, size_t n, size_t k, const doub
         y[0] = 0; y[1] = 0;
       } else {
         const double t = y[1] * beta[1];
+        const double x_old = y[0];
         y[0] = fma(y[0], beta[0], -t);
-        const double t2 = y[0] * beta[1];
+        const double t2 = (ref_beta_quirk ? y[0] : x_old) * beta[1];
         y[1] = fma(y[1], beta[0], t2);
       }
     }
@@ -261,6 +265,13 @@ int oz_gemm_complex(int op_a, int op_b, size_t m, size_t n, size_t k, const doub
   }
   free(as); free(bs); free(amax); free(bmax); free(acc); free(ci);
   return 0;
+}
+
+/* the reference as compiled (beta quirk included) */
+int oz_gemm_complex(int op_a, int op_b, size_t m, size_t n, size_t k, const double *alpha, const double *a,
+                    size_t lda, const double *b, size_t ldb, const double *beta, double *c, size_t ldc,
+                    unsigned num_split) {
+  return oz_gemm_complex_q(op_a, op_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, num_split, 1);
 }
 
 /* src/split.cu:317-380 mantissa-loss totals, INTENDED semantics:

@@ -10,4 +10,4 @@ from .sharded import column_panels, row_block, sharded_gemm  # noqa: F401
 from .api import (auto_mode_select, compute_mode_t, create, destroy, element_kind_t, fp64_int8, gemm, gemm_host,  # noqa: F401
                   gemm_strided_batched, gemm_streamed_b,
                   get_bits_per_int8, get_compute_mode_name_str, handle_t, launch_count, malloc_mode_t, num_split_of,
-                  operation_t, reallocate_working_memory, set_cuda_stream)
+                  operation_t, reallocate_working_memory, set_cuda_stream, set_scalar_pointer_mode)

@@ -53,9 +53,17 @@ PROTOTYPES = {
                                              c_uint, c_void_p]),
     "ozk_mantissa_loss_strided": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int, c_uint,
                                           c_uint, c_void_p]),
-    "ozk_gemm_i8_fused_complex": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p,
-                                          c_void_p, c_uint, c_uint, c_double, c_double, c_int, c_double, c_double,
-                                          c_void_p, c_size_t, c_void_p]),
+    "ozk_gemm_i8_fused_ex": (c_int, [c_void_p, c_void_p]),
+    "ozk_scale_c_ex": (c_int, [c_size_t, c_size_t, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "ozk_split_int8_batched_strided": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t,
+                                               c_size_t, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_uint, c_uint,
+                                               c_uint, c_size_t, c_void_p]),
+    "ozk_mantissa_loss_batched": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_size_t, c_size_t,
+                                          c_int, c_uint, c_uint, c_size_t, c_void_p]),
+    "ozimmu_gemm_strided_batched_ex": (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p,
+                                               c_size_t, C.c_longlong, c_void_p, c_size_t, C.c_longlong, c_void_p,
+                                               c_void_p, c_size_t, C.c_longlong, c_size_t, c_int, c_int]),
+    "ozimmu_set_scalar_pointer_mode": (c_int, [c_void_p, c_int]),
     "ozk_gemm_i8_fused": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
                                   c_uint, c_uint, c_double, c_double, c_void_p, c_size_t, c_void_p]),
     "ozk_scale_c": (c_int, [c_size_t, c_size_t, c_double, c_void_p, c_size_t, c_void_p]),

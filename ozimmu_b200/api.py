@@ -166,26 +166,43 @@ def gemm(handle: handle_t, op_A: operation_t, op_B: operation_t, m: int, n: int,
          b_ptr, ldb: int, beta: float, c_ptr, ldc: int, compute_mode: compute_mode_t,
          element_kind: element_kind_t = element_kind_t.real) -> int:  # :76-83
     """C = alpha * op(A) * op(B) + beta * C on the handle's stream (asynchronous)."""
-    if element_kind == element_kind_t.real:
-        al, be = C.c_double(alpha), C.c_double(beta)
-    else:
-        al, be = (C.c_double * 2)(alpha.real, alpha.imag), (C.c_double * 2)(beta.real, beta.imag)
-    rc = _lib.lib().ozimmu_gemm(handle.raw, int(op_A), int(op_B), m, n, k, C.addressof(al), _ptr(a_ptr), lda,
-                                _ptr(b_ptr), ldb, C.addressof(be), _ptr(c_ptr), ldc, int(compute_mode),
+    al, be, pal, pbe = _scalars(alpha, beta, element_kind)
+    rc = _lib.lib().ozimmu_gemm(handle.raw, int(op_A), int(op_B), m, n, k, pal, _ptr(a_ptr), lda,
+                                _ptr(b_ptr), ldb, pbe, _ptr(c_ptr), ldc, int(compute_mode),
                                 int(element_kind))
     return _check(rc, "gemm")
 
 
-def gemm_strided_batched(handle: handle_t, op_A: operation_t, op_B: operation_t, m: int, n: int, k: int, alpha: float,
-                         a_ptr, lda: int, stride_a: int, b_ptr, ldb: int, stride_b: int, beta: float, c_ptr, ldc: int,
-                         stride_c: int, batch_count: int, compute_mode: compute_mode_t) -> int:
-    """Strided batch of real DGEMMs (X_e = X + e*stride_x elements) through one grouped launch; what the
-    reference's cublasDgemmStridedBatched / cublasGemmStridedBatchedEx interposers loop over
-    (reference src/cublas.cu:315-492).  Asynchronous on the handle's stream."""
-    al, be = C.c_double(alpha), C.c_double(beta)
-    rc = _lib.lib().ozimmu_gemm_strided_batched(handle.raw, int(op_A), int(op_B), m, n, k, C.addressof(al), _ptr(a_ptr),
-                                                lda, stride_a, _ptr(b_ptr), ldb, stride_b, C.addressof(be),
-                                                _ptr(c_ptr), ldc, stride_c, batch_count, int(compute_mode))
+def _scalars(alpha, beta, element_kind):
+    """alpha / beta as the C-ABI takes them: host double (real) / double[2] (complex), or -- after
+    set_scalar_pointer_mode(handle, True) -- device tensors / addresses holding them"""
+    if hasattr(alpha, "data_ptr") or hasattr(beta, "data_ptr"):
+        return alpha, beta, _ptr(alpha), _ptr(beta)
+    if element_kind == element_kind_t.real:
+        al, be = C.c_double(alpha), C.c_double(beta)
+    else:
+        alpha, beta = complex(alpha), complex(beta)
+        al, be = (C.c_double * 2)(alpha.real, alpha.imag), (C.c_double * 2)(beta.real, beta.imag)
+    return al, be, C.addressof(al), C.addressof(be)
+
+
+def set_scalar_pointer_mode(handle: handle_t, on_device: bool) -> None:
+    """alpha / beta of the following gemm / gemm_strided_batched calls are device pointers (cuBLAS device pointer mode)"""
+    _lib.lib().ozimmu_set_scalar_pointer_mode(handle.raw, int(bool(on_device)))
+
+
+def gemm_strided_batched(handle: handle_t, op_A: operation_t, op_B: operation_t, m: int, n: int, k: int, alpha,
+                         a_ptr, lda: int, stride_a: int, b_ptr, ldb: int, stride_b: int, beta, c_ptr, ldc: int,
+                         stride_c: int, batch_count: int, compute_mode: compute_mode_t,
+                         element_kind: element_kind_t = element_kind_t.real) -> int:
+    """Strided batch of DGEMMs / ZGEMMs (X_e = X + e*stride_x elements) through one grouped launch; what the
+    reference's cublas{D,Z}gemmStridedBatched / cublasGemmStridedBatchedEx interposers loop over
+    (reference src/cublas.cu:315-512).  Asynchronous on the handle's stream."""
+    al, be, pal, pbe = _scalars(alpha, beta, element_kind)
+    rc = _lib.lib().ozimmu_gemm_strided_batched_ex(handle.raw, int(op_A), int(op_B), m, n, k, pal, _ptr(a_ptr),
+                                                   lda, stride_a, _ptr(b_ptr), ldb, stride_b, pbe,
+                                                   _ptr(c_ptr), ldc, stride_c, batch_count, int(compute_mode),
+                                                   int(element_kind))
     return _check(rc, "gemm_strided_batched")
 
 

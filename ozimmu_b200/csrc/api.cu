@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "host.hpp"
 #include "oz_common.cuh"
@@ -77,80 +78,47 @@ void mark_done(handle_t h, cudaStream_t s) {
   h->last_stream = s;
 }
 
-// reference src/gemm.cu:344-410 gemm_int8<double>
-void gemm_int8_real(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n,
-                    std::size_t k, double alpha, const double *a, std::size_t lda, const double *b,
-                    std::size_t ldb, double beta, double *c, std::size_t ldc, unsigned num_split) {
-  if (m == 0 || n == 0) return;
-  if (k == 0) {
-    OZ_KERNEL_CHECK(ozk_scale_c(m, n, beta, c, ldc, h->cuda_stream));
-    return;
-  }
-  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
-  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split);
-  reallocate_working_memory(h, w.total);
-  ensure_streams(h);
-  char *ws = static_cast<char *>(h->working_memory_ptr);
-  double *amax = reinterpret_cast<double *>(ws + w.off_amax);
-  double *bmax = reinterpret_cast<double *>(ws + w.off_bmax);
-  auto *scr_a = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_a);
-  auto *scr_b = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_b);
-  auto *a_sl = reinterpret_cast<std::int8_t *>(ws + w.off_a_slices);
-  auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
-  cudaStream_t s = h->cuda_stream;
-  wait_previous(h, s);
+// alpha / beta of one call: host values, or device pointers (cuBLAS device pointer mode; read by the kernels in
+// stream order, never on the host)
+struct Scalars {
+  double alpha[2] = {0, 0}, beta[2] = {0, 0};
+  const double *alpha_dev = nullptr, *beta_dev = nullptr;
+};
 
-  // "rows" of the split are rows of op(A) and columns of op(B) (reference src/split.cu:266-283):
-  //   op_n A (m x k, col-major)  -> row r strided by lda  -> col_major
-  //   op_n B (k x n, col-major)  -> column j contiguous   -> !col_major
-  const int a_col_major = (op_a == op_n), b_col_major = (op_b != op_n);
-  const bool overlap = !h->profiler.enabled;
-  if (overlap) {
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
-    OZ_KERNEL_CHECK(ozk_split_int8(a_sl, w.pitch, amax, scr_a, m, k, a, lda, a_col_major, num_split, bits, s));
-    OZ_KERNEL_CHECK(ozk_split_int8(b_sl, w.pitch, bmax, scr_b, n, k, b, ldb, b_col_major, num_split, bits,
-                                   h->aux_stream));
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, h->aux_stream));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
-  } else {
-    h->profiler.start("split_A", s);
-    OZ_KERNEL_CHECK(ozk_split_int8(a_sl, w.pitch, amax, scr_a, m, k, a, lda, a_col_major, num_split, bits, s));
-    h->profiler.stop("split_A", s);
-    h->profiler.start("split_B", s);
-    OZ_KERNEL_CHECK(ozk_split_int8(b_sl, w.pitch, bmax, scr_b, n, k, b, ldb, b_col_major, num_split, bits, s));
-    h->profiler.stop("split_B", s);
-  }
-  h->profiler.start("int8tc_accumulate_fused", s);
-  OZ_KERNEL_CHECK(ozk_gemm_i8_fused(m, n, k, a_sl, b_sl, w.pitch, amax, bmax, num_split, bits, alpha, beta, c,
-                                    ldc, s));
-  h->profiler.stop("int8tc_accumulate_fused", s);
-  mark_done(h, s);
-}
-
-// Strided batch of real fp64_int8 products: the reference's interposers run one gemm_int8<double> per entry
-// (src/cublas.cu:380-406); here the entries are split on two streams and multiplied by ONE grouped launch
-// whose tile queue spans all entries, so that small entries fill the GPU together.  Entries are processed in
-// chunks that keep the workspace below OZIMMU_B200_BATCH_WORKSPACE_MB (default 8192).
-void gemm_int8_real_batched(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n,
-                            std::size_t k, double alpha, const double *a, std::size_t lda, long long stride_a,
-                            const double *b, std::size_t ldb, long long stride_b, double beta, double *c,
-                            std::size_t ldc, long long stride_c, std::size_t batch, unsigned num_split) {
+// The Ozaki path of every fp64_int8_S GEMM -- real (reference src/gemm.cu:344-410 gemm_int8<double>) or complex
+// (:412-521 gemm_int8<cuDoubleComplex>: the real and imaginary planes of each operand are split independently and four
+// real plane products are folded into C), a single product or a strided batch (the reference's interposers run one
+// GEMM per entry, src/cublas.cu:380-406):
+//   * split: ONE launch per operand plane for the whole chunk of entries, A on the caller's stream, B on the aux stream
+//     (an operand shared by all entries, stride 0, is split once);
+//   * products: ONE grouped launch whose tile queue spans all entries; a complex tile runs its four plane products
+//     back to back, so a complex GEMM is one launch as well (the reference: 4 x (P(s) cuBLAS GEMMs + P(s) + 1 kernels)).
+// Entries are processed in chunks that keep the workspace below OZIMMU_B200_BATCH_WORKSPACE_MB (default 8192).
+// Strides count elements (complex elements for complex data).
+void gemm_int8(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n, std::size_t k,
+               const Scalars &sc, const double *a, std::size_t lda, long long stride_a, const double *b, std::size_t ldb,
+               long long stride_b, double *c, std::size_t ldc, long long stride_c, std::size_t batch, unsigned num_split,
+               element_kind_t kind) {
   if (m == 0 || n == 0 || batch == 0) return;
+  const unsigned es = kind == real ? 1u : 2u;   // doubles per element = planes per operand
+  cudaStream_t s = h->cuda_stream;
   if (k == 0) {
     for (std::size_t e = 0; e < batch; e++)
-      OZ_KERNEL_CHECK(ozk_scale_c(m, n, beta, c + static_cast<long long>(e) * stride_c, ldc, h->cuda_stream));
+      OZ_KERNEL_CHECK(ozk_scale_c_ex(m, n, sc.beta, sc.beta_dev, es == 2, c + static_cast<long long>(e) * stride_c * es,
+                                     ldc, s));
     return;
   }
   const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
-  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split);
+  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split, es);
   const std::size_t limit = std::stoull(H::env_or("OZIMMU_B200_BATCH_WORKSPACE_MB", "8192")) << 20;
   const std::size_t chunk = std::max<std::size_t>(1, std::min<std::size_t>({batch, limit / w.total, 65535}));
   reallocate_working_memory(h, w.total * chunk);
   ensure_streams(h);
   char *ws = static_cast<char *>(h->working_memory_ptr);
-  cudaStream_t s = h->cuda_stream;
   wait_previous(h, s);
+  // "rows" of the split are rows of op(A) and columns of op(B) (reference src/split.cu:266-283):
+  //   op_n A (m x k, col-major)  -> row r strided by lda  -> col_major
+  //   op_n B (k x n, col-major)  -> column j contiguous   -> !col_major
   const int a_col_major = (op_a == op_n), b_col_major = (op_b != op_n);
   const bool overlap = !h->profiler.enabled;
   cudaStream_t sb = overlap ? h->aux_stream : s;
@@ -160,103 +128,90 @@ void gemm_int8_real_batched(handle_t h, operation_t op_a, operation_t op_b, std:
       OZ_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));   // also: the previous chunk's products are done with the slices
       OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, h->ev_fork, 0));
     }
-    // one split launch per operand for the whole chunk (entry e's workspace is ws + e * w.total)
+    // one split launch per operand plane for the whole chunk (entry e's workspace is ws + e * w.total)
     auto split_chunk = [&](const double *x, long long stride, std::size_t ld, std::size_t rows, int col_major,
-                           std::size_t off_slices, std::size_t off_max, std::size_t off_scr, cudaStream_t st) {
-      if (stride >= 0) {
-        // stride 0: one operand shared by every entry -- split once, the grouped launch reads it with stride 0
-        const std::size_t count = stride == 0 ? 1 : ne;
-        OZ_KERNEL_CHECK(ozk_split_int8_batched(reinterpret_cast<std::int8_t *>(ws + off_slices), w.total, w.pitch,
-                                               reinterpret_cast<double *>(ws + off_max), w.total / sizeof(double),
-                                               reinterpret_cast<std::uint32_t *>(ws + off_scr),
-                                               w.total / sizeof(std::uint32_t), rows, k, x + static_cast<long long>(e0) * stride,
-                                               ld, static_cast<std::size_t>(stride), col_major, num_split, bits, count, st));
-        return;
-      }
-      for (std::size_t e = 0; e < ne; e++) {   // backward-strided input: entry by entry
-        char *we = ws + e * w.total;
-        OZ_KERNEL_CHECK(ozk_split_int8(reinterpret_cast<std::int8_t *>(we + off_slices), w.pitch,
-                                       reinterpret_cast<double *>(we + off_max),
-                                       reinterpret_cast<std::uint32_t *>(we + off_scr), rows, k,
-                                       x + static_cast<long long>(e0 + e) * stride, ld, col_major, num_split, bits, st));
+                           std::size_t off_slices, std::size_t plane_bytes, std::size_t off_max, std::size_t off_scr,
+                           cudaStream_t st) {
+      for (unsigned part = 0; part < es; part++) {
+        auto *out = reinterpret_cast<std::int8_t *>(ws + off_slices + part * plane_bytes);
+        auto *mx = reinterpret_cast<double *>(ws + off_max) + part * rows;
+        auto *scr = reinterpret_cast<std::uint32_t *>(ws + off_scr) + part * rows;
+        if (stride >= 0) {
+          // stride 0: one operand shared by every entry -- split once, the grouped launch reads it with stride 0
+          const std::size_t count = stride == 0 ? 1 : ne;
+          OZ_KERNEL_CHECK(ozk_split_int8_batched_strided(
+              out, w.total, w.pitch, mx, w.total / sizeof(double), scr, w.total / sizeof(std::uint32_t), rows, k,
+              x + static_cast<long long>(e0) * stride * es + part, ld, static_cast<std::size_t>(stride) * es, col_major,
+              num_split, bits, es, count, st));
+          continue;
+        }
+        for (std::size_t e = 0; e < ne; e++)   // backward-strided input: entry by entry
+          OZ_KERNEL_CHECK(ozk_split_int8_strided(out + e * w.total, w.pitch, mx + e * (w.total / sizeof(double)),
+                                                 scr + e * (w.total / sizeof(std::uint32_t)), rows, k,
+                                                 x + static_cast<long long>(e0 + e) * stride * es + part, ld, col_major,
+                                                 num_split, bits, es, st));
       }
     };
     h->profiler.start("split_A", s);
-    split_chunk(a, stride_a, lda, m, a_col_major, w.off_a_slices, w.off_amax, w.off_scr_a, s);
+    split_chunk(a, stride_a, lda, m, a_col_major, w.off_a_slices, w.a_plane, w.off_amax, w.off_scr_a, s);
     h->profiler.stop("split_A", s);
     h->profiler.start("split_B", sb);
-    split_chunk(b, stride_b, ldb, n, b_col_major, w.off_b_slices, w.off_bmax, w.off_scr_b, sb);
+    split_chunk(b, stride_b, ldb, n, b_col_major, w.off_b_slices, w.b_plane, w.off_bmax, w.off_scr_b, sb);
     h->profiler.stop("split_B", sb);
     if (overlap) {
       OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, sb));
       OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
     }
+    ozk_fused_args_t fa{};
+    fa.m = m, fa.n = n, fa.k = k, fa.pitch = w.pitch;
+    fa.a_slices = reinterpret_cast<const std::int8_t *>(ws + w.off_a_slices);
+    fa.b_slices = reinterpret_cast<const std::int8_t *>(ws + w.off_b_slices);
+    fa.amax = reinterpret_cast<const double *>(ws + w.off_amax);
+    fa.bmax = reinterpret_cast<const double *>(ws + w.off_bmax);
+    fa.num_split = num_split, fa.bits_per_int8 = bits;
+    fa.complex_c = es == 2;
+    fa.a_plane_bytes = w.a_plane, fa.b_plane_bytes = w.b_plane, fa.amax_plane = m, fa.bmax_plane = n;
+    fa.alpha[0] = sc.alpha[0], fa.alpha[1] = sc.alpha[1], fa.beta[0] = sc.beta[0], fa.beta[1] = sc.beta[1];
+    fa.alpha_dev = sc.alpha_dev, fa.beta_dev = sc.beta_dev;
+    fa.c = c + static_cast<long long>(e0) * stride_c * es;
+    fa.ldc = ldc;
+    fa.batch = ne;
+    fa.a_batch_bytes = stride_a == 0 ? 0 : w.total, fa.b_batch_bytes = stride_b == 0 ? 0 : w.total;
+    fa.amax_batch = stride_a == 0 ? 0 : w.total / sizeof(double), fa.bmax_batch = stride_b == 0 ? 0 : w.total / sizeof(double);
+    fa.c_batch = static_cast<std::size_t>(stride_c);
     h->profiler.start("int8tc_accumulate_fused", s);
-    OZ_KERNEL_CHECK(ozk_gemm_i8_fused_batched(
-        m, n, k, ne, reinterpret_cast<const std::int8_t *>(ws + w.off_a_slices), stride_a == 0 ? 0 : w.total,
-        reinterpret_cast<const std::int8_t *>(ws + w.off_b_slices), stride_b == 0 ? 0 : w.total, w.pitch,
-        reinterpret_cast<const double *>(ws + w.off_amax), stride_a == 0 ? 0 : w.total / sizeof(double),
-        reinterpret_cast<const double *>(ws + w.off_bmax), stride_b == 0 ? 0 : w.total / sizeof(double), num_split, bits,
-        alpha, beta,
-        c + static_cast<long long>(e0) * stride_c, ldc, static_cast<std::size_t>(stride_c), s));
+    OZ_KERNEL_CHECK(ozk_gemm_i8_fused_ex(&fa, s));
     h->profiler.stop("int8tc_accumulate_fused", s);
   }
   mark_done(h, s);
 }
 
-// reference src/gemm.cu:412-521 gemm_int8<cuDoubleComplex>: real and imaginary planes are split
-// independently, then four real fp64_int8 products are added into C in the order
-// (im,im) -> -alpha, (re,re) -> +alpha, (im,re) and (re,im) -> i*alpha, after C = beta*C.
-void gemm_int8_complex(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n, std::size_t k,
-                       const double *alpha, const double *a, std::size_t lda, const double *b, std::size_t ldb,
-                       const double *beta, double *c, std::size_t ldc, unsigned num_split) {
-  if (m == 0 || n == 0) return;
-  if (k == 0) throw std::runtime_error("ozIMMU: complex GEMM with k == 0 is not implemented");
-  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
-  const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split, 2);  // two planes per operand
-  reallocate_working_memory(h, w.total);
-  ensure_streams(h);
-  char *ws = static_cast<char *>(h->working_memory_ptr);
-  double *amax = reinterpret_cast<double *>(ws + w.off_amax);   // [re m][im m]
-  double *bmax = reinterpret_cast<double *>(ws + w.off_bmax);   // [re n][im n]
-  auto *scr_a = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_a);
-  auto *scr_b = reinterpret_cast<std::uint32_t *>(ws + w.off_scr_b);
-  auto *a_sl = reinterpret_cast<std::int8_t *>(ws + w.off_a_slices);
-  auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
-  const std::size_t a_plane = w.a_plane, b_plane = w.b_plane;
-  cudaStream_t s = h->cuda_stream;
-  wait_previous(h, s);
-  const int a_col_major = (op_a == op_n), b_col_major = (op_b != op_n);
-  const bool overlap = !h->profiler.enabled;
-  cudaStream_t sb = overlap ? h->aux_stream : s;
-  if (overlap) {
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, h->ev_fork, 0));
+// host copies of device-resident scalars (a blocking read; only the paths that need the values on the host -- auto
+// mode, dgemm / sgemm through the private cuBLAS handle -- use it)
+Scalars fetch_scalars(handle_t h, const Scalars &sc, element_kind_t kind) {
+  if (sc.alpha_dev == nullptr) return sc;
+  Scalars out;
+  const std::size_t bytes = sizeof(double) * (kind == real ? 1 : 2);
+  OZ_CUDA_CHECK(cudaMemcpyAsync(out.alpha, sc.alpha_dev, bytes, cudaMemcpyDeviceToHost, h->cuda_stream));
+  OZ_CUDA_CHECK(cudaMemcpyAsync(out.beta, sc.beta_dev, bytes, cudaMemcpyDeviceToHost, h->cuda_stream));
+  OZ_CUDA_CHECK(cudaStreamSynchronize(h->cuda_stream));
+  return out;
+}
+
+Scalars read_scalars(handle_t h, const void *alpha, const void *beta, element_kind_t kind) {
+  Scalars sc;
+  if (h->scalars_on_device) {
+    sc.alpha_dev = static_cast<const double *>(alpha);
+    sc.beta_dev = static_cast<const double *>(beta);
+    return sc;
   }
-  h->profiler.start("split_A", s);
-  for (int part = 0; part < 2; part++)
-    OZ_KERNEL_CHECK(ozk_split_int8_strided(a_sl + part * a_plane, w.pitch, amax + part * m, scr_a + part * m, m, k,
-                                           a + part, lda, a_col_major, num_split, bits, 2, s));
-  h->profiler.stop("split_A", s);
-  h->profiler.start("split_B", sb);
-  for (int part = 0; part < 2; part++)
-    OZ_KERNEL_CHECK(ozk_split_int8_strided(b_sl + part * b_plane, w.pitch, bmax + part * n, scr_b + part * n, n, k,
-                                           b + part, ldb, b_col_major, num_split, bits, 2, sb));
-  h->profiler.stop("split_B", sb);
-  if (overlap) {
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, sb));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
+  sc.alpha[0] = static_cast<const double *>(alpha)[0];
+  sc.beta[0] = static_cast<const double *>(beta)[0];
+  if (kind != real) {
+    sc.alpha[1] = static_cast<const double *>(alpha)[1];
+    sc.beta[1] = static_cast<const double *>(beta)[1];
   }
-  // (A plane, B plane, coefficient): reference src/gemm.cu:479-518
-  const struct { int pa, pb; double re, im; } groups[4] = {
-      {1, 1, -alpha[0], -alpha[1]}, {0, 0, alpha[0], alpha[1]}, {1, 0, -alpha[1], alpha[0]}, {0, 1, -alpha[1], alpha[0]}};
-  h->profiler.start("int8tc_accumulate_fused", s);
-  for (int g = 0; g < 4; g++)
-    OZ_KERNEL_CHECK(ozk_gemm_i8_fused_complex(m, n, k, a_sl + groups[g].pa * a_plane, b_sl + groups[g].pb * b_plane,
-                                              w.pitch, amax + groups[g].pa * m, bmax + groups[g].pb * n, num_split, bits,
-                                              groups[g].re, groups[g].im, g == 0, beta[0], beta[1], c, ldc, s));
-  h->profiler.stop("int8tc_accumulate_fused", s);
-  mark_done(h, s);
+  return sc;
 }
 
 template <class F>
@@ -414,6 +369,65 @@ std::size_t mtk::ozimmu::get_data_size_in_byte(const data_t d) {
 
 std::uint32_t mtk::ozimmu::get_bits_per_int8(const std::uint32_t k) { return ozk_bits_per_int8(k); }
 
+// reference src/split.cu:383-445 get_mantissa_loss_total, for `batch` problems of the same shape at once: ONE counter
+// pass per operand plane over all entries (the reference's strided-batched interposers run auto mode entry by entry
+// with a blocking read each, src/cublas.cu:380-406), then one blocking read.  out: [batch][16].
+namespace {
+void mantissa_loss_totals(handle_t h, operation_t op_A, operation_t op_B, std::size_t m, std::size_t n, std::size_t k,
+                          const double *a, std::size_t lda, long long stride_a, const double *b, std::size_t ldb,
+                          long long stride_b, std::size_t batch, element_kind_t kind,
+                          std::vector<unsigned long long> &out) {
+  constexpr int N = handle::mantissa_loss_counter_length;
+  out.assign(batch * N, 0);
+  if (m == 0 || n == 0 || k == 0 || batch == 0) return;
+  const unsigned es = kind == real ? 1u : 2u;  // complex: both planes, each against its own row scale
+  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
+  ensure_streams(h);
+  cudaStream_t s = h->cuda_stream;
+  std::vector<unsigned long long> part(N);
+  for (std::size_t e0 = 0; e0 < batch;) {
+    // workspace of a chunk: [counters ne x 16 u64][row-max scratch ne x max(m, n) u32]
+    const std::size_t ne = std::min<std::size_t>(batch - e0, 4096);
+    const std::size_t scr_rows = std::max(m, n);
+    const std::size_t cnt_bytes = sizeof(unsigned long long) * N * ne;
+    reallocate_working_memory(h, cnt_bytes + sizeof(std::uint32_t) * scr_rows * ne);
+    wait_previous(h, s);
+    auto *cnt = static_cast<unsigned long long *>(h->working_memory_ptr);
+    auto *scr = reinterpret_cast<std::uint32_t *>(static_cast<char *>(h->working_memory_ptr) + cnt_bytes);
+    OZ_CUDA_CHECK(cudaMemsetAsync(cnt, 0, cnt_bytes, s));
+    // a negative stride walks backwards: entry by entry (the batched launch takes unsigned strides)
+    auto pass = [&](const double *x, long long stride, std::size_t ld, std::size_t rows, int col_major) {
+      for (unsigned p = 0; p < es; p++) {
+        if (stride >= 0) {
+          OZ_KERNEL_CHECK(ozk_mantissa_loss_batched(cnt, scr, scr_rows, rows, k, x + static_cast<long long>(e0) * stride * es + p,
+                                                    ld, static_cast<std::size_t>(stride) * es, col_major, bits, es, ne, s));
+        } else {
+          for (std::size_t e = 0; e < ne; e++)
+            OZ_KERNEL_CHECK(ozk_mantissa_loss_strided(cnt + e * N, scr, rows, k,
+                                                      x + static_cast<long long>(e0 + e) * stride * es + p, ld, col_major,
+                                                      bits, es, s));
+        }
+      }
+    };
+    pass(a, stride_a, lda, m, op_A == op_n);
+    pass(b, stride_b, ldb, n, op_B != op_n);
+    OZ_CUDA_CHECK(cudaMemcpyAsync(out.data() + e0 * N, cnt, cnt_bytes, cudaMemcpyDeviceToHost, s));
+    mark_done(h, s);
+    OZ_CUDA_CHECK(cudaStreamSynchronize(s));
+    e0 += ne;
+  }
+}
+
+// reference src/split.cu:484-493: first split count whose average loss is within the threshold, else dgemm
+compute_mode_t mode_for_loss(const unsigned long long *counters, std::size_t m, std::size_t n, std::size_t k,
+                             double threshold) {
+  const double denom = static_cast<double>(m * k + k * n);
+  for (int i = 0; i < handle::mantissa_loss_counter_length; i++)
+    if (static_cast<double>(counters[i]) / denom <= threshold) return H::mode_of_num_split(static_cast<unsigned>(i) + 3u);
+  return dgemm;
+}
+}  // namespace
+
 // reference src/split.cu:454-518
 compute_mode_t mtk::ozimmu::auto_mode_select(handle_t h, const operation_t op_A, const operation_t op_B,
                                              const std::size_t m, const std::size_t n, const std::size_t k,
@@ -421,35 +435,14 @@ compute_mode_t mtk::ozimmu::auto_mode_select(handle_t h, const operation_t op_A,
                                              const void *const b_ptr, const std::size_t ldb,
                                              const element_kind_t element_kind,
                                              const double mantissa_loss_threshold) {
-  const unsigned es = element_kind == real ? 1u : 2u;  // complex: both planes, each against its own row scale
   constexpr int N = handle::mantissa_loss_counter_length;
   for (int i = 0; i < N; i++) h->last_loss_counters[i] = 0;
   if (m == 0 || n == 0 || k == 0) return fp64_int8_3;
-  const unsigned bits = ozk_bits_per_int8(static_cast<std::uint32_t>(k));
-  const std::size_t scr_bytes = sizeof(std::uint32_t) * std::max(m, n);
-  reallocate_working_memory(h, scr_bytes);
-  ensure_streams(h);
-  cudaStream_t s = h->cuda_stream;
-  wait_previous(h, s);
-  auto *scr = static_cast<std::uint32_t *>(h->working_memory_ptr);
-  OZ_CUDA_CHECK(cudaMemsetAsync(h->d_mantissa_loss_counter_ptr, 0, sizeof(unsigned long long) * N, s));
-  for (unsigned part = 0; part < es; part++) {
-    OZ_KERNEL_CHECK(ozk_mantissa_loss_strided(h->d_mantissa_loss_counter_ptr, scr, m, k,
-                                              static_cast<const double *>(a_ptr) + part, lda, op_A == op_n, bits, es, s));
-    OZ_KERNEL_CHECK(ozk_mantissa_loss_strided(h->d_mantissa_loss_counter_ptr, scr, n, k,
-                                              static_cast<const double *>(b_ptr) + part, ldb, op_B != op_n, bits, es, s));
-  }
-  OZ_CUDA_CHECK(cudaMemcpyAsync(h->h_mantissa_loss_counter_ptr, h->d_mantissa_loss_counter_ptr,
-                                sizeof(unsigned long long) * N, cudaMemcpyDeviceToHost, s));
-  mark_done(h, s);
-  OZ_CUDA_CHECK(cudaStreamSynchronize(s));
-  for (int i = 0; i < N; i++) h->last_loss_counters[i] = h->h_mantissa_loss_counter_ptr[i];
-  // reference src/split.cu:484-493: first split count whose average loss is within the threshold
-  const double denom = static_cast<double>(m * k + k * n);
-  for (int i = 0; i < N; i++)
-    if (static_cast<double>(h->last_loss_counters[i]) / denom <= mantissa_loss_threshold)
-      return H::mode_of_num_split(static_cast<unsigned>(i) + 3u);
-  return dgemm;
+  std::vector<unsigned long long> totals;
+  mantissa_loss_totals(h, op_A, op_B, m, n, k, static_cast<const double *>(a_ptr), lda, 0,
+                       static_cast<const double *>(b_ptr), ldb, 0, 1, element_kind, totals);
+  for (int i = 0; i < N; i++) h->last_loss_counters[i] = totals[i];
+  return mode_for_loss(h->last_loss_counters, m, n, k, mantissa_loss_threshold);
 }
 
 int mtk::ozimmu::gemm(handle_t h, const operation_t op_A, const operation_t op_B, const std::size_t m,
@@ -467,17 +460,26 @@ int mtk::ozimmu::gemm(handle_t h, const operation_t op_A, const operation_t op_B
   arg_error |= check_alignment(c_ptr, esz, "C");
   if (arg_error) return 1;
 
+  const Scalars sc = read_scalars(h, alpha, beta, element_kind);
   if (H::is_int8_mode(compute_mode)) {
-    if (element_kind != real) {
-      gemm_int8_complex(h, op_A, op_B, m, n, k, static_cast<const double *>(alpha), static_cast<const double *>(a_ptr),
-                        lda, static_cast<const double *>(b_ptr), ldb, static_cast<const double *>(beta),
-                        static_cast<double *>(c_ptr), ldc, H::num_split_of(compute_mode));
-      return 0;
-    }
-    gemm_int8_real(h, op_A, op_B, m, n, k, *static_cast<const double *>(alpha), static_cast<const double *>(a_ptr),
-                   lda, static_cast<const double *>(b_ptr), ldb, *static_cast<const double *>(beta),
-                   static_cast<double *>(c_ptr), ldc, H::num_split_of(compute_mode));
+    gemm_int8(h, op_A, op_B, m, n, k, sc, static_cast<const double *>(a_ptr), lda, 0, static_cast<const double *>(b_ptr),
+              ldb, 0, static_cast<double *>(c_ptr), ldc, 0, 1, H::num_split_of(compute_mode), element_kind);
     return 0;
+  }
+  if (h->scalars_on_device) {
+    // every other mode needs the values on the host (auto mode reads its counters anyway; dgemm / sgemm go through the
+    // private cuBLAS handle, which is in host pointer mode): one blocking read, then the host-scalar path
+    const Scalars hs = fetch_scalars(h, sc, element_kind);
+    h->scalars_on_device = false;
+    int rc = 0;
+    try {
+      rc = gemm(h, op_A, op_B, m, n, k, hs.alpha, a_ptr, lda, b_ptr, ldb, hs.beta, c_ptr, ldc, compute_mode, element_kind);
+    } catch (...) {
+      h->scalars_on_device = true;
+      throw;
+    }
+    h->scalars_on_device = true;
+    return rc;
   }
   if (compute_mode == fp64_int8_auto) {
     const compute_mode_t chosen = auto_mode_select(h, op_A, op_B, m, n, k, a_ptr, lda, b_ptr, ldb, element_kind,
@@ -664,20 +666,22 @@ int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const opera
 }
 
 // Not in the reference's header: its strided-batched interposers loop over gemm() (src/cublas.cu:380-406).
+// Strides count elements (complex elements for element_kind == complx).
 int mtk::ozimmu::gemm_strided_batched(handle_t h, const operation_t op_A, const operation_t op_B, const std::size_t m,
-                                      const std::size_t n, const std::size_t k, const double *alpha,
-                                      const double *const a_ptr, const std::size_t lda, const long long stride_a,
-                                      const double *const b_ptr, const std::size_t ldb, const long long stride_b,
-                                      const double *beta, double *const c_ptr, const std::size_t ldc,
+                                      const std::size_t n, const std::size_t k, const void *alpha,
+                                      const void *const a_ptr, const std::size_t lda, const long long stride_a,
+                                      const void *const b_ptr, const std::size_t ldb, const long long stride_b,
+                                      const void *beta, void *const c_ptr, const std::size_t ldc,
                                       const long long stride_c, const std::size_t batch_count,
-                                      const compute_mode_t compute_mode) {
+                                      const compute_mode_t compute_mode, const element_kind_t element_kind) {
+  const std::size_t es = element_kind == real ? 1 : 2, esz = es * sizeof(double);
   int arg_error = 0;
   arg_error |= check_shape(op_A, m, k, lda, "A");
   arg_error |= check_shape(op_B, k, n, ldb, "B");
   arg_error |= check_shape(op_n, m, n, ldc, "C");
-  arg_error |= check_alignment(a_ptr, sizeof(double), "A");
-  arg_error |= check_alignment(b_ptr, sizeof(double), "B");
-  arg_error |= check_alignment(c_ptr, sizeof(double), "C");
+  arg_error |= check_alignment(a_ptr, esz, "A");
+  arg_error |= check_alignment(b_ptr, esz, "B");
+  arg_error |= check_alignment(c_ptr, esz, "C");
   // entries of C must not overlap (they are written concurrently); stride 0 is fine for the inputs
   if (batch_count > 1 && m > 0 && n > 0 &&
       static_cast<unsigned long long>(stride_c < 0 ? -stride_c : stride_c) < ldc * (n - 1) + m) {
@@ -685,20 +689,62 @@ int mtk::ozimmu::gemm_strided_batched(handle_t h, const operation_t op_A, const 
     arg_error |= 1;
   }
   if (arg_error) return 1;
-  if (H::is_int8_mode(compute_mode) && stride_c >= 0) {
-    gemm_int8_real_batched(h, op_A, op_B, m, n, k, *alpha, a_ptr, lda, stride_a, b_ptr, ldb, stride_b, *beta, c_ptr,
-                           ldc, stride_c, batch_count, H::num_split_of(compute_mode));
+  const auto *a = static_cast<const double *>(a_ptr);
+  const auto *b = static_cast<const double *>(b_ptr);
+  auto *c = static_cast<double *>(c_ptr);
+  // entries [e0, e0 + ne) in one grouped launch (int8 modes, forward-strided C), else entry by entry
+  auto run = [&](std::size_t e0, std::size_t ne, compute_mode_t mode) -> int {
+    if (H::is_int8_mode(mode) && stride_c >= 0) {
+      gemm_int8(h, op_A, op_B, m, n, k, read_scalars(h, alpha, beta, element_kind),
+                a + static_cast<long long>(e0) * stride_a * es, lda, stride_a, b + static_cast<long long>(e0) * stride_b * es,
+                ldb, stride_b, c + static_cast<long long>(e0) * stride_c * es, ldc, stride_c, ne, H::num_split_of(mode),
+                element_kind);
+      return 0;
+    }
+    for (std::size_t e = e0; e < e0 + ne; e++) {
+      const int rc = gemm(h, op_A, op_B, m, n, k, alpha, a + static_cast<long long>(e) * stride_a * es, lda,
+                          b + static_cast<long long>(e) * stride_b * es, ldb, beta,
+                          c + static_cast<long long>(e) * stride_c * es, ldc, mode, element_kind);
+      if (rc) return rc;
+    }
     return 0;
-  }
-  // auto mode decides per entry (a blocking counter read each), dgemm goes to cuBLAS: entry by entry
-  for (std::size_t e = 0; e < batch_count; e++) {
-    const int rc = gemm(h, op_A, op_B, m, n, k, alpha, a_ptr + static_cast<long long>(e) * stride_a, lda,
-                        b_ptr + static_cast<long long>(e) * stride_b, ldb, beta,
-                        c_ptr + static_cast<long long>(e) * stride_c, ldc, compute_mode, real);
+  };
+  if (compute_mode != fp64_int8_auto || m == 0 || n == 0 || k == 0 || batch_count == 0)
+    return run(0, batch_count, compute_mode == fp64_int8_auto ? fp64_int8_3 : compute_mode);
+  // auto mode: the split count is chosen per entry (as the reference does by looping), but from ONE counter pass over
+  // the whole batch and one blocking read; runs of consecutive entries with the same choice share a grouped launch
+  std::vector<unsigned long long> totals;
+  mantissa_loss_totals(h, op_A, op_B, m, n, k, a, lda, stride_a, b, ldb, stride_b, batch_count, element_kind, totals);
+  constexpr int N = handle::mantissa_loss_counter_length;
+  for (int i = 0; i < N; i++) h->last_loss_counters[i] = totals[(batch_count - 1) * N + i];
+  std::vector<compute_mode_t> chosen(batch_count);
+  for (std::size_t e = 0; e < batch_count; e++)
+    chosen[e] = mode_for_loss(totals.data() + e * N, m, n, k, h->avg_mantissa_loss_threshold);
+  for (std::size_t e0 = 0; e0 < batch_count;) {
+    std::size_t e1 = e0 + 1;
+    while (e1 < batch_count && chosen[e1] == chosen[e0]) e1++;
+    H::log_info("AUTO selected mode = " + get_compute_mode_name_str(chosen[e0]) + " for batch entries " +
+                std::to_string(e0) + ".." + std::to_string(e1 - 1));
+    const int rc = run(e0, e1 - e0, chosen[e0]);
     if (rc) return rc;
+    e0 = e1;
   }
   return 0;
 }
+
+int mtk::ozimmu::gemm_strided_batched(handle_t h, const operation_t op_A, const operation_t op_B, const std::size_t m,
+                                      const std::size_t n, const std::size_t k, const double *alpha,
+                                      const double *const a_ptr, const std::size_t lda, const long long stride_a,
+                                      const double *const b_ptr, const std::size_t ldb, const long long stride_b,
+                                      const double *beta, double *const c_ptr, const std::size_t ldc,
+                                      const long long stride_c, const std::size_t batch_count,
+                                      const compute_mode_t compute_mode) {
+  return gemm_strided_batched(h, op_A, op_B, m, n, k, static_cast<const void *>(alpha), a_ptr, lda, stride_a, b_ptr, ldb,
+                              stride_b, static_cast<const void *>(beta), c_ptr, ldc, stride_c, batch_count, compute_mode,
+                              real);
+}
+
+void mtk::ozimmu::set_scalar_pointer_mode(handle_t handle, const bool on_device) { handle->scalars_on_device = on_device; }
 
 // ===============================================================================================
 // C spelling
@@ -787,6 +833,27 @@ int ozimmu_gemm_strided_batched(ozimmu_handle_t handle, int op_a, int op_b, size
                                 static_cast<operation_t>(op_b != 0), m, n, k, alpha, a, lda, stride_a, b, ldb, stride_b,
                                 beta, c, ldc, stride_c, batch, static_cast<compute_mode_t>(compute_mode));
   });
+}
+
+int ozimmu_gemm_strided_batched_ex(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,
+                                   const void *alpha, const void *a, size_t lda, long long stride_a, const void *b,
+                                   size_t ldb, long long stride_b, const void *beta, void *c, size_t ldc,
+                                   long long stride_c, size_t batch, int compute_mode, int element_kind) {
+  if (handle == nullptr || alpha == nullptr || beta == nullptr || compute_mode < 0 ||
+      compute_mode > OZIMMU_FP64_INT8_AUTO || (element_kind != OZIMMU_REAL && element_kind != OZIMMU_COMPLX))
+    return 1;
+  return guarded([&] {
+    return gemm_strided_batched(reinterpret_cast<handle_t>(handle), static_cast<operation_t>(op_a != 0),
+                                static_cast<operation_t>(op_b != 0), m, n, k, alpha, a, lda, stride_a, b, ldb, stride_b,
+                                beta, c, ldc, stride_c, batch, static_cast<compute_mode_t>(compute_mode),
+                                static_cast<element_kind_t>(element_kind));
+  });
+}
+
+int ozimmu_set_scalar_pointer_mode(ozimmu_handle_t handle, int on_device) {
+  if (handle == nullptr) return 1;
+  set_scalar_pointer_mode(reinterpret_cast<handle_t>(handle), on_device != 0);
+  return 0;
 }
 
 int ozimmu_gemm_streamed_b(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_t n, size_t k,

@@ -64,11 +64,18 @@ struct FusedParams {
   const double *amax;
   const double *bmax;
   int32_t *c_i32;
-  // complex accumulation (reference src/gemm.cu:160-239,479-518): C is cuDoubleComplex (ldc in complex
-  // elements) and this launch adds one of the four real products: y = fma(x, (alpha, alpha_im), y),
-  // after y = beta * y (the reference's init_c_complex, applied once, by the first of the four launches)
-  uint32_t cplx, cplx_init;
+  // complex GEMM (reference src/gemm.cu:412-521): C is cuDoubleComplex (ldc in complex elements), each operand is two
+  // planes of slices (real, imaginary) `*_plane_bytes` apart with row scales `*max_plane` apart, and every tile runs
+  // the FOUR real plane products back to back -- (im,im) -> -alpha, (re,re) -> +alpha, (im,re), (re,im) -> i*alpha,
+  // the reference's order (:479-518) -- each followed by y = fma(x, coef, y) on the tile of C (axy_complex, :160-186);
+  // the first one starts from y = beta*y (init_c_complex, :188-239).  (alpha, alpha_im), (beta, beta_im) = the scalars.
+  uint32_t cplx;
+  uint32_t groups;             // plane products per tile: 1 (real) or 4 (complex)
   double alpha_im, beta_im;
+  unsigned long long a_plane_bytes, b_plane_bytes, amax_plane, bmax_plane;
+  // cuBLAS device pointer mode: alpha / beta (1 double each, 2 for complex) are read from device memory in the
+  // finalize step, in stream order, instead of being passed by value
+  const double *alpha_dev, *beta_dev;
   // soft lockstep between CTA pairs
   uint32_t *sync_ctr;          // one arrival counter per kSyncEvery k-steps, zeroed before launch (or null)
   uint32_t sync_window;        // a pair starts sync interval j only after interval j - window is complete
@@ -187,6 +194,11 @@ struct PairIter {
   }
 };
 
+// Complex GEMM: plane (0 = real, 1 = imaginary) of A and of B that plane product g multiplies -- reference
+// src/gemm.cu:479-480: (im,im), (re,re), (im,re), (re,im); always plane 0 for a real GEMM.
+__device__ __forceinline__ uint32_t group_plane_a(const FusedParams &p, uint32_t g) { return p.cplx ? (0x5u >> g) & 1u : 0u; }
+__device__ __forceinline__ uint32_t group_plane_b(const FusedParams &p, uint32_t g) { return p.cplx ? (0x9u >> g) & 1u : 0u; }
+
 // tile index -> (tile row, tile column): bands of group_m tile rows, column-major inside a band, so the tiles
 // that run concurrently cover a compact block of C and share their A / B panels through L2
 __device__ __forceinline__ void tile_coords(const FusedParams &p, uint32_t t, uint32_t &tm, uint32_t &tn,
@@ -268,7 +280,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
   const uint32_t pair_id = (blockIdx.x >> 1) + (kQueue ? p.q_pair0 : 0u);
   const uint32_t num_pairs = gridDim.x >> 1;
   const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
-  const uint32_t steps_per_tile = (p.single_a != 0 ? 1u : p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
+  const uint32_t steps_per_tile = (p.single_a != 0 ? 1u : p.num_split * (p.num_split + 1) / 2) * p.k_blocks * p.groups;
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < kStagesP; s++) {
@@ -328,10 +340,12 @@ oz_gemm_pair_kernel(const FusedParams p) {
         const size_t b_tile = b_row0 >> 7;
         const size_t b_sub = static_cast<size_t>(b_row0 & 127u) * BK;
         const uint32_t stage_tx = BM * BK + (b_rows1 + b_rows2) * BK;
+        for (uint32_t grp = 0; grp < p.groups; grp++)
         for (PairIter it(p); it.valid(); it.next()) {
-          const int8_t *a_src = a_base + ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
-          const int8_t *b_src =
-              b_base + ((it.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
+          const int8_t *a_src = a_base + group_plane_a(p, grp) * p.a_plane_bytes +
+                                ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
+          const int8_t *b_src = b_base + group_plane_b(p, grp) * p.b_plane_bytes +
+                                ((it.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
           const int8_t *b_src2 = b_src - b_sub + static_cast<size_t>(p.k_blocks) * kTileBytes;  // next row tile
           for (uint32_t kb = 0; kb < p.k_blocks; kb++, g++) {
             if (lockstep && (g % kSyncEvery) == 0) {
@@ -379,6 +393,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
       uint32_t stage = 0, ph = 0, buf = 0, bph = 0;
       TileSeq<kQueue> seq;
       for (uint32_t t; seq.next(p, pair_id, num_pairs, num_tiles, false, t);) {
+        for (uint32_t grp = 0; grp < p.groups; grp++)
         for (PairIter it(p); it.valid(); it.next()) {
           ptx::mbar_wait_cluster(tempty_bar(buf), bph ^ 1u);
           ptx::tc_fence_after();
@@ -442,115 +457,135 @@ oz_gemm_pair_kernel(const FusedParams p) {
         row = tm * 2 * BM + rank * BM + q * 32u + lane;
         col0 = tn * BN_ + half * kCols;
       }
+      uint32_t done_idx = 0;
       double acc[kRegCols];
-#pragma unroll
-      for (uint32_t j = 0; j < kRegCols; j++) acc[j] = 0.0;
       // this thread's spill accumulators: columns [half*kSpillCols, +kSpillCols) of the [col][row] array
       double *spill = reinterpret_cast<double *>(smem_raw + (spill_base - ptx::smem_u32(smem_raw))) +
                       static_cast<size_t>(half * kSpillCols) * BM + (q * 32u + lane);
-      bool first = true;
-      for (PairIter it(p); it.valid(); it.next(), pc++) {
-        const uint32_t buf = pc % kBufs, bph = (pc / kBufs) & 1u;
-        ptx::mbar_wait(tfull_bar(buf), bph);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * Cfg::kBufStride + half * kCols;
-        const double scale = it.scale(p.bits);
+      // one plane product per group: 1 for a real GEMM, the reference's 4 for a complex one (src/gemm.cu:479-518),
+      // each folded into C by its own finalize before the next starts from a zero accumulator
+      for (uint32_t grp = 0; grp < p.groups; grp++) {
 #pragma unroll
-        for (uint32_t c = 0; c < (kCols + 15) / 16; c++) {
-          // 16 columns per TMEM load; a tile width that is not a multiple of 32 ends with one 8-column load
-          const bool wide = c * 16 + 16 <= kCols;
-          const uint32_t nv = wide ? 16u : 8u;
-          uint32_t v[16];
-          if (wide) ptx::tmem_ld_x16(taddr + c * 16, v);
-          else ptx::tmem_ld_x8(taddr + c * 16, v);
-          ptx::tmem_ld_wait();
-          if (!raw) {
-            // (double)p without I2F.F64 (a quarter-rate conversion, 15/clk/SM measured, that would make the
-            // epilogue as slow as the MMAs): 2^52 + 2^31 + p is the bit pattern {0x43300000, p ^ 0x80000000};
-            // subtracting 2^52 + 2^31 is exact.
+        for (uint32_t j = 0; j < kRegCols; j++) acc[j] = 0.0;
+        bool first = true;
+        for (PairIter it(p); it.valid(); it.next(), pc++) {
+          const uint32_t buf = pc % kBufs, bph = (pc / kBufs) & 1u;
+          ptx::mbar_wait(tfull_bar(buf), bph);
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * Cfg::kBufStride + half * kCols;
+          const double scale = it.scale(p.bits);
 #pragma unroll
-            for (uint32_t g = 0; g < nv; g += 8) {
-              double d[8];
+          for (uint32_t c = 0; c < (kCols + 15) / 16; c++) {
+            // 16 columns per TMEM load; a tile width that is not a multiple of 32 ends with one 8-column load
+            const bool wide = c * 16 + 16 <= kCols;
+            const uint32_t nv = wide ? 16u : 8u;
+            uint32_t v[16];
+            if (wide) ptx::tmem_ld_x16(taddr + c * 16, v);
+            else ptx::tmem_ld_x8(taddr + c * 16, v);
+            ptx::tmem_ld_wait();
+            if (!raw) {
+              // (double)p without I2F.F64 (a quarter-rate conversion, 15/clk/SM measured, that would make the
+              // epilogue as slow as the MMAs): 2^52 + 2^31 + p is the bit pattern {0x43300000, p ^ 0x80000000};
+              // subtracting 2^52 + 2^31 is exact.
 #pragma unroll
-              for (uint32_t j = 0; j < 8; j++)
-                d[j] = __dadd_rn(__hiloint2double(0x43300000, static_cast<int>(v[g + j] ^ 0x80000000u)),
-                                 -4503601774854144.0);
-              if (c * 16 + g < kRegCols) {
+              for (uint32_t g = 0; g < nv; g += 8) {
+                double d[8];
 #pragma unroll
                 for (uint32_t j = 0; j < 8; j++)
-                  acc[(c * 16 + g + j) % kRegCols] = __fma_rn(d[j], scale, acc[(c * 16 + g + j) % kRegCols]);
-              } else {
+                  d[j] = __dadd_rn(__hiloint2double(0x43300000, static_cast<int>(v[g + j] ^ 0x80000000u)),
+                                   -4503601774854144.0);
+                if (c * 16 + g < kRegCols) {
 #pragma unroll
-                for (uint32_t j = 0; j < 8; j++) {
-                  double *sp = spill + static_cast<size_t>(c * 16 + g + j - kRegCols) * BM;
-                  *sp = __fma_rn(d[j], scale, first ? 0.0 : *sp);
+                  for (uint32_t j = 0; j < 8; j++)
+                    acc[(c * 16 + g + j) % kRegCols] = __fma_rn(d[j], scale, acc[(c * 16 + g + j) % kRegCols]);
+                } else {
+#pragma unroll
+                  for (uint32_t j = 0; j < 8; j++) {
+                    double *sp = spill + static_cast<size_t>(c * 16 + g + j - kRegCols) * BM;
+                    *sp = __fma_rn(d[j], scale, first ? 0.0 : *sp);
+                  }
                 }
               }
-            }
-          } else if (!kQueue && row < p.m) {
+            } else if (!kQueue && row < p.m) {
 #pragma unroll
-            for (uint32_t j = 0; j < nv; j++) {
-              const uint32_t col = col0 + c * 16 + j;
-              if (col < p.n)
-                p.c_i32[(static_cast<size_t>(entry) * p.n + col) * p.m + row] = static_cast<int32_t>(v[j]);
+              for (uint32_t j = 0; j < nv; j++) {
+                const uint32_t col = col0 + c * 16 + j;
+                if (col < p.n)
+                  p.c_i32[(static_cast<size_t>(entry) * p.n + col) * p.m + row] = static_cast<int32_t>(v[j]);
+              }
             }
           }
+          first = false;
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) ptx::mbar_arrive(tempty_bar(buf));
+            else ptx::mbar_arrive_remote(ptx::mapa(tempty_bar(buf), 0));
+          }
         }
-        first = false;
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (rank == 0) ptx::mbar_arrive(tempty_bar(buf));
-          else ptx::mbar_arrive_remote(ptx::mapa(tempty_bar(buf), 0));
+        if constexpr (kQueue) {
+          const uint32_t item =
+              __shfl_sync(0xffffffffu, ptx::ld_acquire_gpu(p.q_slots + static_cast<size_t>(pair_id) * p.q_cap + (seq.i - 1)), 0) - 1u;
+          item_coords(p, item, tm, tn, done_idx);
+          row = tm * 2 * BM + rank * BM + q * 32u + lane;
+          col0 = tn * BN_ + half * kCols;
         }
-      }
-      uint32_t done_idx = 0;
-      if constexpr (kQueue) {
-        const uint32_t item =
-            __shfl_sync(0xffffffffu, ptx::ld_acquire_gpu(p.q_slots + static_cast<size_t>(pair_id) * p.q_cap + (seq.i - 1)), 0) - 1u;
-        item_coords(p, item, tm, tn, done_idx);
-        row = tm * 2 * BM + rank * BM + q * 32u + lane;
-        col0 = tn * BN_ + half * kCols;
-      }
-      if (!raw && row < p.m) {
-        // reference src/gemm.cu:124-148: x = acc / 2^44 * amax[mi] * bmax[ni]
-        const double am = p.amax[static_cast<size_t>(entry) * p.amax_batch + row];
-        const double *bmax = p.bmax + static_cast<size_t>(entry) * p.bmax_batch;
-        double *cbase = p.c + static_cast<size_t>(entry) * p.c_batch * (p.cplx ? 2 : 1);
-        double *crow = cbase + row;
-#pragma unroll
-        for (uint32_t j = 0; j < kCols; j++) {
-          const uint32_t col = col0 + j;
-          if (col < p.n) {
-            const double a_j = (j < kRegCols) ? acc[j % kRegCols] : spill[static_cast<size_t>(j - kRegCols) * BM];
-            double x = __dmul_rn(a_j, 0x1p-44);
-            x = __dmul_rn(x, am);
-            x = __dmul_rn(x, __ldg(bmax + col));
+        if (!raw && row < p.m) {
+          // alpha / beta by value, or read here from device memory (cuBLAS device pointer mode)
+          double alpha = p.alpha, alpha_im = p.alpha_im, beta = p.beta, beta_im = p.beta_im;
+          if (p.alpha_dev != nullptr) {
+            alpha = __ldg(p.alpha_dev);
+            beta = __ldg(p.beta_dev);
             if (p.cplx) {
-              double2 *dst = reinterpret_cast<double2 *>(cbase) + static_cast<size_t>(col) * p.ldc + row;
-              double2 y = make_double2(0.0, 0.0);
-              if (p.cplx_init) {
-                if (p.beta != 0 || p.beta_im != 0) {
-                  // init_c_complex_kernel<false> as compiled (reference src/gemm.cu:214-222, incl. its use
-                  // of the already-updated real part): t = y.y*b.y; y.x = fma(y.x, b.x, -t);
-                  // t = y.x*b.y; y.y = fma(y.y, b.x, t)
-                  y = *dst;
-                  const double yx = __fma_rn(y.x, p.beta, -__dmul_rn(y.y, p.beta_im));
-                  y.y = __fma_rn(y.y, p.beta, __dmul_rn(yx, p.beta_im));
-                  y.x = yx;
+              alpha_im = __ldg(p.alpha_dev + 1);
+              beta_im = __ldg(p.beta_dev + 1);
+            }
+          }
+          // reference src/gemm.cu:124-148: x = acc / 2^44 * amax[mi] * bmax[ni]
+          const double am = p.amax[static_cast<size_t>(entry) * p.amax_batch + group_plane_a(p, grp) * p.amax_plane + row];
+          const double *bmax = p.bmax + static_cast<size_t>(entry) * p.bmax_batch + group_plane_b(p, grp) * p.bmax_plane;
+          double *cbase = p.c + static_cast<size_t>(entry) * p.c_batch * (p.cplx ? 2 : 1);
+          double *crow = cbase + row;
+          // complex: the coefficient of this plane product (reference src/gemm.cu:497-509):
+          // (im,im) -> -alpha, (re,re) -> +alpha, (im,re) and (re,im) -> i*alpha
+          const double coef_re = grp == 1 ? alpha : (grp == 0 ? -alpha : -alpha_im);
+          const double coef_im = grp == 1 ? alpha_im : (grp == 0 ? -alpha_im : alpha);
+#pragma unroll
+          for (uint32_t j = 0; j < kCols; j++) {
+            const uint32_t col = col0 + j;
+            if (col < p.n) {
+              const double a_j = (j < kRegCols) ? acc[j % kRegCols] : spill[static_cast<size_t>(j - kRegCols) * BM];
+              double x = __dmul_rn(a_j, 0x1p-44);
+              x = __dmul_rn(x, am);
+              x = __dmul_rn(x, __ldg(bmax + col));
+              if (p.cplx) {
+                double2 *dst = reinterpret_cast<double2 *>(cbase) + static_cast<size_t>(col) * p.ldc + row;
+                double2 y = make_double2(0.0, 0.0);
+                if (grp == 0) {
+                  if (beta != 0 || beta_im != 0) {
+                    // C = beta * C (reference init_c_complex_kernel<false>, src/gemm.cu:214-222), contracted as the
+                    // reference compiles it: t = y.y*b.y; x' = fma(y.x, b.x, -t); t = y.x*b.y; y' = fma(y.y, b.x, t).
+                    // The reference's source reads the already-updated real part in the second product (an aliasing
+                    // bug: Im(beta*C) is wrong whenever Im(beta) != 0); this uses the original one.
+                    // Identical bits when Im(beta) == 0.
+                    y = *dst;
+                    const double yx = __fma_rn(y.x, beta, -__dmul_rn(y.y, beta_im));
+                    y.y = __fma_rn(y.y, beta, __dmul_rn(y.x, beta_im));
+                    y.x = yx;
+                  }
+                } else {
+                  y = *dst;   // written by this very thread after the previous plane product
                 }
+                y.x = __fma_rn(x, coef_re, y.x);      // axy_complex_kernel (reference src/gemm.cu:160-186)
+                y.y = __fma_rn(x, coef_im, y.y);
+                *dst = y;
               } else {
-                y = *dst;
-              }
-              y.x = __fma_rn(x, p.alpha, y.x);      // axy_complex_kernel (reference src/gemm.cu:160-186)
-              y.y = __fma_rn(x, p.alpha_im, y.y);
-              *dst = y;
-            } else {
-              double *dst = crow + static_cast<size_t>(col) * p.ldc;
-              if (p.beta != 0) {
-                *dst = __fma_rn(p.alpha, x, __dmul_rn(p.beta, *dst));
-              } else {
-                *dst = __dmul_rn(p.alpha, x);
+                double *dst = crow + static_cast<size_t>(col) * p.ldc;
+                if (beta != 0) {
+                  *dst = __fma_rn(alpha, x, __dmul_rn(beta, *dst));
+                } else {
+                  *dst = __dmul_rn(alpha, x);
+                }
               }
             }
           }
@@ -572,13 +607,32 @@ oz_gemm_pair_kernel(const FusedParams p) {
   if (warp == 2) ptx::tmem_dealloc_2sm<512>(tmem_base);
 }
 
-// k == 0: every product is empty, C = beta * C (beta == 0: C is not read, reference src/gemm.cu:143-147)
+// k == 0: every product is empty, C = beta * C (beta == 0: C is not read, reference src/gemm.cu:143-147); complex C:
+// the beta pre-scale of the complex path (init_c_complex, src/gemm.cu:188-239, with the App. B.6 fix).  beta by value
+// or read from device memory (cuBLAS device pointer mode).
 __global__ void __launch_bounds__(256)
-oz_scale_c_kernel(double *__restrict__ c, const size_t ldc, const uint32_t m, const uint32_t n, const double beta) {
+oz_scale_c_kernel(double *__restrict__ c, const size_t ldc, const uint32_t m, const uint32_t n, double beta,
+                  double beta_im, const double *__restrict__ beta_dev, const bool cplx) {
   const uint32_t r = blockIdx.x * 256 + threadIdx.x, col = blockIdx.y;
   if (r >= m || col >= n) return;
-  double *p = c + static_cast<size_t>(col) * ldc + r;
-  *p = (beta != 0) ? __dmul_rn(beta, *p) : 0.0;
+  if (beta_dev != nullptr) {
+    beta = __ldg(beta_dev);
+    if (cplx) beta_im = __ldg(beta_dev + 1);
+  }
+  if (!cplx) {
+    double *p = c + static_cast<size_t>(col) * ldc + r;
+    *p = (beta != 0) ? __dmul_rn(beta, *p) : 0.0;
+  } else {
+    double2 *p = reinterpret_cast<double2 *>(c) + static_cast<size_t>(col) * ldc + r;
+    double2 y = make_double2(0.0, 0.0);
+    if (beta != 0 || beta_im != 0) {
+      y = *p;
+      const double yx = __fma_rn(y.x, beta, -__dmul_rn(y.y, beta_im));
+      y.y = __fma_rn(y.y, beta, __dmul_rn(y.x, beta_im));
+      y.x = yx;
+    }
+    *p = y;
+  }
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -606,26 +660,25 @@ uint32_t lockstep_window() {
 
 constexpr uint32_t kSyncCounters = 1u << 16;  // per buffer: 64 Ki intervals = 1 Mi k-steps per CTA pair
 constexpr int kSyncBuffers = 8;               // launches that may be in flight at once without sharing
+// per device: a small ring of counter buffers, allocated on first use and kept for the life of the process (more
+// than kSyncBuffers launches in flight at once share counters, which only costs pacing time-outs)
 uint32_t *next_sync_buffer() {
   static std::mutex mu;
-  static uint32_t *pool[kSyncBuffers] = {};
-  static int pool_dev[kSyncBuffers] = {};
-  static int next = 0;
+  static uint32_t *pool[kMaxDevices][kSyncBuffers] = {};
+  static int next[kMaxDevices] = {};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
-  const int i = next;
-  next = (next + 1) % kSyncBuffers;
-  if (pool[i] != nullptr && pool_dev[i] != dev) pool[i] = nullptr;  // another device's buffer: not reusable here
-  if (pool[i] == nullptr) {
-    if (cudaMalloc(&pool[i], kSyncCounters * sizeof(uint32_t)) != cudaSuccess) {
-      pool[i] = nullptr;
+  const int i = next[dev];
+  next[dev] = (i + 1) % kSyncBuffers;
+  if (pool[dev][i] == nullptr) {
+    if (cudaMalloc(&pool[dev][i], kSyncCounters * sizeof(uint32_t)) != cudaSuccess) {
+      pool[dev][i] = nullptr;
       cudaGetLastError();
       return nullptr;
     }
-    pool_dev[i] = dev;
   }
-  return pool[i];
+  return pool[dev][i];
 }
 
 template <uint32_t BN_>
@@ -693,7 +746,7 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   // within a single round, and the polling costs ~7 % there)
   p.sync_ctr = nullptr;
   if (p.sync_window > 0 && pairs > 1 && num_tiles > pairs && p.single_a == 0 && !p.no_lockstep) {
-    const uint64_t steps = static_cast<uint64_t>(ceil_div_u32(num_tiles, pairs)) * (p.num_split * (p.num_split + 1) / 2) * p.k_blocks;
+    const uint64_t steps = static_cast<uint64_t>(ceil_div_u32(num_tiles, pairs)) * (p.num_split * (p.num_split + 1) / 2) * p.k_blocks * p.groups;
     const uint64_t need = steps / kSyncEvery + 1;
     if (need <= kSyncCounters) {
       uint32_t *buf = next_sync_buffer();
@@ -839,6 +892,7 @@ FusedParams base_params(size_t m, size_t n, size_t pitch, const int8_t *a_slices
   p.bits = static_cast<int32_t>(bits);
   p.a_slices = a_slices;
   p.b_slices = b_slices;
+  p.groups = 1;
   return p;
 }
 
@@ -852,21 +906,80 @@ extern "C" int ozk_set_cluster_shape(int cm, int cn) {
   return 0;
 }
 
+// The general launcher: every other ozk_gemm_i8_fused* entry point fills this struct.
+extern "C" int ozk_gemm_i8_fused_ex(const ozk_fused_args_t *a, void *stream) {
+  if (a == nullptr) return static_cast<int>(cudaErrorInvalidValue);
+  const size_t batch = a->batch ? a->batch : 1;
+  if (a->m == 0 || a->n == 0) return 0;
+  const size_t a_plane_rows = a->a_plane_rows ? a->a_plane_rows : a->m;
+  const size_t b_plane_rows = a->b_plane_rows ? a->b_plane_rows : a->n;
+  const size_t tiles = ((a->m + 255) / 256) * ((a->n + 127) / 128);  // upper bound (128-wide tiles)
+  if (!oz::valid_common(a->m, a->n, a->k, a->pitch, a->num_split, a->bits_per_int8) || a->ldc < a->m ||
+      a->row0 % 256 != 0 || a->col0 % 256 != 0 || a->row0 + a->m > a_plane_rows || a->col0 + a->n > b_plane_rows ||
+      a_plane_rows >= (1ull << 31) || b_plane_rows >= (1ull << 31) || a->a_batch_bytes % 16 != 0 ||
+      a->b_batch_bytes % 16 != 0 || a->a_plane_bytes % 16 != 0 || a->b_plane_bytes % 16 != 0 || batch >= (1ull << 31) ||
+      tiles * batch >= (1ull << 31) || (a->alpha_dev == nullptr) != (a->beta_dev == nullptr) || a->c == nullptr)
+    return static_cast<int>(cudaErrorInvalidValue);
+  // a block starts on a row-tile boundary of its plane: the kernel only needs the plane's slice stride
+  const size_t tile_row_bytes = a->pitch * oz::kTileRows;
+  oz::FusedParams p = oz::base_params(a->m, a->n, a->pitch, a->a_slices + (a->row0 / oz::kTileRows) * tile_row_bytes,
+                                      a->b_slices + (a->col0 / oz::kTileRows) * tile_row_bytes, a->num_split,
+                                      a->bits_per_int8);
+  p.rt_a = static_cast<uint32_t>(oz::slice_row_tiles(a_plane_rows));
+  p.rt_b = static_cast<uint32_t>(oz::slice_row_tiles(b_plane_rows));
+  p.b_rows = p.rt_b * static_cast<uint32_t>(oz::kTileRows) - static_cast<uint32_t>(a->col0);
+  // entries of a batch share no operands: nothing to gain from pacing the CTA pairs
+  p.no_lockstep = ((a->flags & OZK_FUSED_NO_LOCKSTEP) || batch > 1) ? 1u : 0u;
+  p.one_tile_per_pair = (a->flags & OZK_FUSED_ONE_TILE_PER_PAIR) ? 1u : 0u;
+  p.alpha = a->alpha[0];
+  p.alpha_im = a->alpha[1];
+  p.beta = a->beta[0];
+  p.beta_im = a->beta[1];
+  p.alpha_dev = a->alpha_dev;
+  p.beta_dev = a->beta_dev;
+  p.c = static_cast<double *>(a->c);
+  p.ldc = a->ldc;
+  p.amax = a->amax;
+  p.bmax = a->bmax;
+  p.batch = static_cast<uint32_t>(batch);
+  p.a_batch_bytes = a->a_batch_bytes;
+  p.b_batch_bytes = a->b_batch_bytes;
+  p.amax_batch = a->amax_batch;
+  p.bmax_batch = a->bmax_batch;
+  p.c_batch = a->c_batch;
+  if (a->complex_c) {
+    p.cplx = 1;
+    p.groups = 4;
+    p.a_plane_bytes = a->a_plane_bytes;
+    p.b_plane_bytes = a->b_plane_bytes;
+    p.amax_plane = a->amax_plane;
+    p.bmax_plane = a->bmax_plane;
+  }
+  return oz::dispatch_fused(p, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+ozk_fused_args_t real_args(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices, size_t pitch,
+                           const double *amax, const double *bmax, unsigned num_split, unsigned bits_per_int8,
+                           double alpha, double beta, double *c, size_t ldc) {
+  ozk_fused_args_t a{};
+  a.m = m, a.n = n, a.k = k, a.pitch = pitch;
+  a.a_slices = a_slices, a.b_slices = b_slices;
+  a.amax = amax, a.bmax = bmax;
+  a.num_split = num_split, a.bits_per_int8 = bits_per_int8;
+  a.alpha[0] = alpha, a.beta[0] = beta;
+  a.c = c, a.ldc = ldc;
+  return a;
+}
+}  // namespace
+
 extern "C" int ozk_gemm_i8_fused(size_t m, size_t n, size_t k, const int8_t *a_slices,
                                  const int8_t *b_slices, size_t pitch, const double *amax,
                                  const double *bmax, unsigned num_split, unsigned bits_per_int8,
                                  double alpha, double beta, double *c, size_t ldc, void *stream) {
-  if (m == 0 || n == 0) return 0;
-  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m)
-    return static_cast<int>(cudaErrorInvalidValue);
-  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices, b_slices, num_split, bits_per_int8);
-  p.alpha = alpha;
-  p.beta = beta;
-  p.c = c;
-  p.ldc = ldc;
-  p.amax = amax;
-  p.bmax = bmax;
-  return oz::dispatch_fused(p, static_cast<cudaStream_t>(stream));
+  const ozk_fused_args_t a = real_args(m, n, k, a_slices, b_slices, pitch, amax, bmax, num_split, bits_per_int8, alpha,
+                                       beta, c, ldc);
+  return ozk_gemm_i8_fused_ex(&a, stream);
 }
 
 extern "C" int ozk_gemm_i8_fused_block(size_t m, size_t n, size_t k, const int8_t *a_slices, size_t a_plane_rows,
@@ -874,27 +987,12 @@ extern "C" int ozk_gemm_i8_fused_block(size_t m, size_t n, size_t k, const int8_
                                        size_t pitch, const double *amax, const double *bmax, unsigned num_split,
                                        unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
                                        unsigned flags, void *stream) {
-  if (m == 0 || n == 0) return 0;
-  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m || row0 % 256 != 0 ||
-      col0 % 256 != 0 || row0 + m > a_plane_rows || col0 + n > b_plane_rows || a_plane_rows >= (1ull << 31) ||
-      b_plane_rows >= (1ull << 31))
-    return static_cast<int>(cudaErrorInvalidValue);
-  // a block starts on a row-tile boundary of its plane: the kernel only needs the plane's slice stride
-  const size_t tile_row_bytes = pitch * oz::kTileRows;
-  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices + (row0 / oz::kTileRows) * tile_row_bytes,
-                                      b_slices + (col0 / oz::kTileRows) * tile_row_bytes, num_split, bits_per_int8);
-  p.rt_a = static_cast<uint32_t>(oz::slice_row_tiles(a_plane_rows));
-  p.rt_b = static_cast<uint32_t>(oz::slice_row_tiles(b_plane_rows));
-  p.b_rows = p.rt_b * static_cast<uint32_t>(oz::kTileRows) - static_cast<uint32_t>(col0);
-  p.no_lockstep = (flags & OZK_FUSED_NO_LOCKSTEP) ? 1u : 0u;
-  p.one_tile_per_pair = (flags & OZK_FUSED_ONE_TILE_PER_PAIR) ? 1u : 0u;
-  p.alpha = alpha;
-  p.beta = beta;
-  p.c = c;
-  p.ldc = ldc;
-  p.amax = amax;
-  p.bmax = bmax;
-  return oz::dispatch_fused(p, static_cast<cudaStream_t>(stream));
+  ozk_fused_args_t a = real_args(m, n, k, a_slices, b_slices, pitch, amax, bmax, num_split, bits_per_int8, alpha, beta,
+                                 c, ldc);
+  a.a_plane_rows = a_plane_rows, a.b_plane_rows = b_plane_rows;
+  a.row0 = row0, a.col0 = col0;
+  a.flags = flags;
+  return ozk_gemm_i8_fused_ex(&a, stream);
 }
 
 extern "C" int ozk_gemm_i8_fused_batched(size_t m, size_t n, size_t k, size_t batch, const int8_t *a_slices,
@@ -903,26 +1001,13 @@ extern "C" int ozk_gemm_i8_fused_batched(size_t m, size_t n, size_t k, size_t ba
                                          size_t bmax_batch, unsigned num_split, unsigned bits_per_int8,
                                          double alpha, double beta, double *c, size_t ldc, size_t c_batch,
                                          void *stream) {
-  if (m == 0 || n == 0 || batch == 0) return 0;
-  const size_t tiles = ((m + 255) / 256) * ((n + 127) / 128);  // upper bound (128-wide tiles)
-  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m || a_batch_bytes % 16 != 0 ||
-      b_batch_bytes % 16 != 0 || batch >= (1ull << 31) || tiles * batch >= (1ull << 31))
-    return static_cast<int>(cudaErrorInvalidValue);
-  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices, b_slices, num_split, bits_per_int8);
-  p.batch = static_cast<uint32_t>(batch);
-  p.a_batch_bytes = a_batch_bytes;
-  p.b_batch_bytes = b_batch_bytes;
-  p.amax_batch = amax_batch;
-  p.bmax_batch = bmax_batch;
-  p.c_batch = c_batch;
-  p.no_lockstep = 1;  // entries share no operands: nothing to gain from pacing the CTA pairs
-  p.alpha = alpha;
-  p.beta = beta;
-  p.c = c;
-  p.ldc = ldc;
-  p.amax = amax;
-  p.bmax = bmax;
-  return oz::dispatch_fused(p, static_cast<cudaStream_t>(stream));
+  if (batch == 0) return 0;
+  ozk_fused_args_t a = real_args(m, n, k, a_slices, b_slices, pitch, amax, bmax, num_split, bits_per_int8, alpha, beta,
+                                 c, ldc);
+  a.batch = batch;
+  a.a_batch_bytes = a_batch_bytes, a.b_batch_bytes = b_batch_bytes;
+  a.amax_batch = amax_batch, a.bmax_batch = bmax_batch, a.c_batch = c_batch;
+  return ozk_gemm_i8_fused_ex(&a, stream);
 }
 
 extern "C" size_t ozk_queue_scratch_words(size_t num_items, unsigned reserve_sms) {
@@ -985,39 +1070,26 @@ extern "C" int ozk_gemm_i8_fused_queue_join(size_t m, size_t n, size_t k, const 
                                static_cast<int>(first_pair), num_pairs);
 }
 
-extern "C" int ozk_gemm_i8_fused_complex(size_t m, size_t n, size_t k, const int8_t *a_slices,
-                                         const int8_t *b_slices, size_t pitch, const double *amax,
-                                         const double *bmax, unsigned num_split, unsigned bits_per_int8,
-                                         double coef_re, double coef_im, int apply_beta, double beta_re,
-                                         double beta_im, void *c, size_t ldc, void *stream) {
+extern "C" int ozk_scale_c_ex(size_t m, size_t n, const double beta[2], const double *beta_dev, int complex_c, void *c,
+                              size_t ldc, void *stream) {
   if (m == 0 || n == 0) return 0;
-  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m)
+  if (ldc < m || m >= (1ull << 31) || n >= 65536ull * 32768ull || c == nullptr || (beta == nullptr && beta_dev == nullptr))
     return static_cast<int>(cudaErrorInvalidValue);
-  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices, b_slices, num_split, bits_per_int8);
-  p.alpha = coef_re;
-  p.alpha_im = coef_im;
-  p.beta = beta_re;
-  p.beta_im = beta_im;
-  p.cplx = 1;
-  p.cplx_init = apply_beta ? 1u : 0u;
-  p.c = static_cast<double *>(c);
-  p.ldc = ldc;
-  p.amax = amax;
-  p.bmax = bmax;
-  return oz::dispatch_fused(p, static_cast<cudaStream_t>(stream));
-}
-
-extern "C" int ozk_scale_c(size_t m, size_t n, double beta, double *c, size_t ldc, void *stream) {
-  if (m == 0 || n == 0) return 0;
-  if (ldc < m || m >= (1ull << 31) || n >= 65536ull * 32768ull) return static_cast<int>(cudaErrorInvalidValue);
+  const size_t es = complex_c ? 2 : 1;
   for (size_t j0 = 0; j0 < n; j0 += 65535) {
     const unsigned nj = static_cast<unsigned>(n - j0 < 65535 ? n - j0 : 65535);
     dim3 grid(static_cast<unsigned>((m + 255) / 256), nj);
-    oz::oz_scale_c_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(c + j0 * ldc, ldc, static_cast<uint32_t>(m),
-                                                                              nj, beta);
+    oz::oz_scale_c_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<double *>(c) + j0 * ldc * es, ldc, static_cast<uint32_t>(m), nj, beta ? beta[0] : 0.0,
+        (beta && complex_c) ? beta[1] : 0.0, beta_dev, complex_c != 0);
     oz::count_launch(1);
   }
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ozk_scale_c(size_t m, size_t n, double beta, double *c, size_t ldc, void *stream) {
+  const double b[2] = {beta, 0.0};
+  return ozk_scale_c_ex(m, n, b, nullptr, 0, c, ldc, stream);
 }
 
 extern "C" int ozk_gemm_i8_pair(size_t m, size_t n, size_t k, const int8_t *a_slices,

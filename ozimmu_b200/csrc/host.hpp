@@ -154,5 +154,8 @@ struct mtk::ozimmu::handle {
   bool streamed_warm = false;  // same for gemm_streamed_b's queue mode
   bool queue_warm = false;  // every kernel of the path has been launched once (lazy module loading must not happen
                             // while the persistent kernel spins)
+  // alpha / beta of gemm() are device pointers (set by the interposers when the application's cuBLAS handle is in
+  // CUBLAS_POINTER_MODE_DEVICE; the reference dereferences them on the host regardless, src/gemm.cu:405)
+  bool scalars_on_device = false;
   int device = 0;
 };

@@ -9,7 +9,11 @@
 // (SURVEY App. B.3/B.4/B.7): n is compared with THRESHOLD_N, a failed Ozaki call reports
 // CUBLAS_STATUS_INTERNAL_ERROR, the global handle is created on first use (no null deref when
 // the application's cublasCreate ran before this library was loaded), and device-pointer-mode
-// scalars fall through to the real cuBLAS instead of being dereferenced on the host.
+// scalars are read on the device by the Ozaki kernels (the reference dereferences them on the host, src/gemm.cu:405).
+// State is per device: one ozIMMU handle (workspace, streams, events) and one lock per GPU, created on first use
+// with that GPU current, so a process that drives several GPUs -- one cuBLAS handle each, from one or several
+// threads -- gets the right workspace on each and calls on different GPUs do not serialise (the reference keeps ONE
+// global handle, src/cublas.cu:58-86).
 // Complex (CUDA_C_64F) GEMMs take the complex Ozaki path (reference src/gemm.cu:412-521) unless an
 // operand is CUBLAS_OP_C: the reference silently treats OP_C as OP_T (src/cublas.cu:50-56), which
 // is wrong for complex data, so those calls go to the real cuBLAS instead.
@@ -24,8 +28,21 @@ namespace H = oz::host;
 
 namespace {
 
-std::mutex g_mu;
-handle_t g_handle = nullptr;
+// per-device state, indexed by the current CUDA device (the device the application's cuBLAS handle lives on: cuBLAS
+// requires it to be current for every call on that handle)
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  std::mutex mu;
+  handle_t handle = nullptr;
+};
+DeviceState g_state[kMaxDevices];
+
+DeviceState &device_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+    throw std::runtime_error("ozIMMU: no current CUDA device");
+  return g_state[dev];
+}
 
 // reference src/cublas.cu:18-48: unknown / unset -> dgemm (passthrough)
 compute_mode_t env_compute_mode() {
@@ -36,21 +53,21 @@ compute_mode_t env_compute_mode() {
   return dgemm;
 }
 
-// reference src/cublas.cu:60-86
-handle_t global_handle() {
-  if (g_handle == nullptr) {
+// reference src/cublas.cu:60-86; call with st.mu held
+handle_t device_handle(DeviceState &st) {
+  if (st.handle == nullptr) {
     const malloc_mode_t mm = H::env_enabled("OZIMMU_MALLOC_ASYNC", false) ? malloc_async : malloc_sync;
     H::log_info("Initializing ozIMMU handle...");
-    create(&g_handle, mm);
+    create(&st.handle, mm);
     H::log_info("Successfully initialized");
   }
   if (const char *t = std::getenv("OZIMMU_AUTO_AVG_MANTISSA_LOSS_THRESHOLD")) {
     char *end = nullptr;
     const double v = std::strtod(t, &end);
     if (end == t) throw std::runtime_error(std::string("ERROR: invalid OZIMMU_AUTO_AVG_MANTISSA_LOSS_THRESHOLD = ") + t);
-    set_auto_mantissa_loss_threashold(g_handle, v);
+    set_auto_mantissa_loss_threashold(st.handle, v);
   }
-  return g_handle;
+  return st.handle;
 }
 
 template <class Fn>
@@ -96,11 +113,16 @@ bool should_intercept(handle_t h, compute_mode_t mode, int m, int n, int k, cuda
 // reference src/culip.cu:14-50: one "[CULiP Result][name] ns" line per intercepted call
 struct CulipScope {
   bool on;
-  cudaStream_t s;
+  cudaStream_t s = nullptr;
   std::string name;
   std::chrono::steady_clock::time_point t0;
-  CulipScope(cudaStream_t stream, std::string n) : on(H::env_enabled("OZIMMU_ENABLE_CULIP_PROFILING", false)), s(stream), name(std::move(n)) {
+  // make_name is only evaluated when profiling is on (it formats several numbers; every passthrough GEMM of a
+  // preloaded application comes through here)
+  template <class MakeName, class GetStream>
+  CulipScope(GetStream &&get_stream, MakeName &&make_name) : on(H::env_enabled("OZIMMU_ENABLE_CULIP_PROFILING", false)) {
     if (!on) return;
+    s = get_stream();
+    name = make_name();
     cudaStreamSynchronize(s);
     t0 = std::chrono::steady_clock::now();
   }
@@ -115,19 +137,45 @@ struct CulipScope {
 
 const char *op_str(cublasOperation_t op) { return op == CUBLAS_OP_N ? "N" : (op == CUBLAS_OP_T ? "T" : "C"); }
 
+std::string shape_str(cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k) {
+  return std::string(op_str(ta)) + op_str(tb) + "-m" + std::to_string(m) + "-n" + std::to_string(n) + "-k" + std::to_string(k);
+}
+
+// true if this call goes through the Ozaki path (thresholds of the current device's handle)
+bool take_call(compute_mode_t mode, int m, int n, int k, cudaDataType_t a, cudaDataType_t b, cudaDataType_t c) {
+  try {
+    DeviceState &st = device_state();
+    std::lock_guard<std::mutex> lock(st.mu);
+    return should_intercept(device_handle(st), mode, m, n, k, a, b, c);
+  } catch (const std::exception &e) {
+    H::log_error(e.what());
+    return false;
+  }
+}
+
+// one GEMM (batch == 1) or a strided batch through the Ozaki path, real or complex; strides in elements
 cublasStatus_t ozaki_gemm(cublasHandle_t handle, compute_mode_t mode, cublasOperation_t ta, cublasOperation_t tb, int m,
-                          int n, int k, const void *alpha, const void *A, int lda, const void *B, int ldb,
-                          const void *beta, void *C, int ldc, element_kind_t kind) {
-  std::lock_guard<std::mutex> lock(g_mu);
+                          int n, int k, const void *alpha, const void *A, int lda, long long strideA, const void *B,
+                          int ldb, long long strideB, const void *beta, void *C, int ldc, long long strideC, int batch,
+                          element_kind_t kind) {
   try {
-    handle_t h = global_handle();
+    DeviceState &st = device_state();
+    std::lock_guard<std::mutex> lock(st.mu);
+    handle_t h = device_handle(st);
     cudaStream_t s = stream_of(handle);
     set_cuda_stream(h, s);
-    CulipScope scope(s, std::string(kind == mtk::ozimmu::real ? "D" : "Z") + get_compute_mode_name_str(mode) + "-" + op_str(ta) + op_str(tb) + "-m" +
-                            std::to_string(m) + "-n" + std::to_string(n) + "-k" + std::to_string(k));
+    // cuBLAS device pointer mode: the scalars stay on the device (reference src/gemm.cu:405 dereferences them on the host)
+    set_scalar_pointer_mode(h, !host_pointer_mode(handle));
+    CulipScope scope([&] { return s; }, [&] {
+      return std::string(kind == mtk::ozimmu::real ? "D" : "Z") + get_compute_mode_name_str(mode) +
+             (batch > 1 ? "-batched" + std::to_string(batch) : std::string()) + "-" + shape_str(ta, tb, m, n, k);
+    });
     // reference src/cublas.cu:50-56: everything that is not OP_N is treated as OP_T (real data)
-    const int err = gemm(h, ta == CUBLAS_OP_N ? op_n : op_t, tb == CUBLAS_OP_N ? op_n : op_t, m, n, k, alpha, A, lda, B,
-                         ldb, beta, C, ldc, mode, kind);
+    const operation_t oa = ta == CUBLAS_OP_N ? op_n : op_t, ob = tb == CUBLAS_OP_N ? op_n : op_t;
+    const int err = batch == 1 ? gemm(h, oa, ob, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mode, kind)
+                               : gemm_strided_batched(h, oa, ob, m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C,
+                                                      ldc, strideC, static_cast<std::size_t>(batch), mode, kind);
+    set_scalar_pointer_mode(h, false);
     return err ? CUBLAS_STATUS_INVALID_VALUE : CUBLAS_STATUS_SUCCESS;
   } catch (const std::exception &e) {
     H::log_error(e.what());
@@ -135,33 +183,25 @@ cublasStatus_t ozaki_gemm(cublasHandle_t handle, compute_mode_t mode, cublasOper
   }
 }
 
-cublasStatus_t ozaki_dgemm(cublasHandle_t handle, compute_mode_t mode, cublasOperation_t ta, cublasOperation_t tb, int m,
-                           int n, int k, const double *alpha, const double *A, int lda, const double *B, int ldb,
-                           const double *beta, double *C, int ldc) {
-  return ozaki_gemm(handle, mode, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, mtk::ozimmu::real);
-}
-
-// the whole strided batch through one grouped launch (the reference loops: src/cublas.cu:380-406)
-cublasStatus_t ozaki_dgemm_batched(cublasHandle_t handle, compute_mode_t mode, cublasOperation_t ta, cublasOperation_t tb,
-                                   int m, int n, int k, const double *alpha, const double *A, int lda, long long strideA,
-                                   const double *B, int ldb, long long strideB, const double *beta, double *C, int ldc,
-                                   long long strideC, int batch) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  try {
-    handle_t h = global_handle();
-    cudaStream_t s = stream_of(handle);
-    set_cuda_stream(h, s);
-    CulipScope scope(s, std::string("D") + get_compute_mode_name_str(mode) + "-batched" + std::to_string(batch) + "-" +
-                            op_str(ta) + op_str(tb) + "-m" + std::to_string(m) + "-n" + std::to_string(n) + "-k" +
-                            std::to_string(k));
-    const int err = gemm_strided_batched(h, ta == CUBLAS_OP_N ? op_n : op_t, tb == CUBLAS_OP_N ? op_n : op_t, m, n, k,
-                                         alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
-                                         static_cast<std::size_t>(batch), mode);
-    return err ? CUBLAS_STATUS_INVALID_VALUE : CUBLAS_STATUS_SUCCESS;
-  } catch (const std::exception &e) {
-    H::log_error(e.what());
-    return CUBLAS_STATUS_INTERNAL_ERROR;
+// a strided batch: one grouped launch (the reference loops, src/cublas.cu:380-406) unless entries of C overlap or walk
+// backwards -- those cannot run concurrently and go entry by entry, as the reference does
+cublasStatus_t ozaki_batch(cublasHandle_t handle, compute_mode_t mode, cublasOperation_t ta, cublasOperation_t tb, int m,
+                           int n, int k, const void *alpha, const void *A, int lda, long long strideA, const void *B,
+                           int ldb, long long strideB, const void *beta, void *C, int ldc, long long strideC, int batch,
+                           element_kind_t kind) {
+  const std::size_t esz = kind == mtk::ozimmu::real ? sizeof(double) : 2 * sizeof(double);
+  const unsigned long long span = static_cast<unsigned long long>(ldc) * (n > 0 ? n - 1 : 0) + m;
+  if (batch == 1 || strideC < 0 || static_cast<unsigned long long>(strideC) < span) {
+    for (int i = 0; i < batch; i++) {
+      const cublasStatus_t st =
+          ozaki_gemm(handle, mode, ta, tb, m, n, k, alpha, static_cast<const char *>(A) + strideA * i * static_cast<long long>(esz),
+                     lda, 0, static_cast<const char *>(B) + strideB * i * static_cast<long long>(esz), ldb, 0, beta,
+                     static_cast<char *>(C) + strideC * i * static_cast<long long>(esz), ldc, 0, 1, kind);
+      if (st != CUBLAS_STATUS_SUCCESS) return st;
+    }
+    return CUBLAS_STATUS_SUCCESS;
   }
+  return ozaki_gemm(handle, mode, ta, tb, m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC, batch, kind);
 }
 
 bool no_conj(cublasOperation_t ta, cublasOperation_t tb) { return ta != CUBLAS_OP_C && tb != CUBLAS_OP_C; }
@@ -176,10 +216,11 @@ cublasStatus_t cublasCreate_v2(cublasHandle_t *handle) {
   if (fn == nullptr) return CUBLAS_STATUS_NOT_INITIALIZED;
   const cublasStatus_t st = fn(handle);
   if (st == CUBLAS_STATUS_SUCCESS && env_compute_mode() != dgemm) {
-    std::lock_guard<std::mutex> lock(g_mu);
     try {
-      // pre-size the workspace for one 1024^3 fp64_int8_9 product (reference src/cublas.cu:12-16)
-      reallocate_working_memory(global_handle(), gemm_list_t{{op_n, op_n, 1024, 1024, 1024, mtk::ozimmu::real, fp64_int8_9}});
+      // pre-size this device's workspace for one 1024^3 fp64_int8_9 product (reference src/cublas.cu:12-16)
+      DeviceState &ds = device_state();
+      std::lock_guard<std::mutex> lock(ds.mu);
+      reallocate_working_memory(device_handle(ds), gemm_list_t{{op_n, op_n, 1024, 1024, 1024, mtk::ozimmu::real, fp64_int8_9}});
     } catch (const std::exception &e) {
       H::log_error(e.what());
     }
@@ -188,7 +229,7 @@ cublasStatus_t cublasCreate_v2(cublasHandle_t *handle) {
 }
 
 // reference src/cublas.cu:117-131.  The reference tears its global handle down on ANY
-// cublasDestroy; here it lives until the process ends (another cuBLAS handle may still be in use).
+// cublasDestroy; here the per-device handles live until the process ends (another cuBLAS handle may still be in use).
 cublasStatus_t cublasDestroy_v2(cublasHandle_t handle) {
   auto fn = real_fn<cublasStatus_t (*)(cublasHandle_t)>("cublasDestroy_v2");
   if (fn == nullptr) return CUBLAS_STATUS_NOT_INITIALIZED;
@@ -203,25 +244,12 @@ cublasStatus_t cublasGemmEx(cublasHandle_t handle, cublasOperation_t transa, cub
   const compute_mode_t mode = env_compute_mode();
   const bool is_real = Atype == CUDA_R_64F && Btype == CUDA_R_64F && Ctype == CUDA_R_64F;
   const bool is_cplx = Atype == CUDA_C_64F && Btype == CUDA_C_64F && Ctype == CUDA_C_64F && no_conj(transa, transb);
-  if (mode != dgemm && (is_real || is_cplx)) {
-    bool take = false;
-    {
-      std::lock_guard<std::mutex> lock(g_mu);
-      try {
-        take = should_intercept(global_handle(), mode, m, n, k, Atype, Btype, Ctype) && host_pointer_mode(handle);
-      } catch (const std::exception &e) {
-        H::log_error(e.what());
-      }
-    }
-    if (take)
-      return ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
-                        is_real ? mtk::ozimmu::real : complx);
-  }
+  if (mode != dgemm && (is_real || is_cplx) && take_call(mode, m, n, k, Atype, Btype, Ctype))
+    return ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, 1,
+                      is_real ? mtk::ozimmu::real : complx);
   auto fn = real_fn<GemmExFn>("cublasGemmEx");
   if (fn == nullptr) return CUBLAS_STATUS_NOT_INITIALIZED;
-  CulipScope scope(H::env_enabled("OZIMMU_ENABLE_CULIP_PROFILING", false) ? stream_of(handle) : nullptr,
-                   std::string("cublasGemmEx-") + op_str(transa) + op_str(transb) + "-m" + std::to_string(m) + "-n" +
-                       std::to_string(n) + "-k" + std::to_string(k));
+  CulipScope scope([&] { return stream_of(handle); }, [&] { return "cublasGemmEx-" + shape_str(transa, transb, m, n, k); });
   return fn(handle, transa, transb, m, n, k, alpha, A, Atype, lda, B, Btype, ldb, beta, C, Ctype, ldc, computeType, algo);
 }
 
@@ -230,19 +258,9 @@ cublasStatus_t cublasDgemm_v2(cublasHandle_t handle, cublasOperation_t transa, c
                               int k, const double *alpha, const double *A, int lda, const double *B, int ldb,
                               const double *beta, double *C, int ldc) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm) {
-    bool take = false;
-    {
-      std::lock_guard<std::mutex> lock(g_mu);
-      try {
-        take = should_intercept(global_handle(), mode, m, n, k, CUDA_R_64F, CUDA_R_64F, CUDA_R_64F) &&
-               host_pointer_mode(handle);
-      } catch (const std::exception &e) {
-        H::log_error(e.what());
-      }
-    }
-    if (take) return ozaki_dgemm(handle, mode, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-  }
+  if (mode != dgemm && take_call(mode, m, n, k, CUDA_R_64F, CUDA_R_64F, CUDA_R_64F))
+    return ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, 1,
+                      mtk::ozimmu::real);
   auto fn = real_fn<cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const double *,
                                     const double *, int, const double *, int, const double *, double *, int)>(
       "cublasDgemm_v2");
@@ -256,19 +274,8 @@ cublasStatus_t cublasZgemm_v2(cublasHandle_t handle, cublasOperation_t transa, c
                               const cuDoubleComplex *B, int ldb, const cuDoubleComplex *beta, cuDoubleComplex *C,
                               int ldc) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm && no_conj(transa, transb)) {
-    bool take = false;
-    {
-      std::lock_guard<std::mutex> lock(g_mu);
-      try {
-        take = should_intercept(global_handle(), mode, m, n, k, CUDA_C_64F, CUDA_C_64F, CUDA_C_64F) &&
-               host_pointer_mode(handle);
-      } catch (const std::exception &e) {
-        H::log_error(e.what());
-      }
-    }
-    if (take) return ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, complx);
-  }
+  if (mode != dgemm && no_conj(transa, transb) && take_call(mode, m, n, k, CUDA_C_64F, CUDA_C_64F, CUDA_C_64F))
+    return ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, 1, complx);
   auto fn = real_fn<cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int,
                                     const cuDoubleComplex *, const cuDoubleComplex *, int, const cuDoubleComplex *, int,
                                     const cuDoubleComplex *, cuDoubleComplex *, int)>("cublasZgemm_v2");
@@ -276,7 +283,7 @@ cublasStatus_t cublasZgemm_v2(cublasHandle_t handle, cublasOperation_t transa, c
   return fn(handle, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
-// reference src/cublas.cu:315-472 (one Ozaki GEMM per batch entry, :380-406): here one grouped launch
+// reference src/cublas.cu:315-472 (one Ozaki GEMM per batch entry, :380-406): here one grouped launch, real or complex
 cublasStatus_t cublasGemmStridedBatchedEx(cublasHandle_t handle, cublasOperation_t transa, cublasOperation_t transb, int m,
                                           int n, int k, const void *alpha, const void *A, cudaDataType_t Atype, int lda,
                                           long long strideA, const void *B, cudaDataType_t Btype, int ldb,
@@ -284,41 +291,11 @@ cublasStatus_t cublasGemmStridedBatchedEx(cublasHandle_t handle, cublasOperation
                                           long long strideC, int batchCount, cublasComputeType_t computeType,
                                           cublasGemmAlgo_t algo) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm && Atype == CUDA_R_64F && Btype == CUDA_R_64F && Ctype == CUDA_R_64F) {
-    bool take = false;
-    {
-      std::lock_guard<std::mutex> lock(g_mu);
-      try {
-        take = should_intercept(global_handle(), mode, m, n, k, Atype, Btype, Ctype) && host_pointer_mode(handle);
-      } catch (const std::exception &e) {
-        H::log_error(e.what());
-      }
-    }
-    if (take && batchCount > 0) {
-      const auto *a = static_cast<const double *>(A);
-      const auto *b = static_cast<const double *>(B);
-      auto *c = static_cast<double *>(C);
-      // entries of C that overlap (or walk backwards) cannot run concurrently: entry by entry, as the reference
-      const unsigned long long span = static_cast<unsigned long long>(ldc) * (n > 0 ? n - 1 : 0) + m;
-      if (batchCount == 1 || strideC < 0 || static_cast<unsigned long long>(strideC) < span) {
-        for (int i = 0; i < batchCount; i++) {
-          const cublasStatus_t st =
-              ozaki_dgemm(handle, mode, transa, transb, m, n, k, static_cast<const double *>(alpha), a + strideA * i, lda,
-                          b + strideB * i, ldb, static_cast<const double *>(beta), c + strideC * i, ldc);
-          if (st != CUBLAS_STATUS_SUCCESS) return st;
-        }
-        return CUBLAS_STATUS_SUCCESS;
-      }
-      return ozaki_dgemm_batched(handle, mode, transa, transb, m, n, k, static_cast<const double *>(alpha), a, lda,
-                                 strideA, b, ldb, strideB, static_cast<const double *>(beta), c, ldc, strideC, batchCount);
-    }
-  }
-  if (mode != dgemm && Atype == CUDA_C_64F && Btype == CUDA_C_64F && Ctype == CUDA_C_64F)
-    return cublasZgemmStridedBatched(handle, transa, transb, m, n, k, static_cast<const cuDoubleComplex *>(alpha),
-                                     static_cast<const cuDoubleComplex *>(A), lda, strideA,
-                                     static_cast<const cuDoubleComplex *>(B), ldb, strideB,
-                                     static_cast<const cuDoubleComplex *>(beta), static_cast<cuDoubleComplex *>(C), ldc,
-                                     strideC, batchCount);
+  const bool is_real = Atype == CUDA_R_64F && Btype == CUDA_R_64F && Ctype == CUDA_R_64F;
+  const bool is_cplx = Atype == CUDA_C_64F && Btype == CUDA_C_64F && Ctype == CUDA_C_64F && no_conj(transa, transb);
+  if (mode != dgemm && (is_real || is_cplx) && batchCount > 0 && take_call(mode, m, n, k, Atype, Btype, Ctype))
+    return ozaki_batch(handle, mode, transa, transb, m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
+                       batchCount, is_real ? mtk::ozimmu::real : complx);
   auto fn = real_fn<GemmStridedBatchedExFn>("cublasGemmStridedBatchedEx");
   if (fn == nullptr) return CUBLAS_STATUS_NOT_INITIALIZED;
   return fn(handle, transa, transb, m, n, k, alpha, A, Atype, lda, strideA, B, Btype, ldb, strideB, beta, C, Ctype, ldc,
@@ -331,10 +308,9 @@ cublasStatus_t cublasDgemmStridedBatched(cublasHandle_t handle, cublasOperation_
                                          const double *B, int ldb, long long strideB, const double *beta, double *C,
                                          int ldc, long long strideC, int batchCount) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm)
-    return cublasGemmStridedBatchedEx(handle, transa, transb, m, n, k, alpha, A, CUDA_R_64F, lda, strideA, B, CUDA_R_64F,
-                                      ldb, strideB, beta, C, CUDA_R_64F, ldc, strideC, batchCount, CUBLAS_COMPUTE_64F,
-                                      CUBLAS_GEMM_DEFAULT);
+  if (mode != dgemm && batchCount > 0 && take_call(mode, m, n, k, CUDA_R_64F, CUDA_R_64F, CUDA_R_64F))
+    return ozaki_batch(handle, mode, transa, transb, m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
+                       batchCount, mtk::ozimmu::real);
   auto fn = real_fn<cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const double *,
                                     const double *, int, long long, const double *, int, long long, const double *,
                                     double *, int, long long, int)>("cublasDgemmStridedBatched");
@@ -349,26 +325,10 @@ cublasStatus_t cublasZgemmStridedBatched(cublasHandle_t handle, cublasOperation_
                                          const cuDoubleComplex *beta, cuDoubleComplex *C, int ldc, long long strideC,
                                          int batchCount) {
   const compute_mode_t mode = env_compute_mode();
-  if (mode != dgemm && no_conj(transa, transb)) {
-    bool take = false;
-    {
-      std::lock_guard<std::mutex> lock(g_mu);
-      try {
-        take = should_intercept(global_handle(), mode, m, n, k, CUDA_C_64F, CUDA_C_64F, CUDA_C_64F) &&
-               host_pointer_mode(handle);
-      } catch (const std::exception &e) {
-        H::log_error(e.what());
-      }
-    }
-    if (take) {
-      for (int i = 0; i < batchCount; i++) {
-        const cublasStatus_t st = ozaki_gemm(handle, mode, transa, transb, m, n, k, alpha, A + strideA * i, lda,
-                                             B + strideB * i, ldb, beta, C + strideC * i, ldc, complx);
-        if (st != CUBLAS_STATUS_SUCCESS) return st;
-      }
-      return CUBLAS_STATUS_SUCCESS;
-    }
-  }
+  if (mode != dgemm && no_conj(transa, transb) && batchCount > 0 &&
+      take_call(mode, m, n, k, CUDA_C_64F, CUDA_C_64F, CUDA_C_64F))
+    return ozaki_batch(handle, mode, transa, transb, m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
+                       batchCount, complx);
   auto fn = real_fn<cublasStatus_t (*)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int,
                                     const cuDoubleComplex *, const cuDoubleComplex *, int, long long,
                                     const cuDoubleComplex *, int, long long, const cuDoubleComplex *, cuDoubleComplex *,

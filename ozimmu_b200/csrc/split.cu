@@ -78,15 +78,24 @@ extern "C" int ozk_split_int8_block(int8_t *out, size_t pitch, size_t plane_rows
 
 // `batch` operands of the same shape in one launch: entry e reads in + e*in_stride (doubles) and writes its slices
 // at out + e*out_stride (bytes), its row scales at max_exp + e*max_stride, scratch at scratch + e*scr_stride.
-extern "C" int ozk_split_int8_batched(int8_t *out, size_t out_stride, size_t pitch, double *max_exp, size_t max_stride,
-                                      uint32_t *scratch, size_t scr_stride, size_t rows, size_t len, const double *in,
-                                      size_t ld, size_t in_stride, int col_major, unsigned num_split,
-                                      unsigned bits_per_int8, size_t batch, void *stream) {
+extern "C" int ozk_split_int8_batched_strided(int8_t *out, size_t out_stride, size_t pitch, double *max_exp,
+                                              size_t max_stride, uint32_t *scratch, size_t scr_stride, size_t rows,
+                                              size_t len, const double *in, size_t ld, size_t in_stride, int col_major,
+                                              unsigned num_split, unsigned bits_per_int8, unsigned elem_stride,
+                                              size_t batch, void *stream) {
   if (batch == 0) return 0;
   if (batch > 65535) return static_cast<int>(cudaErrorInvalidValue);
   const oz::SplitBatch bt{static_cast<uint32_t>(batch), in_stride, out_stride, max_stride, scr_stride};
   return oz::split_block_impl(out, pitch, rows, 0, max_exp, scratch, rows, len, in, ld, col_major, num_split,
-                              bits_per_int8, 1, static_cast<cudaStream_t>(stream), bt);
+                              bits_per_int8, elem_stride, static_cast<cudaStream_t>(stream), bt);
+}
+
+extern "C" int ozk_split_int8_batched(int8_t *out, size_t out_stride, size_t pitch, double *max_exp, size_t max_stride,
+                                      uint32_t *scratch, size_t scr_stride, size_t rows, size_t len, const double *in,
+                                      size_t ld, size_t in_stride, int col_major, unsigned num_split,
+                                      unsigned bits_per_int8, size_t batch, void *stream) {
+  return ozk_split_int8_batched_strided(out, out_stride, pitch, max_exp, max_stride, scratch, scr_stride, rows, len, in,
+                                        ld, in_stride, col_major, num_split, bits_per_int8, 1, batch, stream);
 }
 
 extern "C" int ozk_split_int8_strided(int8_t *out, size_t pitch, double *max_exp, uint32_t *scratch,
@@ -104,29 +113,41 @@ extern "C" int ozk_split_int8(int8_t *out, size_t pitch, double *max_exp, uint32
                                 bits_per_int8, 1, stream);
 }
 
-extern "C" int ozk_mantissa_loss_strided(unsigned long long *counters16, uint32_t *scratch, size_t rows,
-                                         size_t len, const double *in, size_t ld, int col_major,
-                                         unsigned bits_per_int8, unsigned elem_stride, void *stream) {
-  if (rows == 0 || len == 0) return 0;
+// counters16: [batch][16]; entry e reads in + e*in_stride (doubles) and uses scratch + e*scr_stride
+extern "C" int ozk_mantissa_loss_batched(unsigned long long *counters16, uint32_t *scratch, size_t scr_stride,
+                                         size_t rows, size_t len, const double *in, size_t ld, size_t in_stride,
+                                         int col_major, unsigned bits_per_int8, unsigned elem_stride, size_t batch,
+                                         void *stream) {
+  if (rows == 0 || len == 0 || batch == 0) return 0;
   if (len > 0xFFFFFFF0ull || rows > 0x7FFFFFFFull || (col_major && scratch == nullptr) || elem_stride < 1 ||
-      elem_stride > 2)
+      elem_stride > 2 || batch > 65535)
     return static_cast<int>(cudaErrorInvalidValue);
   const uint32_t es = elem_stride;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   using namespace oz;
+  const unsigned nb = static_cast<unsigned>(batch);
   if (col_major) {
-    OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), s));
-    dim3 g(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk));
-    rowmax_cols_kernel<<<g, 256, 0, s>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es, oz::SplitBatch{1, 0, 0, 0, 0});
+    const SplitBatch bt{nb, in_stride, 0, 0, scr_stride};
+    if (batch == 1) OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), s));
+    else OZ_CUDA_TRY(cudaMemset2DAsync(scratch, scr_stride * sizeof(uint32_t), 0, rows * sizeof(uint32_t), batch, s));
+    dim3 g(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk), nb);
+    rowmax_cols_kernel<<<g, 256, 0, s>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es, bt);
     loss_cols_kernel<<<g, 256, 0, s>>>(counters16, scratch, rows, static_cast<uint32_t>(len), in, ld,
-                                       bits_per_int8, es);
+                                       bits_per_int8, es, bt);
     count_launch(2);
   } else {
-    loss_rows_kernel<<<static_cast<unsigned>(rows), kSplitThreads, 0, s>>>(
-        counters16, static_cast<uint32_t>(len), in, ld, bits_per_int8, es);
+    loss_rows_kernel<<<dim3(static_cast<unsigned>(rows), nb), kSplitThreads, 0, s>>>(
+        counters16, static_cast<uint32_t>(len), in, ld, bits_per_int8, es, in_stride);
     count_launch(1);
   }
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ozk_mantissa_loss_strided(unsigned long long *counters16, uint32_t *scratch, size_t rows,
+                                         size_t len, const double *in, size_t ld, int col_major,
+                                         unsigned bits_per_int8, unsigned elem_stride, void *stream) {
+  return ozk_mantissa_loss_batched(counters16, scratch, 0, rows, len, in, ld, 0, col_major, bits_per_int8, elem_stride,
+                                   1, stream);
 }
 
 extern "C" int ozk_mantissa_loss(unsigned long long *counters16, uint32_t *scratch, size_t rows,

@@ -376,10 +376,13 @@ __device__ __forceinline__ void loss_block_reduce(uint32_t (&cnt)[16], unsigned 
 }
 
 __global__ void __launch_bounds__(kSplitThreads)
-loss_rows_kernel(unsigned long long *__restrict__ counters, const uint32_t len,
-                 const double *__restrict__ in, const size_t ld, const unsigned L, const uint32_t es) {
+loss_rows_kernel(unsigned long long *__restrict__ counters_, const uint32_t len,
+                 const double *__restrict__ in, const size_t ld, const unsigned L, const uint32_t es,
+                 const size_t in_stride) {
+  // blockIdx.y = entry of a strided batch: its own input and its own 16 counters
   __shared__ uint32_t s_red[kSplitThreads / 32];
-  const double *__restrict__ src = in + static_cast<size_t>(blockIdx.x) * ld * es;
+  unsigned long long *__restrict__ counters = counters_ + 16 * blockIdx.y;
+  const double *__restrict__ src = in + blockIdx.y * in_stride + static_cast<size_t>(blockIdx.x) * ld * es;
   uint32_t e = 0;
   for (uint32_t i = threadIdx.x; i < len; i += kSplitThreads)
     e = max(e, exp_field(__ldg(src + static_cast<size_t>(i) * es)));
@@ -395,9 +398,13 @@ loss_rows_kernel(unsigned long long *__restrict__ counters, const uint32_t len,
 }
 
 __global__ void __launch_bounds__(256)
-loss_cols_kernel(unsigned long long *__restrict__ counters, const uint32_t *__restrict__ emax,
-                 const size_t rows, const uint32_t len, const double *__restrict__ in,
-                 const size_t ld, const unsigned L, const uint32_t es) {
+loss_cols_kernel(unsigned long long *__restrict__ counters_, const uint32_t *__restrict__ emax_,
+                 const size_t rows, const uint32_t len, const double *__restrict__ in_,
+                 const size_t ld, const unsigned L, const uint32_t es, const SplitBatch bt) {
+  // blockIdx.z = entry of a strided batch
+  unsigned long long *__restrict__ counters = counters_ + 16 * blockIdx.z;
+  const uint32_t *__restrict__ emax = emax_ + blockIdx.z * bt.scr_stride;
+  const double *__restrict__ in = in_ + blockIdx.z * bt.in_stride;
   const size_t r = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
   uint32_t cnt[16];
 #pragma unroll

@@ -41,6 +41,8 @@ def oracle() -> C.CDLL:
         L.oz_gemm.restype, L.oz_gemm.argtypes = i32, [i32, i32, sz, sz, sz, dbl, vp, sz, vp, sz, dbl, vp, sz, u32,
                                                       vp, vp, vp, vp]
         L.oz_mantissa_loss.restype, L.oz_mantissa_loss.argtypes = None, [vp, sz, sz, vp, sz, i32, u32]
+        L.oz_gemm_complex_q.restype, L.oz_gemm_complex_q.argtypes = i32, [i32, i32, sz, sz, sz, vp, vp, sz, vp, sz, vp, vp,
+                                                                          sz, u32, i32]
         L.oz_gemm_complex.restype, L.oz_gemm_complex.argtypes = i32, [i32, i32, sz, sz, sz, vp, vp, sz, vp, sz, vp, vp,
                                                                       sz, u32]
         L.oz_auto_select_complex.restype = i32
@@ -103,15 +105,19 @@ def oracle_gemm(op_a: int, op_b: int, m: int, n: int, k: int, alpha: float, a: n
 
 
 def oracle_gemm_complex(op_a: int, op_b: int, m: int, n: int, k: int, alpha: complex, a: np.ndarray, lda: int,
-                        b: np.ndarray, ldb: int, beta: complex, c: np.ndarray, ldc: int, num_split: int) -> np.ndarray:
-    """a, b, c: complex128 flat column-major storage (ld in complex elements); returns the new C"""
+                        b: np.ndarray, ldb: int, beta: complex, c: np.ndarray, ldc: int, num_split: int,
+                        reference_beta_quirk: bool = False) -> np.ndarray:
+    """a, b, c: complex128 flat column-major storage (ld in complex elements); returns the new C.
+    reference_beta_quirk=True reproduces the reference's aliasing bug in C = beta*C (Im(beta) != 0 only; SURVEY
+    App. B.6) -- that is what its golden vectors contain; the product ships the corrected arithmetic (False)."""
     L = oracle()
     a = np.ascontiguousarray(a, dtype=np.complex128)
     b = np.ascontiguousarray(b, dtype=np.complex128)
     out = np.array(c, dtype=np.complex128, copy=True)
     al = np.array([alpha.real, alpha.imag], dtype=np.float64)
     be = np.array([beta.real, beta.imag], dtype=np.float64)
-    rc = L.oz_gemm_complex(op_a, op_b, m, n, k, _p(al), _p(a), lda, _p(b), ldb, _p(be), _p(out), ldc, num_split)
+    rc = L.oz_gemm_complex_q(op_a, op_b, m, n, k, _p(al), _p(a), lda, _p(b), ldb, _p(be), _p(out), ldc, num_split,
+                             int(reference_beta_quirk))
     assert rc == 0
     return out
 
