@@ -142,34 +142,6 @@ int ozk_gemm_i8_fused_batched(size_t m, size_t n, size_t k, size_t batch, const 
                               unsigned num_split, unsigned bits_per_int8, double alpha, double beta, double *c,
                               size_t ldc, size_t c_batch, void *stream);
 
-/* EXPERIMENTAL (not used by any default path; parity verified on hardware at the end of round 1 --
- * tests/test_gpu_queue.py, opt-in; performance work open -- DESIGN.md 10, profiles/r1_queue_experiment.txt):
- * ozk_gemm_i8_fused as ONE persistent launch that pops tiles from a device-side queue.  items[i] names a 256 x 256
- * tile of C (tile = tile_row | tile_col << 16) in the order the host wants them started; a tile starts only when
- * flags[a_flag] == epoch and flags[b_flag] == epoch (the host makes a block of A / B "ready" by writing epoch there
- * after its split has finished, e.g. with cuStreamWriteValue32), and every finished tile adds 16 to done[items[i].done]
- * (the host's copy-out stream waits for 16 x tiles of a block of C).  reserve_sms SMs are left free for the kernels
- * that produce the operands while this launch waits.  scratch: ozk_queue_scratch_words(num_items, reserve_sms)
- * uint32 of device memory, cleared by the launch; after completion scratch[1] != 0 means a readiness wait timed out. */
-typedef struct { uint32_t tile, a_flag, b_flag, done; } ozk_queue_item_t;
-size_t ozk_queue_scratch_words(size_t num_items, unsigned reserve_sms);
-int ozk_gemm_i8_fused_queue(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
-                            size_t pitch, const double *amax, const double *bmax, unsigned num_split,
-                            unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
-                            const ozk_queue_item_t *items, size_t num_items, const uint32_t *flags, uint32_t epoch,
-                            uint32_t *done, uint32_t *scratch, size_t scratch_words, unsigned reserve_sms,
-                            void *stream);
-
-/* EXPERIMENTAL, not yet run on hardware: a second launch that JOINS the queue of a running ozk_gemm_i8_fused_queue
- * launch (same arguments, same scratch -- not cleared), with num_pairs CTA pairs that record their items in the slot
- * rows first_pair ...: for the SMs that were kept free for the operand-producing kernels, once those are done. */
-int ozk_gemm_i8_fused_queue_join(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
-                                 size_t pitch, const double *amax, const double *bmax, unsigned num_split,
-                                 unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
-                                 const ozk_queue_item_t *items, size_t num_items, const uint32_t *flags,
-                                 uint32_t epoch, uint32_t *done, uint32_t *scratch, size_t scratch_words,
-                                 unsigned first_pair, unsigned num_pairs, void *stream);
-
 /* The general form of the fused launch -- real or complex C, whole matrix or block, single or strided batch,
  * scalars by value or in device memory; the ozk_gemm_i8_fused* functions above fill this struct.  Zero-initialise
  * it and set what applies.
@@ -316,13 +288,6 @@ int ozimmu_gemm_host(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_
  * edge `want` (0 = one block) -- ascending, edges[0] = 0, last = extent, inner edges multiples of 256, at most 17
  * entries.  Writes min(count, capacity) entries, returns count. */
 size_t ozimmu_host_block_edges(size_t extent, size_t want, int taper, size_t *edges, size_t capacity);
-
-/* Diagnostic: the work-item list of the experimental queue mode (ozk_gemm_i8_fused_queue) for an m x n product whose
- * operands are cut into blocks of want_rows / want_cols: items in start order, expected[a] = the done count arrival a's
- * part of C must reach (32 entries), *num_arrivals = blocks of A + blocks of B.  Flag indices: blocks of A first, then
- * blocks of B.  Writes min(count, capacity) items, returns count. */
-size_t ozimmu_host_queue_plan(size_t m, size_t n, size_t want_rows, size_t want_cols, int taper,
-                              ozk_queue_item_t *items, size_t capacity, uint32_t *expected, size_t *num_arrivals);
 
 /* Number of kernels this library launched since load (bench.py's gpu_launches). */
 unsigned long long ozimmu_launch_count(void);

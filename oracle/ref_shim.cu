@@ -14,6 +14,7 @@
 #include <exception>
 
 #include "split.hpp"   // reference src/split.hpp: split_int8<T>, get_mantissa_loss_total<T>
+#include "cublas_helper.hpp"   // reference src/cublas_helper.hpp: dgemm_f32<T> (compute mode `sgemm`)
 #include <ozimmu/ozimmu.hpp>
 
 #define OZREF_API extern "C" __attribute__((visibility("default")))
@@ -117,4 +118,17 @@ OZREF_API void ozref_print_profile(void *handle, const char *tag) {
   auto h = static_cast<mtk::ozimmu::handle_t>(handle);
   mtk::ozimmu::print_profiler_result(h, tag, true);
   mtk::ozimmu::clear_profiler_result(h);
+}
+
+// Compute mode `sgemm`: the reference only reaches it from its cuBLAS interposers (src/cublas.cu:169-186), which
+// call dgemm_f32<double> (src/cublas_helper.cu:84-134); mtk::ozimmu::gemm(..., sgemm) throws "Not implemented".
+OZREF_API int ozref_dgemm_f32(void *handle, int op_a, int op_b, size_t m, size_t n, size_t k, double alpha,
+                              const double *a, size_t lda, const double *b, size_t ldb, double beta, double *c,
+                              size_t ldc) {
+  return guarded([&] {
+    const cublasStatus_t st = mtk::ozimmu::dgemm_f32<double>(
+        static_cast<mtk::ozimmu::handle_t>(handle), op_a ? CUBLAS_OP_T : CUBLAS_OP_N, op_b ? CUBLAS_OP_T : CUBLAS_OP_N, m,
+        n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+    return st == CUBLAS_STATUS_SUCCESS ? 0 : 1;
+  });
 }

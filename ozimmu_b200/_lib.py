@@ -43,14 +43,6 @@ PROTOTYPES = {
     "ozk_split_int8_batched": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t,
                                        c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_uint, c_uint, c_size_t,
                                        c_void_p]),
-    "ozk_queue_scratch_words": (c_size_t, [c_size_t, c_uint]),
-    "ozk_gemm_i8_fused_queue": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
-                                        c_uint, c_uint, c_double, c_double, c_void_p, c_size_t, c_void_p, c_size_t,
-                                        c_void_p, C.c_uint32, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
-    "ozk_gemm_i8_fused_queue_join": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p,
-                                             c_void_p, c_uint, c_uint, c_double, c_double, c_void_p, c_size_t, c_void_p,
-                                             c_size_t, c_void_p, C.c_uint32, c_void_p, c_void_p, c_size_t, c_uint,
-                                             c_uint, c_void_p]),
     "ozk_mantissa_loss_strided": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int, c_uint,
                                           c_uint, c_void_p]),
     "ozk_gemm_i8_fused_ex": (c_int, [c_void_p, c_void_p]),
@@ -93,8 +85,6 @@ PROTOTYPES = {
     "ozimmu_gemm_host": (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t,
                                  c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int]),
     "ozimmu_host_block_edges": (c_size_t, [c_size_t, c_size_t, c_int, c_void_p, c_size_t]),
-    "ozimmu_host_queue_plan": (c_size_t, [c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_void_p, c_size_t, c_void_p,
-                                          c_void_p]),
     "ozimmu_launch_count": (C.c_ulonglong, []),
 }
 

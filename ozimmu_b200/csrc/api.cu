@@ -258,8 +258,6 @@ int mtk::ozimmu::destroy(handle_t h) {
   cudaFree(h->stage_a);
   cudaFree(h->stage_b);
   cudaFree(h->stage_c);
-  cudaFree(h->queue_dev);
-  cudaFreeHost(h->queue_host);
   for (cudaStream_t s : {h->aux_stream, h->h2d_stream, h->d2h_stream, h->compute_stream})
     if (s) cudaStreamDestroy(s);
   for (cudaStream_t s : h->product_stream)
@@ -573,66 +571,6 @@ int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const opera
   cudaEvent_t ev_a = h->ev_block_split[0][0];
   OZ_CUDA_CHECK(cudaEventRecord(ev_a, s));  // also orders the products after everything queued on s before this call
 
-  // ---- experimental (OZIMMU_B200_STREAMED_QUEUE=1; parity verified on hardware, not yet timed): ONE product launch fed by the tile
-  // queue instead of one launch per panel.  split(A) and the first panel's split run on the idle GPU;
-  // the queue launch then starts, and the later panels' splits run on the SMs it leaves free, each followed by a
-  // stream memory operation that publishes the panel.  Only after a call of the same configuration has gone through
-  // the multi-launch path (a kernel's first launch must not happen while the persistent kernel spins).
-  const std::uint64_t warm_key = (static_cast<std::uint64_t>(num_split) << 8) | (op_A == op_n ? 1u : 0u) |
-                                 (op_B == op_n ? 2u : 0u) |
-                                 (static_cast<std::uint64_t>(k <= 2048 ? 0 : k <= 4096 ? 1 : k <= 8192 ? 2 : k <= 16384 ? 3 : 4) << 4);
-  if (H::env_or("OZIMMU_B200_STREAMED_QUEUE", "0") == "1" && h->streamed_warm && h->streamed_warm_key == warm_key &&
-      H::stream_mem_ops_available() && (m + 255) / 256 <= 0xFFFF && (n + 255) / 256 <= 0xFFFF) {
-    std::vector<ozk_queue_item_t> items;
-    const std::size_t tm1 = (m + 255) / 256;
-    for (std::size_t p = 0; p < num_panels; p++) {
-      const std::size_t tn0 = col_edges[p] / 256, tn1 = (col_edges[p + 1] + 255) / 256;
-      for (std::size_t band = 0; band < tm1; band += 8)
-        for (std::size_t tn = tn0; tn < tn1; tn++)
-          for (std::size_t tm = band; tm < std::min(band + 8, tm1); tm++)
-            items.push_back({static_cast<std::uint32_t>(tm | (tn << 16)), 0u, static_cast<std::uint32_t>(1 + p),
-                             static_cast<std::uint32_t>(p)});
-    }
-    const unsigned reserve = static_cast<unsigned>(std::stoul(H::env_or("OZIMMU_B200_STREAMED_QUEUE_RESERVE_SMS", "8")));
-    const H::QueueBuffers q = H::queue_buffers(h, items.data(), items.size(), reserve);
-    cudaStream_t sp = h->product_stream[0];
-    H::stream_write_value32(s, q.flags + 0, q.epoch);  // A is split (stream order)
-    bool launched = false;
-    for (std::size_t p = 0; p < num_panels; p++) {
-      const std::size_t j0 = col_edges[p], nj = col_edges[p + 1] - j0;
-      OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, ready[p], 0));
-      if (nj != 0) {
-        const double *src = (op_B == op_n) ? b_ptr + j0 * ldb : b_ptr + j0;
-        OZ_KERNEL_CHECK(ozk_split_int8_block(b_sl, w.pitch, n, j0, bmax + j0, scr_b + j0, nj, k, src, ldb, op_B != op_n,
-                                             num_split, bits, 1, sb));
-      }
-      H::stream_write_value32(sb, q.flags + 1 + p, q.epoch);
-      if (!launched) {
-        // the queue launch starts once A and the first panel are split: nothing it needs first is still crawling
-        OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[1][0], sb));
-        OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_a, 0));
-        OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, h->ev_block_split[1][0], 0));
-        OZ_CUDA_CHECK(cudaMemcpyAsync(q.items, q.items_host, items.size() * sizeof(ozk_queue_item_t),
-                                      cudaMemcpyHostToDevice, sp));
-        OZ_CUDA_CHECK(cudaMemsetAsync(q.done, 0, 256, sp));
-        OZ_KERNEL_CHECK(ozk_gemm_i8_fused_queue(m, n, k, a_sl, b_sl, w.pitch, amax, bmax, num_split, bits, *alpha, *beta,
-                                                c_ptr, ldc, q.items, items.size(), q.flags, q.epoch, q.done, q.scratch,
-                                                q.scratch_words, reserve, sp));
-        launched = true;
-      }
-    }
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, sb));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_product_tail[0], sp));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_product_tail[0], 0));
-    mark_done(h, s);
-    // experimental mode: check the queue's error flag right away (this makes the call synchronous)
-    OZ_CUDA_CHECK(cudaStreamSynchronize(s));
-    std::uint32_t q_error = 0;
-    OZ_CUDA_CHECK(cudaMemcpy(&q_error, q.scratch + 1, sizeof(q_error), cudaMemcpyDeviceToHost));
-    if (q_error) throw std::runtime_error("ozIMMU: the tile queue timed out waiting for a panel of B");
-    return 0;
-  }
   bool used[handle::kProductStreams] = {};
   // one CTA pair per tile (OZIMMU_B200_STREAMED_ONE_TILE, default 1): the panels' launches interleave tile by tile and
   // whatever carries the next panel (a NCCL broadcast kernel, the panel's split) gets SMs whenever a tile ends
@@ -660,8 +598,6 @@ int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const opera
     OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_product_tail[r], 0));
   }
   mark_done(h, s);
-  h->streamed_warm = true;  // the kernels of this configuration have been launched once (see the queue mode above)
-  h->streamed_warm_key = warm_key;
   return 0;
 }
 

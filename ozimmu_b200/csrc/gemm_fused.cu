@@ -26,8 +26,10 @@
 //    share slice panels through L2.
 //  * Tile queue: entry x tiles_m x tiles_n (entry = index in a strided batch, ozk_gemm_i8_fused_batched), static
 //    round-robin over ceil(tiles / rounds) CTA pairs so that every pair owns the same number of tiles; block launches
-//    (ozk_gemm_i8_fused_block) address a rectangle of C inside the operands' slice planes.  A separate instantiation
-//    (kQueue, experimental, ozk_gemm_i8_fused_queue) takes its tiles from a device-side queue gated by ready flags.
+//    (ozk_gemm_i8_fused_block) address a rectangle of C inside the operands' slice planes and may run one CTA pair per
+//    tile (OZK_FUSED_ONE_TILE_PER_PAIR), which makes the hardware CTA scheduler the tile queue of the block pipelines.
+//    (A device-side tile queue gated by ready flags was built and measured in rounds 1-2 and removed: 28 ms against
+//    26 ms for the multi-launch pipeline at 8192^3 end to end, profiles/r2_e2e_sweep.txt.)
 #include <cstdlib>
 #include <mutex>
 
@@ -89,71 +91,6 @@ struct FusedParams {
   // has its own slices / row scales / C at these distances (bytes for the slices, doubles for the rest)
   uint32_t batch;
   unsigned long long a_batch_bytes, b_batch_bytes, amax_batch, bmax_batch, c_batch;
-  // device-side tile queue (kernel instantiations with kQueue; see TileSeq): work items in a host-defined order,
-  // each gated by two "operand block is ready" flags and counted into a "block of C is complete" counter
-  const uint4 *q_items;        // {tm | tn << 16, index of A's flag, index of B's flag, index of the done counter}
-  uint32_t q_num_items;
-  const uint32_t *q_flags;     // a block is ready when its flag == q_epoch
-  uint32_t q_epoch;
-  uint32_t *q_done;            // += 1 per epilogue warp per finished tile (16 per tile)
-  uint32_t *q_next;            // the queue head (zeroed before launch)
-  uint32_t *q_error;           // set when a readiness wait timed out
-  uint32_t *q_slots;           // [pairs][q_cap]: the items each pair took, in order (zeroed before launch)
-  uint32_t q_cap;
-  long long q_timeout;         // clocks a readiness wait may take
-  uint32_t q_pair0;            // slot row of this launch's first pair (a second launch may join a running queue)
-};
-
-constexpr uint32_t kQueueEnd = 0xFFFFFFFFu;
-
-// The tile sequence of one CTA pair, as seen by one warp (every role of both CTAs walks the same sequence).
-// Static: tile = pair_id + i * num_pairs.  Queue: the pair's fetcher warp (leader CTA's producer) pops the next item
-// from the device-wide head, waits until both operand blocks of the item are ready, and publishes the item in
-// q_slots[pair][i] with a release store; the other roles acquire it from there.  Only global memory is involved, so
-// the roles stay as decoupled as in the static case; a pair that starts late (its SMs were busy) simply takes fewer
-// items.  Every wait except the readiness wait is bounded by the fetcher's progress; the readiness wait is bounded
-// by q_timeout (then the queue is closed for this pair and q_error is set).
-template <bool kQueue>
-struct TileSeq {
-  uint32_t i = 0;  // queue: items taken so far; static: items taken x num_pairs
-  // whole warp calls; the result is warp-uniform
-  __device__ __forceinline__ bool next(const FusedParams &p, const uint32_t pair_id, const uint32_t num_pairs,
-                                       const uint32_t num_tiles, const bool fetcher, uint32_t &t) {
-    if constexpr (!kQueue) {
-      t = pair_id + i;   // i = tiles taken x num_pairs
-      i += num_pairs;
-      return t < num_tiles;
-    } else {
-      uint32_t v = 0;
-      if ((threadIdx.x & 31) == 0) {
-        uint32_t *slot = p.q_slots + static_cast<size_t>(pair_id) * p.q_cap + i;
-        if (fetcher) {
-          const uint32_t idx = (i + 1 < p.q_cap) ? atomicAdd(p.q_next, 1u) : p.q_num_items;
-          v = kQueueEnd;
-          if (idx < p.q_num_items) {
-            const uint4 it = __ldg(p.q_items + idx);
-            const long long t0 = clock64();
-            v = idx + 1;
-            while (ptx::ld_acquire_gpu(p.q_flags + it.y) != p.q_epoch || ptx::ld_acquire_gpu(p.q_flags + it.z) != p.q_epoch) {
-              __nanosleep(200);
-              if (clock64() - t0 > p.q_timeout) {
-                atomicExch(p.q_error, 1u);
-                v = kQueueEnd;
-                break;
-              }
-            }
-          }
-          ptx::st_release_gpu(slot, v);
-        } else {
-          while ((v = ptx::ld_acquire_gpu(slot)) == 0) __nanosleep(100);
-        }
-      }
-      v = __shfl_sync(0xffffffffu, v, 0);
-      i++;
-      t = v - 1;
-      return v != kQueueEnd;
-    }
-  }
 };
 
 // reference src/config.cu:85-92: for sum = 2..s+1, for j = 1..sum-1: (A_id=j, B_id=sum-j)
@@ -215,18 +152,6 @@ __device__ __forceinline__ void tile_coords(const FusedParams &p, uint32_t t, ui
   tn = r / rows;
 }
 
-// queue mode: item -> (tile row, tile column, done counter); one problem, no batch
-__device__ __forceinline__ void item_coords(const FusedParams &p, uint32_t item, uint32_t &tm, uint32_t &tn,
-                                            uint32_t &done_idx) {
-  // whole warp calls.  The values come from memory, so the compiler cannot see that they are warp-uniform; a shuffle
-  // from lane 0 tells it (as for `warp` / `rank` in the kernel): the tile coordinates then live in uniform registers,
-  // which the epilogue needs -- its vector registers are all taken by the FP64 accumulators.
-  const uint4 it = __ldg(p.q_items + item);
-  tm = __shfl_sync(0xffffffffu, it.x & 0xFFFFu, 0);
-  tn = __shfl_sync(0xffffffffu, it.x >> 16, 0);
-  done_idx = __shfl_sync(0xffffffffu, it.w, 0);
-}
-
 template <uint32_t BN_>
 struct PairCfg {
   static_assert(BN_ % 16 == 0 && BN_ >= 128 && BN_ <= 256, "UMMA M=256 needs N % 16 == 0, N <= 256");
@@ -252,7 +177,7 @@ struct PairCfg {
   static constexpr uint32_t kRegsEpi = (BN_ == 128) ? 224 : 232;
 };
 
-template <uint32_t BN_, bool kQueue = false>
+template <uint32_t BN_>
 __global__ void __launch_bounds__(kThreads, 1)
 oz_gemm_pair_kernel(const FusedParams p) {
   using Cfg = PairCfg<BN_>;
@@ -277,7 +202,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0) & 1u;  // 0 = leader (issues the MMAs)
-  const uint32_t pair_id = (blockIdx.x >> 1) + (kQueue ? p.q_pair0 : 0u);
+  const uint32_t pair_id = blockIdx.x >> 1;
   const uint32_t num_pairs = gridDim.x >> 1;
   const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const uint32_t steps_per_tile = (p.single_a != 0 ? 1u : p.num_split * (p.num_split + 1) / 2) * p.k_blocks * p.groups;
@@ -314,18 +239,11 @@ oz_gemm_pair_kernel(const FusedParams p) {
       // the rest of the kernel on the first timeout.
       const uint32_t tiles_max = (num_tiles + num_pairs - 1) / num_pairs;
       const uint32_t pairs_last = num_tiles - (tiles_max - 1) * num_pairs;  // pairs that own tiles_max tiles
-      bool lockstep = !kQueue && p.sync_ctr != nullptr && rank == 0;
+      bool lockstep = p.sync_ctr != nullptr && rank == 0;
       uint32_t g = 0;
-      TileSeq<kQueue> seq;
-      for (uint32_t t; seq.next(p, pair_id, num_pairs, num_tiles, rank == 0, t);) {
+      for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {   // static round-robin tile list of this pair
         uint32_t tm, tn, entry = 0;
-        if constexpr (kQueue) {
-          uint32_t done_idx;
-          item_coords(p, t, tm, tn, done_idx);
-          ptx::fence_proxy_async();  // the ready flags were observed with generic loads; the slices are read by bulk copies
-        } else {
-          tile_coords(p, t, tm, tn, entry);
-        }
+        tile_coords(p, t, tm, tn, entry);
         const int8_t *a_base = p.a_slices + static_cast<size_t>(entry) * p.a_batch_bytes;
         const int8_t *b_base = p.b_slices + static_cast<size_t>(entry) * p.b_batch_bytes;
         // this CTA's 128 rows of A (one 16 KB tile per k-block) and its BN/2 rows of B: rows [b_row0, b_row0 + BN/2) of the
@@ -391,8 +309,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
       constexpr uint32_t idesc = ptx::make_i8_idesc(2 * BM, BN_);
       const bool issuer = ptx::elect_one();
       uint32_t stage = 0, ph = 0, buf = 0, bph = 0;
-      TileSeq<kQueue> seq;
-      for (uint32_t t; seq.next(p, pair_id, num_pairs, num_tiles, false, t);) {
+      for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
         for (uint32_t grp = 0; grp < p.groups; grp++)
         for (PairIter it(p); it.valid(); it.next()) {
           ptx::mbar_wait_cluster(tempty_bar(buf), bph ^ 1u);
@@ -431,13 +348,8 @@ oz_gemm_pair_kernel(const FusedParams p) {
           if (++stage == kStagesP) { stage = 0; ph ^= 1u; }
         }
       };
-      if constexpr (kQueue) {
-        TileSeq<kQueue> seq;
-        for (uint32_t t; seq.next(p, pair_id, num_pairs, num_tiles, false, t);) relay_steps(steps_per_tile);
-      } else {
-        const uint32_t tiles_mine = (num_tiles > pair_id) ? (num_tiles - pair_id + num_pairs - 1) / num_pairs : 0;
-        relay_steps(static_cast<uint64_t>(tiles_mine) * steps_per_tile);
-      }
+      const uint32_t tiles_mine = (num_tiles > pair_id) ? (num_tiles - pair_id + num_pairs - 1) / num_pairs : 0;
+      relay_steps(static_cast<uint64_t>(tiles_mine) * steps_per_tile);
     }
   } else {
     // ===================== epilogue (both CTAs): 8 warps, FP64 accumulators in registers (+ SMEM) ==========
@@ -446,18 +358,11 @@ oz_gemm_pair_kernel(const FusedParams p) {
     const uint32_t half = (warp - 4u) >> 2;  // which column half of the tile
     const bool raw = p.single_a != 0;
     uint32_t pc = 0;
-    TileSeq<kQueue> seq;
-    for (uint32_t t; seq.next(p, pair_id, num_pairs, num_tiles, false, t);) {
-      // Queue mode: nothing that depends on the tile may stay live across the product loop (the FP64 accumulators
-      // take every register, and an item read from memory cannot be rematerialised the way pair_id + i * num_pairs
-      // can): the coordinates are looked up AFTER the products, from the slot this pair recorded the item in.
-      uint32_t tm = 0, tn = 0, entry = 0, row = 0, col0 = 0;
-      if constexpr (!kQueue) {
-        tile_coords(p, t, tm, tn, entry);
-        row = tm * 2 * BM + rank * BM + q * 32u + lane;
-        col0 = tn * BN_ + half * kCols;
-      }
-      uint32_t done_idx = 0;
+    for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
+      uint32_t tm, tn, entry;
+      tile_coords(p, t, tm, tn, entry);
+      const uint32_t row = tm * 2 * BM + rank * BM + q * 32u + lane;
+      const uint32_t col0 = tn * BN_ + half * kCols;
       double acc[kRegCols];
       // this thread's spill accumulators: columns [half*kSpillCols, +kSpillCols) of the [col][row] array
       double *spill = reinterpret_cast<double *>(smem_raw + (spill_base - ptx::smem_u32(smem_raw))) +
@@ -506,7 +411,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
                   }
                 }
               }
-            } else if (!kQueue && row < p.m) {
+            } else if (row < p.m) {
 #pragma unroll
               for (uint32_t j = 0; j < nv; j++) {
                 const uint32_t col = col0 + c * 16 + j;
@@ -522,13 +427,6 @@ oz_gemm_pair_kernel(const FusedParams p) {
             if (rank == 0) ptx::mbar_arrive(tempty_bar(buf));
             else ptx::mbar_arrive_remote(ptx::mapa(tempty_bar(buf), 0));
           }
-        }
-        if constexpr (kQueue) {
-          const uint32_t item =
-              __shfl_sync(0xffffffffu, ptx::ld_acquire_gpu(p.q_slots + static_cast<size_t>(pair_id) * p.q_cap + (seq.i - 1)), 0) - 1u;
-          item_coords(p, item, tm, tn, done_idx);
-          row = tm * 2 * BM + rank * BM + q * 32u + lane;
-          col0 = tn * BN_ + half * kCols;
         }
         if (!raw && row < p.m) {
           // alpha / beta by value, or read here from device memory (cuBLAS device pointer mode)
@@ -590,13 +488,6 @@ oz_gemm_pair_kernel(const FusedParams p) {
             }
           }
         }
-      }
-      if constexpr (kQueue) {
-        // this warp's part of the tile is in memory: count it into the tile's block of C (the host's D2H stream waits
-        // for 16 counts per tile of the block; the copy engines read through L2, system scope to be safe)
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) atomicAdd(p.q_done + done_idx, 1u);
       }
     }
   }
@@ -762,68 +653,6 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   return 0;
 }
 
-// Queue-mode launch: 256-wide tiles, grid = the resident pairs minus the SMs kept free for the kernels that make the
-// operands ready (the split kernels run WHILE this kernel waits for them).
-// join_first_pair >= 0: a second launch on the SAME queue (scratch is not cleared, its pairs use the slot rows
-// join_first_pair ...): started once the SMs that were left to the operand-producing kernels are free again.
-int launch_pair_queue(const FusedParams &p0, unsigned reserve_sms, uint32_t *scratch, size_t scratch_words,
-                      cudaStream_t stream, int join_first_pair = -1, unsigned join_pairs = 0) {
-  using Cfg = PairCfg<256>;
-  FusedParams p = p0;
-  p.tiles_m = ceil_div_u32(p.m, 2 * BM);
-  p.tiles_n = ceil_div_u32(p.n, 256);
-  p.group_m = 8;
-  p.rt_a = static_cast<uint32_t>(slice_row_tiles(p.m));
-  p.rt_b = static_cast<uint32_t>(slice_row_tiles(p.n));
-  p.batch = 1;
-  p.sync_ctr = nullptr;
-  p.b_rows = p.rt_b * static_cast<uint32_t>(kTileRows);
-  auto kern = oz_gemm_pair_kernel<256, true>;
-  int dev = 0, sms = 0, clock_khz = 0;
-  OZ_CUDA_TRY(cudaGetDevice(&dev));
-  OZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  OZ_CUDA_TRY(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, dev));
-  if (dev < 0 || dev >= kMaxDevices) return static_cast<int>(cudaErrorInvalidDevice);
-  static PerDeviceOnce once;
-  {
-    std::lock_guard<std::mutex> lock(once.mu);
-    if (!once.done[dev]) {
-      OZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-      once.done[dev] = true;
-    }
-  }
-  const uint32_t usable = static_cast<uint32_t>(sms) > reserve_sms + 2 ? static_cast<uint32_t>(sms) - reserve_sms : 2u;
-  uint32_t pairs = usable / 2;
-  if (pairs > p.q_num_items) pairs = p.q_num_items;
-  if (join_first_pair >= 0) pairs = join_pairs;
-  if (pairs == 0) return 0;
-  // scratch: [0] queue head, [1] error flag, [2...] slots[pairs of all launches][num_items + 1]
-  p.q_cap = p.q_num_items + 1;
-  p.q_pair0 = join_first_pair >= 0 ? static_cast<uint32_t>(join_first_pair) : 0u;
-  const size_t need = 2 + static_cast<size_t>(p.q_pair0 + pairs) * p.q_cap;
-  if (scratch == nullptr || scratch_words < need) return static_cast<int>(cudaErrorInvalidValue);
-  if (join_first_pair < 0) OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, scratch_words * sizeof(uint32_t), stream));
-  p.q_next = scratch;
-  p.q_error = scratch + 1;
-  p.q_slots = scratch + 2;
-  p.q_timeout = static_cast<long long>(clock_khz) * 1000ll * 4ll;  // ~4 s of SM clocks
-  cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cfg.gridDim = dim3(pairs * 2);
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  OZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
-  count_launch(1);
-  return 0;
-}
-
 // tile widths built into the library (UMMA N of the CTA pair): 256 and 128 are the defaults, the widths in between
 // trade MACs per delivered byte for a deeper operand ring (PairCfg) and a different tile count
 constexpr int kTileWidths[] = {256, 240, 224, 208, 192, 128};
@@ -834,8 +663,7 @@ bool tile_width_ok(int bn) {
   return false;
 }
 
-// OZIMMU_B200_TILE_N=<width>: force the tile width (read once); OZIMMU_B200_TILE_CANDIDATES=a,b,..: the widths the
-// per-problem choice considers (default 256,128)
+// OZIMMU_B200_TILE_N=<width>: force the tile width (read once)
 int env_tile_width() {
   static const int v = [] {
     const char *e = std::getenv("OZIMMU_B200_TILE_N");
@@ -848,19 +676,21 @@ int env_tile_width() {
 int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
   int bn = g_tile_override ? g_tile_override : env_tile_width();
   if (bn == 0) {
-    // The kernel is bound by operand delivery into the SMs, so a launch costs about
-    // rounds x bytes-per-k-block-per-SM = ceil(tiles / resident pairs) x (128 + BN/2).  BN=256 delivers the
-    // fewest bytes per MAC; a narrower tile wins when it fills more SMs.
+    // A launch costs rounds x (time of one tile) with rounds = ceil(tiles / resident pairs).  Measured at 8192^3, s = 9
+    // (profiles/r2_sweep_tile_width.txt): a round of 256 / 240 / 224 / 208 / 192-wide tiles takes 1.28 / 1.19 / 1.20 /
+    // 1.08 / 1.02 ms, i.e. time per tile ~ 55 + BN -- between the tensor-pipe time (~ BN) and the operand-delivery time
+    // (~ 128 + BN/2): BN = 256 moves the fewest bytes per MAC and wins whenever the tile count quantises alike
+    // (8192^3: 14 rounds); a narrower tile wins when it needs fewer rounds x width (4096^3: 192 -> 5 x 247 < 4 x 311).
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint64_t pairs = static_cast<uint64_t>(sms > 1 ? sms / 2 : 1);
     uint64_t best_cost = ~0ull;
-    for (int cand : {256, 128}) {
+    for (int cand : kTileWidths) {
       const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 2 * BM)) * ceil_div_u32(p.n, cand) *
                              (p.batch ? p.batch : 1);
-      const uint64_t cost = ((tiles + pairs - 1) / pairs) * (128 + cand / 2);
-      if (cost < best_cost) {
+      const uint64_t cost = ((tiles + pairs - 1) / pairs) * (55 + cand);
+      if (cost < best_cost) {   // ties go to the wider tile (kTileWidths is descending)
         best_cost = cost;
         bn = cand;
       }
@@ -1008,66 +838,6 @@ extern "C" int ozk_gemm_i8_fused_batched(size_t m, size_t n, size_t k, size_t ba
   a.a_batch_bytes = a_batch_bytes, a.b_batch_bytes = b_batch_bytes;
   a.amax_batch = amax_batch, a.bmax_batch = bmax_batch, a.c_batch = c_batch;
   return ozk_gemm_i8_fused_ex(&a, stream);
-}
-
-extern "C" size_t ozk_queue_scratch_words(size_t num_items, unsigned reserve_sms) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  (void)reserve_sms;  // sized for the full grid
-  return 2 + static_cast<size_t>(sms / 2 + 1) * (num_items + 1);
-}
-
-extern "C" int ozk_gemm_i8_fused_queue(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
-                                       size_t pitch, const double *amax, const double *bmax, unsigned num_split,
-                                       unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
-                                       const ozk_queue_item_t *items, size_t num_items, const uint32_t *flags,
-                                       uint32_t epoch, uint32_t *done, uint32_t *scratch, size_t scratch_words,
-                                       unsigned reserve_sms, void *stream) {
-  if (m == 0 || n == 0 || num_items == 0) return 0;
-  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m || items == nullptr || flags == nullptr ||
-      done == nullptr || num_items >= (1ull << 31) || (m + 255) / 256 > 0xFFFF || (n + 255) / 256 > 0xFFFF)
-    return static_cast<int>(cudaErrorInvalidValue);
-  static_assert(sizeof(ozk_queue_item_t) == sizeof(uint4), "queue items are read as uint4");
-  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices, b_slices, num_split, bits_per_int8);
-  p.alpha = alpha;
-  p.beta = beta;
-  p.c = c;
-  p.ldc = ldc;
-  p.amax = amax;
-  p.bmax = bmax;
-  p.q_items = reinterpret_cast<const uint4 *>(items);
-  p.q_num_items = static_cast<uint32_t>(num_items);
-  p.q_flags = flags;
-  p.q_epoch = epoch;
-  p.q_done = done;
-  return oz::launch_pair_queue(p, reserve_sms, scratch, scratch_words, static_cast<cudaStream_t>(stream));
-}
-
-extern "C" int ozk_gemm_i8_fused_queue_join(size_t m, size_t n, size_t k, const int8_t *a_slices, const int8_t *b_slices,
-                                            size_t pitch, const double *amax, const double *bmax, unsigned num_split,
-                                            unsigned bits_per_int8, double alpha, double beta, double *c, size_t ldc,
-                                            const ozk_queue_item_t *items, size_t num_items, const uint32_t *flags,
-                                            uint32_t epoch, uint32_t *done, uint32_t *scratch, size_t scratch_words,
-                                            unsigned first_pair, unsigned num_pairs, void *stream) {
-  if (m == 0 || n == 0 || num_items == 0 || num_pairs == 0) return 0;
-  if (!oz::valid_common(m, n, k, pitch, num_split, bits_per_int8) || ldc < m || items == nullptr || flags == nullptr ||
-      done == nullptr || num_items >= (1ull << 31) || first_pair > 4096 || num_pairs > 4096)
-    return static_cast<int>(cudaErrorInvalidValue);
-  oz::FusedParams p = oz::base_params(m, n, pitch, a_slices, b_slices, num_split, bits_per_int8);
-  p.alpha = alpha;
-  p.beta = beta;
-  p.c = c;
-  p.ldc = ldc;
-  p.amax = amax;
-  p.bmax = bmax;
-  p.q_items = reinterpret_cast<const uint4 *>(items);
-  p.q_num_items = static_cast<uint32_t>(num_items);
-  p.q_flags = flags;
-  p.q_epoch = epoch;
-  p.q_done = done;
-  return oz::launch_pair_queue(p, 0, scratch, scratch_words, static_cast<cudaStream_t>(stream),
-                               static_cast<int>(first_pair), num_pairs);
 }
 
 extern "C" int ozk_scale_c_ex(size_t m, size_t n, const double beta[2], const double *beta_dev, int complex_c, void *c,

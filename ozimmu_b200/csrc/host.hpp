@@ -13,7 +13,6 @@
 #include <cublas_v2.h>  // types only: every cuBLAS entry point is resolved with dlsym at run time
 #include <cuda_runtime.h>
 #include <ozimmu/ozimmu.hpp>
-#include "ozimmu_b200.h"  // ozk_queue_item_t
 
 namespace oz {
 namespace host {
@@ -86,19 +85,6 @@ void gemm_in_f32(mtk::ozimmu::handle *h, cublasHandle_t cublas, mtk::ozimmu::ope
                  const double *a, std::size_t lda, const double *b, std::size_t ldb, const double *beta, double *c,
                  std::size_t ldc, mtk::ozimmu::element_kind_t kind);
 
-// ---- experimental tile queue (host_e2e.cu): stream memory operations and the queue's device block ----------------
-bool stream_mem_ops_available();   // cuStreamWriteValue32 / cuStreamWaitValue32 found at run time
-void stream_write_value32(cudaStream_t s, std::uint32_t *dev_addr, std::uint32_t value);      // throws on failure
-void stream_wait_value32_geq(cudaStream_t s, std::uint32_t *dev_addr, std::uint32_t value);   // throws on failure
-struct QueueBuffers {
-  std::uint32_t *flags = nullptr, *done = nullptr, *scratch = nullptr;   // device
-  ozk_queue_item_t *items = nullptr;                                     // device
-  const ozk_queue_item_t *items_host = nullptr;                          // pinned copy of the items (upload source)
-  std::size_t scratch_words = 0;
-  std::uint32_t epoch = 0;
-};
-QueueBuffers queue_buffers(mtk::ozimmu::handle *h, const ozk_queue_item_t *items, std::size_t nitems, unsigned reserve_sms);
-
 // reference src/config.cu:85-92: the ordered (A_id, B_id) list of one fp64_int8_S product sweep
 std::vector<std::pair<int, int>> pair_list(unsigned num_split);
 
@@ -145,15 +131,6 @@ struct mtk::ozimmu::handle {
   cudaEvent_t ev_block_in[2][kMaxBlocks] = {}, ev_block_split[2][kMaxBlocks] = {};  // [0] = A, [1] = B
   std::vector<cudaEvent_t> ev_rect_out;                                             // one per fused launch, grown on demand
   cudaEvent_t ev_product_tail[kProductStreams] = {};
-  // experimental queue mode of ozimmu_gemm_host (OZIMMU_B200_E2E_QUEUE=1): device block [flags | done | items |
-  // kernel scratch], pinned staging for the items, the epoch that marks a flag as "ready in this call"
-  void *queue_dev = nullptr, *queue_host = nullptr;
-  std::size_t queue_dev_bytes = 0, queue_host_bytes = 0;
-  std::uint32_t queue_epoch = 0;
-  std::uint64_t queue_warm_key = 0, streamed_warm_key = 0;
-  bool streamed_warm = false;  // same for gemm_streamed_b's queue mode
-  bool queue_warm = false;  // every kernel of the path has been launched once (lazy module loading must not happen
-                            // while the persistent kernel spins)
   // alpha / beta of gemm() are device pointers (set by the interposers when the application's cuBLAS handle is in
   // CUBLAS_POINTER_MODE_DEVICE; the reference dereferences them on the host regardless, src/gemm.cu:405)
   bool scalars_on_device = false;

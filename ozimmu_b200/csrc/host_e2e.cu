@@ -24,8 +24,6 @@
 #include <cstdlib>
 #include <vector>
 
-#include <cuda.h>  // types of the stream memory operations; the entry points are looked up at run time
-
 #include "host.hpp"
 #include "oz_common.cuh"
 #include "ozimmu_b200.h"
@@ -113,141 +111,6 @@ void copy_matrix(double *dst, const double *src, std::size_t ld, std::size_t row
     OZ_CUDA_CHECK(cudaMemcpy2DAsync(dst, sizeof(double) * ld, src, sizeof(double) * ld, sizeof(double) * rows, cols,
                                     kind, st));
   }
-}
-
-// ---- experimental: one persistent product launch fed by a device-side tile queue ---------------------------------
-// (OZIMMU_B200_E2E_QUEUE=1; parity verified on hardware at the end of round 1, but slower than the multi-launch
-// pipeline: the block splits crawl on the few reserved SMs; DESIGN.md 10, profiles/r1_queue_experiment.txt.)  The schedule is the same
-// as below -- blocks of A and B travel alternately, each is split as it lands -- but instead of one product launch
-// per arrival there is ONE launch (ozk_gemm_i8_fused_queue) whose CTA pairs pop 256 x 256 tiles from a queue in
-// arrival-compatible order.  A tile starts when the "ready" flags of its block of A and of B carry this call's
-// epoch; the flags are written by stream memory operations queued behind the blocks' split kernels, which run on
-// the few SMs the product launch leaves free.  Every finished tile counts into its arrival's "done" counter, and
-// the copy-out stream waits for the counter with a stream memory operation before it copies that part of C.
-struct StreamMemOps {
-  using Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-  Fn write = nullptr, wait = nullptr;
-};
-
-void ensure_stage(void **ptr, std::size_t *have, std::size_t need);
-
-const StreamMemOps &stream_mem_ops() {
-  static const StreamMemOps ops = [] {
-    StreamMemOps o;
-    cudaDriverEntryPointQueryResult q;
-    void *fn = nullptr;
-    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      o.write = reinterpret_cast<StreamMemOps::Fn>(fn);
-    fn = nullptr;
-    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      o.wait = reinterpret_cast<StreamMemOps::Fn>(fn);
-    cudaGetLastError();
-    return o;
-  }();
-  return ops;
-}
-
-void mem_op_check(CUresult r, const char *what) {
-  if (r != CUDA_SUCCESS) throw std::runtime_error(std::string("ozIMMU: ") + what + " failed with CUresult " + std::to_string(r));
-}
-
-}  // namespace
-
-bool oz::host::stream_mem_ops_available() { return stream_mem_ops().write != nullptr && stream_mem_ops().wait != nullptr; }
-
-void oz::host::stream_write_value32(cudaStream_t s, std::uint32_t *dev_addr, std::uint32_t value) {
-  mem_op_check(stream_mem_ops().write(s, reinterpret_cast<CUdeviceptr>(dev_addr), value, CU_STREAM_WRITE_VALUE_DEFAULT),
-               "cuStreamWriteValue32");
-}
-
-void oz::host::stream_wait_value32_geq(cudaStream_t s, std::uint32_t *dev_addr, std::uint32_t value) {
-  mem_op_check(stream_mem_ops().wait(s, reinterpret_cast<CUdeviceptr>(dev_addr), value, CU_STREAM_WAIT_VALUE_GEQ),
-               "cuStreamWaitValue32");
-}
-
-// Device block of the tile queue, [flags 64 x u32][done 64 x u32][items][kernel scratch], plus the pinned staging the
-// items are uploaded from; grows on demand.  Copies `items` into the staging and opens a new epoch.
-oz::host::QueueBuffers oz::host::queue_buffers(mtk::ozimmu::handle *h, const ozk_queue_item_t *items, std::size_t nitems,
-                                               unsigned reserve_sms) {
-  QueueBuffers q;
-  q.scratch_words = ozk_queue_scratch_words(nitems, reserve_sms);
-  const std::size_t off_done = 256, off_items = 512;
-  const std::size_t off_scratch = (off_items + nitems * sizeof(ozk_queue_item_t) + 255) / 256 * 256;
-  const std::size_t total = off_scratch + q.scratch_words * sizeof(std::uint32_t);
-  if (total > h->queue_dev_bytes) {
-    ensure_stage(&h->queue_dev, &h->queue_dev_bytes, total);
-    OZ_CUDA_CHECK(cudaMemset(h->queue_dev, 0, total));  // flags start at 0; epochs start at 1
-    h->queue_epoch = 0;
-  }
-  if (nitems * sizeof(ozk_queue_item_t) > h->queue_host_bytes) {
-    if (h->queue_host) OZ_CUDA_CHECK(cudaFreeHost(h->queue_host));
-    h->queue_host = nullptr;
-    h->queue_host_bytes = 0;
-    OZ_CUDA_CHECK(cudaMallocHost(&h->queue_host, nitems * sizeof(ozk_queue_item_t)));
-    h->queue_host_bytes = nitems * sizeof(ozk_queue_item_t);
-  }
-  std::copy(items, items + nitems, static_cast<ozk_queue_item_t *>(h->queue_host));
-  if (++h->queue_epoch == 0) {  // wrapped: stale flags could match again
-    OZ_CUDA_CHECK(cudaDeviceSynchronize());
-    OZ_CUDA_CHECK(cudaMemset(h->queue_dev, 0, 512));
-    h->queue_epoch = 1;
-  }
-  q.epoch = h->queue_epoch;
-  char *qd = static_cast<char *>(h->queue_dev);
-  q.flags = reinterpret_cast<std::uint32_t *>(qd);
-  q.done = reinterpret_cast<std::uint32_t *>(qd + off_done);
-  q.items = reinterpret_cast<ozk_queue_item_t *>(qd + off_items);
-  q.scratch = reinterpret_cast<std::uint32_t *>(qd + off_scratch);
-  q.items_host = static_cast<const ozk_queue_item_t *>(h->queue_host);
-  return q;
-}
-
-namespace {
-
-struct QueuePlan {
-  std::vector<ozk_queue_item_t> items;
-  std::vector<std::uint32_t> expected;   // per arrival: 16 x tiles of its rectangle (0 = no rectangle)
-};
-
-// Arrival order B0 A0 B1 A1 ... (as the multi-launch pipeline); the rectangle an arrival completes contributes its
-// tiles in bands of 8 tile rows, column by column inside a band, so that the pairs working side by side share panels.
-QueuePlan plan_queue(const std::vector<std::size_t> &ae, const std::vector<std::size_t> &be,
-                     const std::vector<std::pair<int, std::size_t>> &order) {
-  QueuePlan plan;
-  const std::size_t nab = ae.size() - 1;
-  auto block_of = [](const std::vector<std::size_t> &edges, std::size_t row) {
-    return static_cast<std::uint32_t>(std::upper_bound(edges.begin(), edges.end(), row) - edges.begin() - 1);
-  };
-  std::size_t have_a = 0, have_b = 0;
-  for (std::size_t arrival = 0; arrival < order.size(); arrival++) {
-    std::size_t r0, r1, c0, c1;
-    if (order[arrival].first) {  // a block of B: all rows of A that are there x this block's columns
-      r0 = 0, r1 = ae[have_a], c0 = be[order[arrival].second], c1 = be[order[arrival].second + 1];
-      have_b++;
-    } else {
-      r0 = ae[order[arrival].second], r1 = ae[order[arrival].second + 1], c0 = 0, c1 = be[have_b];
-      have_a++;
-    }
-    std::uint32_t tiles = 0;
-    if (r1 > r0 && c1 > c0) {
-      const std::size_t tm0 = r0 / 256, tm1 = (r1 + 255) / 256, tn0 = c0 / 256, tn1 = (c1 + 255) / 256;
-      for (std::size_t band = tm0; band < tm1; band += 8)
-        for (std::size_t tn = tn0; tn < tn1; tn++)
-          for (std::size_t tm = band; tm < std::min(band + 8, tm1); tm++) {
-            ozk_queue_item_t it;
-            it.tile = static_cast<std::uint32_t>(tm | (tn << 16));
-            it.a_flag = block_of(ae, tm * 256);
-            it.b_flag = static_cast<std::uint32_t>(nab) + block_of(be, tn * 256);
-            it.done = static_cast<std::uint32_t>(arrival);
-            plan.items.push_back(it);
-            tiles++;
-          }
-    }
-    plan.expected.push_back(16u * tiles);
-  }
-  return plan;
 }
 
 int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n, std::size_t k,
@@ -407,78 +270,6 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     else order.push_back({0, ia++});
   }
 
-  // ---- experimental queue mode: one persistent product launch instead of one launch per arrival ----------------
-  // Only after a call with the same kernels has gone through the multi-launch path: a kernel's first launch loads
-  // its module lazily, which must not happen while the persistent kernel spins on the flags that kernel feeds.
-  const std::uint64_t warm_key = (static_cast<std::uint64_t>(s) << 8) | (op_a == op_n ? 1u : 0u) | (op_b == op_n ? 2u : 0u) |
-                                 (static_cast<std::uint64_t>(k <= 2048 ? 0 : k <= 4096 ? 1 : k <= 8192 ? 2 : k <= 16384 ? 3 : 4) << 4);
-  if (env_size("OZIMMU_B200_E2E_QUEUE", 0) != 0 && h->queue_warm && h->queue_warm_key == warm_key &&
-      H::stream_mem_ops_available() &&
-      (m + 255) / 256 <= 0xFFFF && (n + 255) / 256 <= 0xFFFF) {
-    std::vector<std::pair<int, std::size_t>> ord;
-    for (const Arrival &x : order) ord.emplace_back(x.which, x.idx);
-    const QueuePlan plan = plan_queue(ae, be, ord);
-    const std::size_t nitems = plan.items.size();
-    const unsigned reserve = static_cast<unsigned>(env_size("OZIMMU_B200_E2E_QUEUE_RESERVE_SMS", 4));
-    const H::QueueBuffers qb_ = H::queue_buffers(h, plan.items.data(), nitems, reserve);
-    const std::size_t scratch_words = qb_.scratch_words;
-    const std::uint32_t epoch = qb_.epoch;
-    std::uint32_t *flags_dev = qb_.flags, *done_dev = qb_.done, *scratch_dev = qb_.scratch;
-    ozk_queue_item_t *items_dev = qb_.items;
-    cudaStream_t sp = h->product_stream[0];
-    if (h->has_pending) OZ_CUDA_CHECK(cudaStreamWaitEvent(sp, h->ev_done, 0));
-    OZ_CUDA_CHECK(cudaMemcpyAsync(items_dev, h->queue_host, nitems * sizeof(ozk_queue_item_t), cudaMemcpyHostToDevice, sp));
-    OZ_CUDA_CHECK(cudaMemsetAsync(done_dev, 0, 256, sp));
-    OZ_KERNEL_CHECK(ozk_gemm_i8_fused_queue(m, n, k, a_sl, b_sl, w.pitch, amax, bmax, s, bits, alpha, beta, dc, ldc, items_dev,
-                                            nitems, flags_dev, epoch, done_dev, scratch_dev, scratch_words, reserve, sp));
-    for (const Arrival &x : order) x.which ? copy_b_block(x.idx) : copy_a_block(x.idx);
-    std::size_t qa = 0, qb = 0;
-    for (std::size_t arrival = 0; arrival < order.size(); arrival++) {
-      const Arrival &x = order[arrival];
-      std::size_t r0, r1, c0, c1, flag;
-      if (x.which) {
-        split_b_block(x.idx);
-        r0 = 0, r1 = ae[qa], c0 = be[x.idx], c1 = be[x.idx + 1], flag = nab + x.idx;
-        qb++;
-      } else {
-        split_a_block(x.idx);
-        r0 = ae[x.idx], r1 = ae[x.idx + 1], c0 = 0, c1 = be[qb], flag = x.idx;
-        qa++;
-      }
-      // the block's slices and row scales are complete: publish it to the running product launch
-      H::stream_write_value32(sc, flags_dev + flag, epoch);
-      if (plan.expected[arrival] == 0) continue;
-      H::stream_wait_value32_geq(sout, done_dev + arrival, plan.expected[arrival]);
-      copy_matrix(c + c0 * ldc + r0, dc + c0 * ldc + r0, ldc, r1 - r0, c1 - c0, cudaMemcpyDeviceToHost, sout);
-    }
-    // OZIMMU_B200_E2E_QUEUE_JOIN=1 (not yet run on hardware): once the last split is done, a second launch takes the
-    // SMs that were kept free for the splits and pops from the same queue
-    if (env_size("OZIMMU_B200_E2E_QUEUE_JOIN", 0) != 0) {
-      int dev = 0, sms = 0;
-      OZ_CUDA_CHECK(cudaGetDevice(&dev));
-      OZ_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const std::size_t all_pairs = static_cast<std::size_t>(sms) / 2;
-      const std::size_t main_pairs =
-          std::min<std::size_t>(static_cast<std::size_t>(sms) > reserve + 2 ? (sms - reserve) / 2 : 1, nitems);
-      if (all_pairs > main_pairs)
-        OZ_KERNEL_CHECK(ozk_gemm_i8_fused_queue_join(m, n, k, a_sl, b_sl, w.pitch, amax, bmax, s, bits, alpha, beta, dc, ldc,
-                                                     items_dev, nitems, flags_dev, epoch, done_dev, scratch_dev,
-                                                     scratch_words, static_cast<unsigned>(main_pairs),
-                                                     static_cast<unsigned>(all_pairs - main_pairs), sc));
-    }
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_product_tail[0], sp));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_product_tail[0], 0));
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_done, sc));
-    h->has_pending = true;
-    h->last_stream = sc;
-    OZ_CUDA_CHECK(cudaStreamSynchronize(sout));
-    OZ_CUDA_CHECK(cudaStreamSynchronize(sc));
-    std::uint32_t q_error = 0;
-    OZ_CUDA_CHECK(cudaMemcpy(&q_error, scratch_dev + 1, sizeof(q_error), cudaMemcpyDeviceToHost));
-    if (q_error) throw std::runtime_error("ozIMMU: the tile queue timed out waiting for an operand block");
-    return 0;
-  }
-
   for (const Arrival &x : order) x.which ? copy_b_block(x.idx) : copy_a_block(x.idx);
 
   std::size_t have_a = 0, have_b = 0;  // blocks split so far
@@ -504,35 +295,10 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   h->last_stream = sc;
   OZ_CUDA_CHECK(cudaStreamSynchronize(sout));
   OZ_CUDA_CHECK(cudaStreamSynchronize(sc));
-  h->queue_warm = true;  // every kernel of this configuration has run once (see the queue mode above)
-  h->queue_warm_key = warm_key;
   return 0;
 }
 
 }  // namespace
-
-// Diagnostic: the work-item list of the experimental queue mode for an m x n product cut at the given block edges
-// (CPU-testable host logic).  Writes min(count, capacity) items and, per arrival, the done count its rectangle must
-// reach (expected[], capacity 2 * 16); returns the item count.
-extern "C" size_t ozimmu_host_queue_plan(size_t m, size_t n, size_t want_rows, size_t want_cols, int taper,
-                                         ozk_queue_item_t *items, size_t capacity, uint32_t *expected,
-                                         size_t *num_arrivals) {
-  if (m == 0 || n == 0) return 0;
-  const std::vector<std::size_t> ae = block_edges(m, want_rows == 0 ? m : want_rows, taper != 0 && want_rows != 0);
-  const std::vector<std::size_t> be = block_edges(n, want_cols == 0 ? n : want_cols, taper != 0 && want_cols != 0);
-  const std::size_t nab = ae.size() - 1, nbb = be.size() - 1;
-  std::vector<std::pair<int, std::size_t>> order;
-  for (std::size_t ia = 0, ib = 0; ia < nab || ib < nbb;) {
-    if (ib < nbb && (ib <= ia || ia >= nab)) order.emplace_back(1, ib++);
-    else order.emplace_back(0, ia++);
-  }
-  const QueuePlan plan = plan_queue(ae, be, order);
-  for (std::size_t i = 0; i < plan.items.size() && i < capacity; i++) items[i] = plan.items[i];
-  if (expected)
-    for (std::size_t i = 0; i < plan.expected.size(); i++) expected[i] = plan.expected[i];
-  if (num_arrivals) *num_arrivals = plan.expected.size();
-  return plan.items.size();
-}
 
 // Diagnostic: the block boundaries ozimmu_gemm_host uses for one operand (CPU-testable host logic).
 extern "C" size_t ozimmu_host_block_edges(size_t extent, size_t want, int taper, size_t *edges, size_t capacity) {

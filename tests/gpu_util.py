@@ -118,6 +118,16 @@ class Reference:
                                ldb, C.addressof(be), c.data_ptr(), ldc, int(mode), 1)
         assert rc == 0, f"ozref_gemm (complex) -> {rc}"
 
+    def dgemm_f32(self, op_a, op_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc):
+        """the reference's compute mode `sgemm` (src/cublas_helper.cu:84-134, reached from its interposers only)"""
+        self.L.ozref_set_stream(self.h, stream_ptr())
+        self.L.ozref_dgemm_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double,
+                                           C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p,
+                                           C.c_size_t]
+        rc = self.L.ozref_dgemm_f32(self.h, int(op_a), int(op_b), m, n, k, float(alpha), a.data_ptr(), lda, b.data_ptr(),
+                                    ldb, float(beta), c.data_ptr(), ldc)
+        assert rc == 0, f"ozref_dgemm_f32 -> {rc}"
+
     def split(self, x: torch.Tensor, ld: int, m: int, n: int, op: int, matrix: int, num_split: int, bits_: int):
         """reference split_int8<double>: rows = m (matrix A) / n (matrix B after the swap)."""
         length = n if matrix == 0 else m

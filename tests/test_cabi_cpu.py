@@ -48,7 +48,8 @@ def test_library_exports_cublas_interposers():
 
 
 def test_kernels_are_blackwell_native():
-    """SASS of the shipped library must contain tcgen05 MMA (UTCIMMA), TMEM loads (LDTM) and TMA (UTMALDG)."""
+    """SASS of the shipped library must contain tcgen05 MMA (UTCIMMA), TMEM loads (LDTM) and bulk async copies
+    (UBLKCP: the operand tiles are staged with linear cp.async.bulk, not tensor-map TMA)."""
     out = subprocess.run(["cuobjdump", "-sass", str(oz.LIB_PATH)], capture_output=True, text=True)
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
@@ -107,47 +108,3 @@ def test_host_block_edges(extent, want, taper):
         assert sizes[-1] <= sizes[0] and sizes[-2] <= sizes[0]     # the blocks that arrive last are not the big ones
 
 
-@pytest.mark.parametrize("m,n,want", [(8192, 8192, 768), (1300, 1500, 512), (256, 4096, 1024), (5000, 300, 768),
-                                      (100, 100, 768), (8192, 2048, 0)])
-def test_host_queue_plan(m, n, want):
-    """Work items of the experimental queue mode (csrc/host_e2e.cu plan_queue): every 256 x 256 tile of C exactly once,
-    gated by the flags of the blocks that contain it, counted into the arrival that completes its operands, and never
-    scheduled before an item whose operands arrive earlier."""
-    lib = oz.lib()
-    tiles = (-(-m // 256)) * (-(-n // 256))
-    items = (C.c_uint32 * (4 * tiles))()
-    expected = (C.c_uint32 * 32)()
-    narr = C.c_size_t()
-    cnt = lib.ozimmu_host_queue_plan(m, n, want, want, 0, C.addressof(items), tiles, C.addressof(expected), C.byref(narr))
-    assert cnt == tiles
-    ea = (C.c_size_t * 32)()
-    eb = (C.c_size_t * 32)()
-    na = lib.ozimmu_host_block_edges(m, want, 0, C.addressof(ea), 32) - 1
-    nb = lib.ozimmu_host_block_edges(n, want, 0, C.addressof(eb), 32) - 1
-    assert narr.value == na + nb
-    # arrival index of every block: B0, A0, B1, A1, ... then the longer operand's rest
-    arrival_of = {}
-    ia = ib = 0
-    while ia < na or ib < nb:
-        if ib < nb and (ib <= ia or ia >= na):
-            arrival_of[("b", ib)] = len(arrival_of)
-            ib += 1
-        else:
-            arrival_of[("a", ia)] = len(arrival_of)
-            ia += 1
-    seen = set()
-    per_arrival = [0] * 32
-    last_done = -1
-    for i in range(cnt):
-        tile, fa, fb, done = items[4 * i], items[4 * i + 1], items[4 * i + 2], items[4 * i + 3]
-        tm, tn = tile & 0xFFFF, tile >> 16
-        assert (tm, tn) not in seen
-        seen.add((tm, tn))
-        assert ea[fa] <= tm * 256 < ea[fa + 1]                       # the A block that holds the tile's rows
-        assert fb >= na and eb[fb - na] <= tn * 256 < eb[fb - na + 1]
-        assert done == max(arrival_of[("a", fa)], arrival_of[("b", fb - na)])   # the arrival that completes its operands
-        assert done >= last_done                                     # start order follows arrival order
-        last_done = done
-        per_arrival[done] += 1
-    assert len(seen) == tiles
-    assert [expected[a] for a in range(narr.value)] == [16 * per_arrival[a] for a in range(narr.value)]

@@ -55,6 +55,78 @@ def test_auto_vs_reference_counters(handle):
         ref.close()
 
 
+def _exp_rand_dev(phi: float, count: int, seed: int) -> torch.Tensor:
+    """exp_rand-phi on the device (reference test/main_test.cu:56-70: (u - 0.5) * exp(phi * normal))"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    u = torch.rand(count, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    u = torch.where(u == 0, torch.full_like(u, 0.25), u)      # no exact zeros (SURVEY App. B.2)
+    return u * torch.exp(phi * torch.randn(count, dtype=torch.float64, device="cuda", generator=g))
+
+
+@pytest.mark.parametrize("phi", [0.0, 0.5, 1.0, 2.0, 4.0, 8.0])
+def test_config5_auto_4096_vs_reference(handle, phi):
+    """BASELINE config 5 at its own size: fp64_int8_auto on ill-conditioned 4096^3 inputs, thresholds of SURVEY 8(d).
+    Counters for fp64_int8_3..10 and the selected mode (where the reference's 8 counters can express it) equal the
+    unmodified reference's; the GEMM in the selected mode equals the reference's GEMM in that mode bit for bit."""
+    if oracle_lib.reference() is None:
+        pytest.skip("oracle/_ref/libozref.so not built")
+    ref = Reference()
+    try:
+        m = n = k = 4096
+        a, b = _exp_rand_dev(phi, m * k, 11), _exp_rand_dev(phi, k * n, 12)
+        checked = set()
+        for thr in (0.0, 0.5, 1.0, 1.5, 2.0, 4.0, 8.0):
+            ref_mode, ref_cnt = ref.auto_mode_select(0, 0, m, n, k, a, m, b, k, thr)
+            cnt = []
+            mode = oz.auto_mode_select(handle, 0, 0, m, n, k, a, m, b, k, oz.real, thr, cnt)
+            assert cnt[:8] == ref_cnt, (phi, thr)
+            assert all(x >= y for x, y in zip(cnt, cnt[1:]))            # more slices never lose more
+            in_range = oz.compute_mode_t.fp64_int8_3 <= ref_mode <= oz.compute_mode_t.fp64_int8_10
+            if in_range:
+                assert int(mode) == ref_mode, (phi, thr)
+            else:
+                # the reference has no counters beyond fp64_int8_10 (App. B.1): ours must need more than 10 slices too
+                assert mode == oz.compute_mode_t.dgemm or oz.num_split_of(mode) > 10, (phi, thr, mode)
+            if in_range and int(mode) not in checked and len(checked) < 2:
+                checked.add(int(mode))
+                oz.set_auto_mantissa_loss_threashold(handle, thr)
+                c_new = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+                c_ref = torch.zeros_like(c_new)
+                assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c_new, m, oz.compute_mode_t.fp64_int8_auto) == 0
+                ref.gemm(0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c_ref, m, ref_mode)
+                torch.cuda.synchronize()
+                assert torch.equal(c_new.view(torch.int64), c_ref.view(torch.int64)), (phi, thr)
+        oz.set_auto_mantissa_loss_threashold(handle, 0.0)
+    finally:
+        ref.close()
+
+
+def test_sgemm_mode_vs_reference_sgemm(handle):
+    """compute mode `sgemm` against the REFERENCE's own sgemm mode (src/cublas_helper.cu:84-134: FP32 copies,
+    cublasSgemm, widen): same conversions around the same library GEMM -- equal up to cuBLAS' FP32 summation order
+    (the two private cuBLAS handles may pick different kernels), every output an FP32 value in both."""
+    if oracle_lib.reference() is None:
+        pytest.skip("oracle/_ref/libozref.so not built")
+    ref = Reference()
+    try:
+        m, n, k = 1024, 768, 1536
+        g = torch.Generator(device="cuda").manual_seed(5)
+        a = torch.randn(m * k, dtype=torch.float64, device="cuda", generator=g)
+        b = torch.randn(k * n, dtype=torch.float64, device="cuda", generator=g)
+        c0 = torch.randn(m * n, dtype=torch.float64, device="cuda", generator=g)
+        for op_a, op_b, alpha, beta in ((0, 0, 1.0, 0.0), (1, 0, -0.5, 1.5), (0, 1, 2.0, -1.0)):
+            lda, ldb = (m if op_a == 0 else k), (k if op_b == 0 else n)
+            c_ref, c_new = c0.clone(), c0.clone()
+            ref.dgemm_f32(op_a, op_b, m, n, k, alpha, a, lda, b, ldb, beta, c_ref, m)
+            assert oz.gemm(handle, op_a, op_b, m, n, k, alpha, a, lda, b, ldb, beta, c_new, m, oz.compute_mode_t.sgemm) == 0
+            torch.cuda.synchronize()
+            assert torch.equal(c_new, c_new.float().double()) and torch.equal(c_ref, c_ref.float().double())
+            rel = (torch.linalg.vector_norm(c_new - c_ref) / torch.linalg.vector_norm(c_ref)).item()
+            assert rel < 5e-7, (op_a, op_b, rel)
+    finally:
+        ref.close()
+
+
 def test_auto_mode_gemm_runs_selected_mode(handle):
     m, n, k = 300, 200, 500
     a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 5))

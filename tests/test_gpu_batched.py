@@ -11,7 +11,7 @@ import torch
 
 import oracle_lib
 import ozimmu_b200 as oz
-from gpu_util import bits, to_dev
+from gpu_util import Reference, bits, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -91,7 +91,7 @@ def test_batched_chunks_auto_dgemm_and_errors(handle, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(got.view(torch.int64), want.view(torch.int64))
     monkeypatch.delenv("OZIMMU_B200_BATCH_WORKSPACE_MB")
-    # auto mode decides entry by entry; with threshold 0 on these inputs every entry lands on the same mode as gemm()
+    # auto mode: one counter pass for the whole batch, the split count still chosen per entry
     oz.set_auto_mantissa_loss_threashold(handle, 1.0)
     got_auto, want_auto = to_dev(c), to_dev(c)
     for e in range(batch):
@@ -118,6 +118,95 @@ def test_batched_chunks_auto_dgemm_and_errors(handle, monkeypatch):
                                    oz.fp64_int8(9)) == 0
     torch.cuda.synchronize()
     assert torch.equal(z.view(torch.int64), (to_dev(c) * 2.0).view(torch.int64))
+
+
+def test_batched_matches_oracle_and_reference(handle):
+    """the grouped launch against the CPU oracle entry by entry (small), and against the unmodified reference looping
+    over the entries as its interposer does (src/cublas.cu:380-406) -- not only against this library's own gemm()"""
+    m, n, k, batch, pad, s = 96, 80, 200, 4, 1, 9
+    for op_a, op_b in ((0, 0), (1, 1)):
+        a, lda, sa, b, ldb, sb, c, ldc, sc = _case(op_a, op_b, m, n, k, batch, pad, 21)
+        got = to_dev(c)
+        assert oz.gemm_strided_batched(handle, op_a, op_b, m, n, k, -0.75, to_dev(a), lda, sa, to_dev(b), ldb, sb, 0.5, got,
+                                       ldc, sc, batch, oz.fp64_int8(s)) == 0
+        torch.cuda.synchronize()
+        got = got.cpu().numpy()
+        for e in range(batch):
+            want = oracle_lib.oracle_gemm(op_a, op_b, m, n, k, -0.75, a[e * sa:], lda, b[e * sb:], ldb, 0.5,
+                                          c[e * sc:e * sc + ldc * n], ldc, s)
+            assert np.array_equal(bits(got[e * sc:e * sc + ldc * n]), bits(want)), (op_a, op_b, e)
+    if oracle_lib.reference() is None:
+        pytest.skip("oracle/_ref/libozref.so not built")
+    ref = Reference()
+    try:
+        m, n, k, batch = 1024, 1024, 1028, 5     # m % 4 == 0: the reference's int8 cublasGemmEx needs it on this cuBLAS
+        a, lda, sa, b, ldb, sb, c, ldc, sc = _case(0, 0, m, n, k, batch, 0, 23)
+        da, db = to_dev(a), to_dev(b)
+        want, got = to_dev(c), to_dev(c)
+        for e in range(batch):
+            ref.gemm(0, 0, m, n, k, 1.0, da[e * sa:], lda, db[e * sb:], ldb, -1.0, want[e * sc:], ldc, 9 - 1)
+        assert oz.gemm_strided_batched(handle, 0, 0, m, n, k, 1.0, da, lda, sa, db, ldb, sb, -1.0, got, ldc, sc, batch,
+                                       oz.fp64_int8(9)) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(got.view(torch.int64), want.view(torch.int64))
+    finally:
+        ref.close()
+
+
+@pytest.mark.parametrize("op_a,op_b", [(0, 0), (1, 0), (1, 1)])
+def test_complex_batched_one_launch(handle, op_a, op_b):
+    """a complex strided batch: one grouped launch, every tile running its four plane products; equal to the oracle
+    (small) and to per-entry complex gemm() calls; exactly one product launch for the whole batch"""
+    m, n, k, batch, s = 72, 40, 130, 3, 9
+    lda, ldb = (m if op_a == 0 else k), (k if op_b == 0 else n)
+    sa, sb, sc = m * k + 5, k * n + 3, m * n + 7
+    a = oracle_lib.gen_complex("exp_rand-1", sa * batch, 31)
+    b = oracle_lib.gen_complex("exp_rand-1", sb * batch, 32)
+    c = oracle_lib.gen_complex("normal01", sc * batch, 33)
+    alpha, beta = 0.5 - 1.5j, -0.25 + 2.0j
+    da, db, got, loop = to_dev(a), to_dev(b), to_dev(c), to_dev(c)
+    before = oz.launch_count()
+    assert oz.gemm_strided_batched(handle, op_a, op_b, m, n, k, alpha, da, lda, sa, db, ldb, sb, beta, got, m, sc, batch,
+                                   oz.fp64_int8(s), oz.complx) == 0
+    launches = oz.launch_count() - before
+    for e in range(batch):
+        assert oz.gemm(handle, op_a, op_b, m, n, k, alpha, da[e * sa:], lda, db[e * sb:], ldb, beta, loop[e * sc:], m,
+                       oz.fp64_int8(s), oz.complx) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(torch.view_as_real(got).view(torch.int64), torch.view_as_real(loop).view(torch.int64))
+    g = got.cpu().numpy()
+    for e in range(batch):
+        want = oracle_lib.oracle_gemm_complex(op_a, op_b, m, n, k, alpha, a[e * sa:], lda, b[e * sb:], ldb, beta,
+                                              c[e * sc:e * sc + m * n], m, s)
+        assert np.array_equal(g[e * sc:e * sc + m * n].view(np.int64), want.view(np.int64)), e
+    # splits: <= 2 planes x 2 operands x 2 kernels; products: ONE launch for 3 entries x 4 plane products
+    assert launches <= 9, launches
+
+
+def test_batched_auto_mode_one_pass(handle):
+    """fp64_int8_auto over a batch whose entries need DIFFERENT split counts (entries scaled to different dynamic
+    ranges): per-entry choice from one counter pass == gemm(auto) entry by entry, bit for bit"""
+    m, n, k, batch = 256, 192, 320, 6
+    sa, sb, sc = m * k, k * n, m * n
+    a = np.concatenate([oracle_lib.gen_matrix(f"exp_rand-{phi}", sa, 40 + i)
+                        for i, phi in enumerate((0, 0, 2, 2, 4, 0))])
+    b = np.concatenate([oracle_lib.gen_matrix(f"exp_rand-{phi}", sb, 50 + i)
+                        for i, phi in enumerate((0, 0, 2, 2, 4, 0))])
+    da, db = to_dev(a), to_dev(b)
+    got = torch.zeros(sc * batch, dtype=torch.float64, device="cuda")
+    want = torch.zeros_like(got)
+    oz.set_auto_mantissa_loss_threashold(handle, 1.0)
+    modes = []
+    for e in range(batch):
+        modes.append(oz.auto_mode_select(handle, 0, 0, m, n, k, da[e * sa:], m, db[e * sb:], k, oz.real, 1.0))
+        assert oz.gemm(handle, 0, 0, m, n, k, 1.0, da[e * sa:], m, db[e * sb:], k, 0.0, want[e * sc:], m,
+                       oz.compute_mode_t.fp64_int8_auto) == 0
+    assert len(set(modes)) >= 2, modes     # the batch really mixes split counts
+    assert oz.gemm_strided_batched(handle, 0, 0, m, n, k, 1.0, da, m, sa, db, k, sb, 0.0, got, m, sc, batch,
+                                   oz.compute_mode_t.fp64_int8_auto) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int64), want.view(torch.int64))
+    oz.set_auto_mantissa_loss_threashold(handle, 0.0)
 
 
 DROPIN_BMM = r"""
@@ -157,9 +246,9 @@ def test_ld_preload_bmm(tmp_path, handle):
     assert np.array_equal(bits(c), bits(d["c"]))
     ref = d["a"] @ d["b"]
     assert (torch.linalg.norm(d["c"] - ref) / torch.linalg.norm(ref)).item() < 1e-15
-    # complex128 bmm -> cublasZgemmStridedBatched / GemmStridedBatchedEx(C_64F): one complex Ozaki GEMM per entry
-    # (reference src/cublas.cu:380-406,494-512)
-    assert "[CULiP Result][Zfp64_int8_9-" in p.stdout, p.stdout[-2000:]
+    # complex128 bmm -> cublasZgemmStridedBatched / GemmStridedBatchedEx(C_64F): one grouped complex launch (the reference:
+    # one complex Ozaki GEMM per entry, src/cublas.cu:380-406,494-512)
+    assert "[CULiP Result][Zfp64_int8_9-batched3-" in p.stdout, p.stdout[-2000:]
     za, zb = d["za"].cuda(), d["zb"].cuda()
     zc = torch.zeros_like(za)
     nz = za.shape[1]

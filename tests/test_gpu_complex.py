@@ -91,3 +91,64 @@ def test_complex_auto_mode_vs_oracle(handle):
         mode = oz.auto_mode_select(handle, 0, 0, m, n, k, to_dev(a), m, to_dev(b), k, oz.complx, thr, cnt)
         assert cnt == [int(v) for v in cnt_want]
         assert mode == (oz.fp64_int8(s) if s else oz.compute_mode_t.dgemm)
+
+
+def test_zgemm_is_one_product_launch(handle):
+    """the four plane products of a complex GEMM run inside ONE launch (the reference: 4 x P(s) cuBLAS GEMMs plus
+    4 x (P(s) + 1) elementwise kernels, src/gemm.cu:476-518)"""
+    m, n, k = 512, 384, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(m * k, dtype=torch.complex128, device="cuda", generator=g)
+    b = torch.randn(k * n, dtype=torch.complex128, device="cuda", generator=g)
+    c = torch.zeros(m * n, dtype=torch.complex128, device="cuda")
+    assert oz.gemm(handle, 1, 1, m, n, k, 1.0 + 0j, a, k, b, n, 0j, c, m, oz.fp64_int8(9), oz.complx) == 0   # warm
+    before = oz.launch_count()
+    assert oz.gemm(handle, 1, 1, m, n, k, 1.0 + 0j, a, k, b, n, 0j, c, m, oz.fp64_int8(9), oz.complx) == 0
+    torch.cuda.synchronize()
+    # op_t A / op_t B: A's rows are contiguous (1 split kernel per plane), B's strided (2 per plane) -> 6 + 1 product
+    assert oz.launch_count() - before <= 7
+    want = (a.view(m, k) @ b.view(k, n)).T.reshape(-1)
+    assert (torch.linalg.vector_norm(c - want) / torch.linalg.vector_norm(want)).item() < 1e-14
+
+
+@pytest.mark.parametrize("beta", [0j, 0.5 - 2.0j])
+def test_zgemm_k_zero_scales_c(handle, beta):
+    """k == 0: C = beta * C for complex data as well (the beta pre-scale of the complex path)"""
+    m, n = 70, 33
+    c = oracle_lib.gen_complex("normal01", m * n, 9)
+    dc = to_dev(c)
+    dummy = torch.zeros(4, dtype=torch.complex128, device="cuda")
+    assert oz.gemm(handle, 0, 0, m, n, 0, 1.0 + 1.0j, dummy, m, dummy, 1, beta, dc, m, oz.fp64_int8(9), oz.complx) == 0
+    torch.cuda.synchronize()
+    got = dc.cpu().numpy()
+    want = beta * c
+    assert np.allclose(got, want, rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("kind", ["real", "complex"])
+def test_device_pointer_mode_scalars(handle, kind):
+    """cuBLAS device pointer mode: alpha / beta live in device memory and are read by the kernels in stream order
+    (the reference dereferences them on the host, src/gemm.cu:405); bits equal to the host-scalar call, for the
+    fp64_int8 modes (device read) and for auto mode (one blocking fetch)"""
+    m, n, k = 300, 260, 200
+    if kind == "real":
+        a, b, c = (to_dev(oracle_lib.gen_matrix("exp_rand-1", cnt, sd)) for cnt, sd in ((m * k, 1), (k * n, 2), (m * n, 3)))
+        alpha, beta, ek = 1.5, -0.25, oz.real
+        d_alpha = torch.tensor([alpha], dtype=torch.float64, device="cuda")
+        d_beta = torch.tensor([beta], dtype=torch.float64, device="cuda")
+    else:
+        a, b, c = (to_dev(oracle_lib.gen_complex("exp_rand-1", cnt, sd)) for cnt, sd in ((m * k, 1), (k * n, 2), (m * n, 3)))
+        alpha, beta, ek = 0.5 - 1.5j, -0.25 + 2.0j, oz.complx
+        d_alpha = torch.tensor([alpha], dtype=torch.complex128, device="cuda")
+        d_beta = torch.tensor([beta], dtype=torch.complex128, device="cuda")
+    for mode in (oz.fp64_int8(9), oz.compute_mode_t.fp64_int8_auto):
+        want, got = c.clone(), c.clone()
+        assert oz.gemm(handle, 0, 0, m, n, k, alpha, a, m, b, k, beta, want, m, mode, ek) == 0
+        oz.set_scalar_pointer_mode(handle, True)
+        try:
+            assert oz.gemm(handle, 0, 0, m, n, k, d_alpha, a, m, b, k, d_beta, got, m, mode, ek) == 0
+        finally:
+            oz.set_scalar_pointer_mode(handle, False)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.view_as_real(got).view(torch.int64) if kind == "complex" else got.view(torch.int64),
+                           torch.view_as_real(want).view(torch.int64) if kind == "complex" else want.view(torch.int64))

@@ -31,10 +31,10 @@ def test_cpp_app_under_ld_preload(tmp_path, handle):
     c = oracle_lib.gen_matrix("normal01", n * n, 3)
     np.concatenate([a, bm, c]).tofile(tmp_path / "in.bin")
 
-    def run(extra_env, out):
+    def run(extra_env, out, mode="host"):
         env = dict(os.environ, **extra_env)
-        p = subprocess.run([str(app), str(n), str(tmp_path / "in.bin"), str(tmp_path / out)], env=env, capture_output=True,
-                           text=True, timeout=600)
+        p = subprocess.run([str(app), str(n), str(tmp_path / "in.bin"), str(tmp_path / out), mode], env=env,
+                           capture_output=True, text=True, timeout=600)
         assert p.returncode == 0, (p.returncode, p.stdout[-1000:], p.stderr[-1000:])
         return p.stdout, np.fromfile(tmp_path / out)
 
@@ -49,3 +49,18 @@ def test_cpp_app_under_ld_preload(tmp_path, handle):
     assert np.array_equal(bits(c_oz), bits(dc)), "intercepted cublasDgemm differs from the direct call"
     assert not np.array_equal(bits(c_oz), bits(c_plain))                    # it really took the other path
     assert np.linalg.norm(c_oz - c_plain) / np.linalg.norm(c_plain) < 1e-14
+    # cuBLAS device pointer mode: alpha / beta are read on the device by the Ozaki kernels (the reference dereferences the
+    # device pointers on the host, src/gemm.cu:405) -- same bits as the host-pointer call
+    oz_env = {"LD_PRELOAD": str(oz.LIB_PATH), "OZIMMU_COMPUTE_MODE": "fp64_int8_12", "OZIMMU_INFO": "1"}
+    log, c_dev = run(oz_env, "devptr.bin", "devptr")
+    assert "[ozIMMU LOG]" in log
+    assert np.array_equal(bits(c_dev), bits(dc)), "device-pointer-mode cublasDgemm differs from the direct call"
+    # two host threads, each with its own cuBLAS handle and stream, three DGEMMs each, concurrently: per-device state
+    # behind one lock, the shared workspace ordered across the two streams
+    _, c_thr = run(oz_env, "threads.bin", "threads")
+    assert np.array_equal(bits(c_thr[:n * n]), bits(dc)) and np.array_equal(bits(c_thr[n * n:]), bits(dc))
+    # one process driving two GPUs, one cuBLAS handle per GPU (needs 2 GPUs): every GPU gets its own ozIMMU handle and
+    # workspace (the reference has one process-global handle, src/cublas.cu:58-86)
+    if torch.cuda.device_count() >= 2:
+        _, c_two = run(oz_env, "multigpu.bin", "multigpu")
+        assert np.array_equal(bits(c_two[:n * n]), bits(dc)) and np.array_equal(bits(c_two[n * n:]), bits(dc))

@@ -31,7 +31,9 @@ def main():
     ap.add_argument("n", type=int, nargs="?", default=4096)
     ap.add_argument("s", type=int, nargs="?", default=9)
     ap.add_argument("--ref", action="store_true")
-    ap.add_argument("--shapes", default="00", help="p128,p192 = CTA-pair kernel; 11,21,12,22 = single-CTA clusters")
+    ap.add_argument("--shapes", default="00", help="comma list: p256,p224,... = forced tile width; 00 = default")
+    ap.add_argument("--zgemm", action="store_true", help="also time a complex GEMM of the same size")
+    ap.add_argument("--no-extras", action="store_true", help="skip the stage profile and the cuBLAS comparisons")
     ap.add_argument("--iters", type=int, default=5)
     args = ap.parse_args()
     n, s = args.n, args.s
@@ -44,17 +46,25 @@ def main():
     flop = 2.0 * n ** 3
     pairs = s * (s + 1) // 2
     for shape in args.shapes.split(","):
-        if shape.startswith("p"):      # CTA-pair kernel, BN = 128 / 192
-            cm, cn = 0, int(shape[1:])
-        elif shape.startswith("c"):    # CTA-pair kernel BN=192 in a PM x PN multicast cluster: c21, c12, c22
-            cm, cn = 100, int(shape[1:])
-        else:                          # legacy single-CTA kernel, cm x cn multicast cluster
-            cm, cn = int(shape[0]), int(shape[1])
+        # pNNN = force the tile width of the CTA-pair kernel (128, 192, 208, 224, 240, 256); anything else: default
+        cm, cn = (0, int(shape[1:])) if shape.startswith("p") else (0, 0)
         L.ozk_set_cluster_shape(cm, cn)
         ms = timed(lambda: oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(s)), args.iters)
         print(f"ozimmu_b200 n={n} s={s} cluster={cm}x{cn}: {ms:.3f} ms  {flop / ms / 1e9:.2f} TFLOP/s-equiv  "
               f"int8 {pairs * flop / ms / 1e12:.3f} Pop/s", flush=True)
     L.ozk_set_cluster_shape(0, 0)
+    if args.zgemm:
+        za = torch.randn(n * n, dtype=torch.complex128, device="cuda", generator=g)
+        zb = torch.randn(n * n, dtype=torch.complex128, device="cuda", generator=g)
+        zc = torch.zeros(n * n, dtype=torch.complex128, device="cuda")
+        ms = timed(lambda: oz.gemm(h, 0, 0, n, n, n, 1.0 + 0j, za, n, zb, n, 0j, zc, n, oz.fp64_int8(s), oz.complx), args.iters)
+        print(f"ozimmu_b200 ZGEMM n={n} s={s}: {ms:.3f} ms  {4 * flop / ms / 1e9:.2f} FP64-equiv TFLOP/s (8 n^3 flop)", flush=True)
+        ms = timed(lambda: torch.mm(za.view(n, n), zb.view(n, n)), args.iters)
+        print(f"cuBLAS ZGEMM n={n}: {ms:.3f} ms {4 * flop / ms / 1e9:.2f} TFLOP/s", flush=True)
+        del za, zb, zc
+    if args.no_extras:
+        oz.destroy(h)
+        return
     # stages
     oz.enable_profiling(h)
     for _ in range(3):
