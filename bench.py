@@ -4,13 +4,17 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One step = one C = A*B (N/N, alpha=1, beta=0, tight leading dimensions) of the workload on every rank.
-N=1: 8192^3.  N>1 (torchrun, one rank per GPU, NCCL): weak scaling -- every rank owns an 8192-row
-block of A and C (global m = 8192*N), rank 0 owns B and broadcasts it inside the timed step
-(ozimmu_b200.sharded).  The JSON line carries:
+N=1: 8192^3.  N>1 (torchrun, one rank per GPU): weak scaling -- every rank owns an 8192-row block of A and C (global
+m = 8192*N), rank 0 owns B and broadcasts it inside the timed step (ozimmu_gemm_sharded: the library's own NCCL
+communicator, B in column panels, each panel of C as soon as it has landed).  The JSON line carries:
   value    device-resident throughput (CUDA events, max over ranks)
   e2e      the same through the C-ABI with HOST operands (pinned), H2D/D2H inside the timed region
+           (ozimmu_gemm_host / ozimmu_gemm_sharded_host)
   roofline the fused tcgen05 kernel: int8 ops per launch / its CUDA-event duration, against
            2 x the measured bf16 peak of MEASURED_PEAKS.json (int8 runs at twice the bf16 rate)
+  parity   (N>1) every rank's first 256 rows of C, bit-compared on rank 0 with a single-GPU product of the same rows
+  config4  BASELINE config 4 in the same run: 16384^3 strong scaling, 16384/N rows per rank, B broadcast in the step
+  per_rank_ms / bcast_ms   each rank's own step time and the cost of the bare broadcast (what limits the scaling)
   cpu_baseline  host OpenBLAS DGEMM (numpy) on the box's cores -- the reference has no CPU path and
            north_star names host OpenBLAS as the CPU comparator -- plus the scalar oracle port on a small sample
 --impl reference times the UNMODIFIED reference (oracle/_ref/libozref.so, built from /root/reference by
@@ -204,7 +208,7 @@ def make_inputs(n: int, rank: int):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(n_sample: int = 4096) -> dict:
+def cpu_baseline(n_sample: int = N_DEFAULT) -> dict:
     """host OpenBLAS DGEMM through numpy on a bounded sample + the scalar oracle port on a tiny one"""
     import numpy as np
     try:
@@ -217,7 +221,7 @@ def cpu_baseline(n_sample: int = 4096) -> dict:
     b = rng.random((n_sample, n_sample))
     a @ b  # warm-up
     reps, t0 = 0, time.perf_counter()
-    while reps < 3 or (time.perf_counter() - t0 < 5.0 and reps < 20):
+    while reps < 2 or (time.perf_counter() - t0 < 8.0 and reps < 10):
         a @ b
         reps += 1
     dt = (time.perf_counter() - t0) / reps
@@ -250,19 +254,131 @@ def measured_peaks() -> dict:
 
 
 def ncu_traffic_bytes():
-    """dram bytes per launch of the fused kernel from the committed ncu capture (profiles/), or None"""
-    for name in ("r1_fused_pair256_final_8192.json", "r1_fused_pair256_bulk_8192.json"):
+    """(dram bytes per launch of the fused kernel, file it comes from) from the newest committed ncu capture of the
+    shipped kernel (profiles/), or (None, None).  ncu cannot run inside the timed bench; the capture is re-taken
+    whenever the kernel changes and its file name is stamped into the line."""
+    for name in ("r2_fused_pair256_8192.json", "r1_fused_pair256_final_8192.json"):
         p = ROOT / "profiles" / name
         if p.exists():
             try:
                 d = json.loads(p.read_text())
-                return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+                return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), "profiles/" + name
             except Exception:  # noqa: BLE001
                 continue
-    return None
+    return None, None
 
 
 # ------------------------------------------------------------------------------------------------
+WORKLOAD = "DGEMM N/N {n}x{n}x{n}, fp64_int8_{s}, alpha=1 beta=0, tight ld"   # the same string in both arms
+
+
+def gather_ms(ms: float, world: int):
+    """every rank's own time (ms), on every rank"""
+    if world == 1:
+        return [ms]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
+def timed_loop_ranks(fn, steps: int, warmup: int, world: int, sampler=None):
+    """timed_loop that also returns every rank's own ms per step"""
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier_sync(world)
+    if sampler is not None:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier_sync(world)
+    mine = e0.elapsed_time(e1) / steps
+    per_rank = gather_ms(mine, world)
+    return max(per_rank), per_rank
+
+
+def sharded_parity(oz, h, comm, rank, world, n, k, a, lda, b, c, ldc, rows, mode, sample=256):
+    """Bit-compare every rank's first `sample` rows of C (computed by the sharded step, inside its full row block)
+    with a SINGLE-GPU product of the same rows of A on rank 0.  Returns {"checked", "max_ulp", "rows_per_rank"}."""
+    import torch
+    import torch.distributed as dist
+    sample = min(sample, rows)
+    # column-major (ld x cols): rows 0..sample of every column
+    a_s = a.view(-1, lda)[:, :sample].contiguous()       # k x sample  == column-major sample x k, ld = sample
+    c_s = c.view(-1, ldc)[:, :sample].contiguous()       # n x sample
+    a_all = [torch.empty_like(a_s) for _ in range(world)]
+    c_all = [torch.empty_like(c_s) for _ in range(world)]
+    dist.all_gather(a_all, a_s)
+    dist.all_gather(c_all, c_s)
+    max_ulp = 0
+    if rank == 0:
+        chk = torch.empty_like(c_s)
+        for r in range(world):
+            assert oz.gemm(h, oz.op_n, oz.op_n, sample, n, k, 1.0, a_all[r], sample, b, k, 0.0, chk, sample, mode) == 0
+            torch.cuda.synchronize()
+            x, y = chk.view(torch.int64), c_all[r].view(torch.int64)
+            if not torch.equal(x, y):
+                # ulp distance of finite doubles through the monotone integer mapping
+                fx = torch.where(x < 0, torch.iinfo(torch.int64).min - x, x)
+                fy = torch.where(y < 0, torch.iinfo(torch.int64).min - y, y)
+                max_ulp = max(max_ulp, int((fx - fy).abs().max().item()))
+    t = torch.tensor([max_ulp], dtype=torch.int64, device="cuda")
+    dist.broadcast(t, src=0)
+    return {"checked": True, "max_ulp": int(t.item()), "rows_per_rank": sample,
+            "how": "rank 0: single-GPU ozimmu_gemm of each rank's first rows vs the rows the sharded step produced"}
+
+
+def bcast_alone_ms(comm, oz, b, world: int) -> float:
+    """the bare NCCL broadcast of B through the library's communicator (max_panels=1, no rows), max over ranks"""
+    import torch
+    h = oz.create()
+    dummy = torch.zeros(8, dtype=torch.float64, device="cuda")
+    n = int(round(b.numel() ** 0.5))
+
+    def fn():
+        assert oz.sharded_gemm(h, comm, oz.op_n, oz.op_n, 0, n, n, 1.0, dummy, 1, b, n, 0.0, dummy, 1, oz.fp64_int8(NUM_SPLIT),
+                               src=0, max_panels=1) == 0
+    ms = timed_loop(fn, 5, 2, world)
+    oz.destroy(h)
+    return ms
+
+
+def run_config4(oz, h, comm, rank, world, steps: int, peaks: dict) -> dict:
+    """BASELINE config 4: 16384^3 fp64_int8_9 row-sharded over the ranks (strong scaling), B broadcast inside the step"""
+    import torch
+    n4 = int(os.environ.get("OZ_BENCH_N4", "16384"))
+    s = NUM_SPLIT
+    r0, rows = oz.row_block(n4, world, rank)
+    g = torch.Generator(device="cuda").manual_seed(4321 + rank)
+    a = 1.0 - torch.rand(max(rows, 1) * n4, dtype=torch.float64, device="cuda", generator=g)
+    gb = torch.Generator(device="cuda").manual_seed(77)
+    b = 1.0 - torch.rand(n4 * n4, dtype=torch.float64, device="cuda", generator=gb)   # only rank 0's content is used
+    if rank != 0:
+        b.zero_()
+    c = torch.zeros(max(rows, 1) * n4, dtype=torch.float64, device="cuda")
+    mode = oz.fp64_int8(s)
+    panels = int(os.environ.get("OZIMMU_B200_BENCH_PANELS", "8"))
+
+    def step():
+        assert oz.sharded_gemm(h, comm, oz.op_n, oz.op_n, rows, n4, n4, 1.0, a, max(rows, 1), b, n4, 0.0, c, max(rows, 1),
+                               mode, src=0, max_panels=panels) == 0
+    ms, per_rank = timed_loop_ranks(step, steps, 1, world)
+    parity = sharded_parity(oz, h, comm, rank, world, n4, n4, a, max(rows, 1), b, c, max(rows, 1), rows, mode) if world > 1 else None
+    int8_ops_rank = s * (s + 1) / 2 * 2.0 * rows * n4 * n4
+    out = {"workload": WORKLOAD.format(n=n4, s=s) + f"; rows {n4}/{world} per rank, B broadcast from rank 0 inside the step",
+           "scaling": "strong", "value": 2.0 * n4 ** 3 / ms / 1e9, "unit": "TFLOP/s", "ms_per_step": ms, "steps": steps,
+           "per_rank_ms": per_rank, "tc_fraction": int8_ops_rank / ms / 1e9 / (2.0 * peaks["bf16"]), "parity": parity}
+    del a, b, c
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args) -> dict:
     import torch
     import ozimmu_b200 as oz
@@ -271,53 +387,51 @@ def run_ours(args) -> dict:
     n, s = N_DEFAULT, NUM_SPLIT
     mode = oz.fp64_int8(s)
     a, b, c = make_inputs(n, rank)      # every rank: its own 8192-row block of A and C; B comes from rank 0
+    if rank != 0:
+        b.zero_()                        # only rank 0 owns B: everybody else must receive it in every step
     h = oz.create()
     L = oz.lib()
-
-    # one broadcast of B, then one product launch.  OZIMMU_B200_BENCH_PIPELINE=1: B travels in column panels and
-    # every panel of C starts as soon as its columns have landed (gemm_streamed_b) -- measured SLOWER on 2 x B200
-    # (21.1 vs 19.1 ms, profiles/r1_bench_2gpu_streamed_b.txt): NCCL's broadcast kernels need SMs, and the persistent
-    # product kernel holds all of them, so the later panels' broadcasts wait for whole rounds of tiles.
-    pipeline = os.environ.get("OZIMMU_B200_BENCH_PIPELINE", "0") == "1"
-    transport = os.environ.get("OZIMMU_B200_BENCH_TRANSPORT", "nccl")
+    comm = oz.comm_create()              # the library's own NCCL communicator (None on one GPU)
+    # B travels in up to PANELS column panels on the communicator's stream; every panel of C starts as soon as its
+    # columns have landed (PANELS=1: one broadcast, then one product launch)
+    panels = int(os.environ.get("OZIMMU_B200_BENCH_PANELS", "8"))
 
     def step():
-        rc = oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0, pipeline=pipeline,
-                             transport=transport)
-        assert rc == 0
+        assert oz.sharded_gemm(h, comm, oz.op_n, oz.op_n, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0,
+                               max_panels=panels) == 0
 
     sampler = ClockSampler(local)
     launches0 = oz.launch_count()
-    ms = timed_loop(step, args.steps, args.warmup, world, sampler if rank == 0 else None)
+    ms, per_rank = timed_loop_ranks(step, args.steps, args.warmup, world, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     launches = (oz.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
     flop_step = 2.0 * n * n * n * world
     value = flop_step / ms / 1e9
+    parity = sharded_parity(oz, h, comm, rank, world, n, n, a, n, b, c, n, n, mode) if world > 1 else None
+    bcast_ms = bcast_alone_ms(comm, oz, b, world) if world > 1 else None
 
     # ---- end to end: HOST operands through the C-ABI ------------------------------------------------
     ha = torch.empty(n * n, dtype=torch.float64).pin_memory(); ha.copy_(a)
-    hb = torch.empty(n * n, dtype=torch.float64).pin_memory(); hb.copy_(b)
+    hb = None
+    if rank == 0:
+        hb = torch.empty(n * n, dtype=torch.float64).pin_memory(); hb.copy_(b)
     hc = torch.empty(n * n, dtype=torch.float64).pin_memory()
     if world == 1:
         def e2e_step():
             assert oz.gemm_host(h, oz.op_n, oz.op_n, n, n, n, 1.0, ha, n, hb, n, 0.0, hc, n, mode) == 0
         h2d, d2h = 2 * n * n * 8, n * n * 8
     else:
-        da, db, dc = torch.empty_like(a), torch.empty_like(b), torch.empty_like(c)
-
-        def e2e_step():
-            da.copy_(ha, non_blocking=True)
-            if rank == 0:
-                db.copy_(hb, non_blocking=True)
-            assert oz.sharded_gemm(h, oz.op_n, oz.op_n, n, n, n, 1.0, da, n, db, n, 0.0, dc, n, mode, src=0,
-                                   pipeline=pipeline, transport=transport) == 0
-            hc.copy_(dc, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        def e2e_step():   # every rank: its rows of A up, its rows of C down; rank 0 also uploads B and forwards it over NVLink
+            assert oz.sharded_gemm_host(h, comm, oz.op_n, oz.op_n, n, n, n, 1.0, ha, n, hb, n, 0.0, hc, n, mode, src=0) == 0
         h2d, d2h = (world + 1) * n * n * 8, world * n * n * 8
     e2e_steps = max(2, min(args.steps, 5))
-    e2e_ms = timed_loop(e2e_step, e2e_steps, 1, world)
+    e2e_ms, e2e_per_rank = timed_loop_ranks(e2e_step, e2e_steps, 2, world)
     e2e = {"value": flop_step / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_ms, "steps": e2e_steps}
+           "ms_per_step": e2e_ms, "steps": e2e_steps, "per_rank_ms": e2e_per_rank}
+    if world > 1:
+        # the host-operand result must be the device-resident one (same rows, same B)
+        e2e["bit_identical_to_device_path"] = bool(torch.equal(hc.view(torch.int64), c.cpu().view(torch.int64)))
+    del ha, hb, hc
 
     # ---- roofline of the dominant kernel (fused tcgen05 product+accumulate), CUDA events on its stream ----
     roof = None
@@ -347,7 +461,7 @@ def run_ours(args) -> dict:
         int8_ops = s * (s + 1) / 2 * 2.0 * n * n * n
         peaks = measured_peaks()
         peak = 2.0 * peaks["bf16"]
-        traffic = ncu_traffic_bytes()
+        traffic, traffic_src = ncu_traffic_bytes()
         roof = {"bound": "tensor", "achieved": int8_ops / kms / 1e9, "peak": peak, "unit": "TFLOP/s",
                 "frac": int8_ops / kms / 1e9 / peak, "traffic": traffic,
                 "hbm_gbs": (traffic / (kms * 1e-3) / 1e9) if traffic else None, "hbm_peak_gbs": peaks["hbm"],
@@ -355,20 +469,32 @@ def run_ours(args) -> dict:
                 "ops_per_launch": int8_ops,
                 "note": f"int8 TOP/s; peak = 2 x bf16_tflops (burst: launches timed one at a time) of MEASURED_PEAKS.json "
                         f"({peaks['src']}); 2 x sustained bf16 = {2.0 * peaks['bf16_sustained'] if peaks['bf16_sustained'] else None}; "
-                        "nominal dense int8 4500; traffic = dram bytes of one launch from the committed ncu capture "
-                        "(profiles/r1_fused_pair256_final_8192.json)"}
+                        f"nominal dense int8 4500; traffic = dram bytes of one launch from the committed ncu capture ({traffic_src})"}
         del a_sl, b_sl
+    peaks = measured_peaks()
+    int8_ops_rank = s * (s + 1) / 2 * 2.0 * n * n * n
+    # BASELINE config 4 (16384^3 strong scaling) in the same run; OZ_BENCH_CONFIG4=0 skips it
+    config4 = None
+    if os.environ.get("OZ_BENCH_CONFIG4", "1") != "0":
+        del a, c
+        torch.cuda.empty_cache()
+        config4 = run_config4(oz, h, comm, rank, world, max(2, min(args.steps, 3)), peaks)
     base = cpu_baseline() if (rank == 0 and world == 1) else None
     oz.destroy(h)
+    if comm is not None:
+        comm.destroy()
     out = {"metric": "FP64-equiv TFLOP/s at fp64_int8_9, 8192^3 (2*m*n*k/t)", "value": value, "unit": "TFLOP/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "int8 (int32 products, f64 accumulation; f64 in/out)",
            "data": "synthetic urand01 (0,1], seeded torch.rand on device",
-           "config": {"workload": f"DGEMM N/N {n}x{n}x{n} per GPU, fp64_int8_{s}, alpha=1 beta=0, tight ld"
-                                  + ("" if world == 1 else f"; global m={n * world} row-sharded, B broadcast from rank 0 over NCCL every step"),
+           "config": {"workload": WORKLOAD.format(n=n, s=s),
+                      "sharding": "none" if world == 1 else f"one {n}-row block of A and C per GPU (global m={n * world}), B broadcast "
+                                  f"from rank 0 inside every step (library NCCL communicator, {panels} column panels)",
                       "timing": "CUDA events on the call stream, inputs (1 GiB) larger than L2 (126 MB) so no flush",
                       "parallelism": f"rows{world}"},
-           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": base}
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": base,
+           "per_rank_ms": per_rank, "bcast_ms": bcast_ms, "parity": parity,
+           "tc_fraction": int8_ops_rank / ms / 1e9 / (2.0 * peaks["bf16"]), "config4": config4}
     return out if rank == 0 else {}
 
 
@@ -418,7 +544,7 @@ def run_reference(args) -> dict:
             "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 (int32 products, f64 accumulation; f64 in/out)",
             "data": "synthetic urand01 (0,1], seeded torch.rand on device",
-            "config": {"workload": f"DGEMM N/N {n}x{n}x{n}, fp64_int8_{s}, alpha=1 beta=0, tight ld",
+            "config": {"workload": WORKLOAD.format(n=n, s=s),
                        "timing": "CUDA events, inputs larger than L2"},
             "clocks": clocks,
             "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": 0, "kind": "reference",

@@ -284,6 +284,49 @@ int ozimmu_gemm_host(ozimmu_handle_t handle, int op_a, int op_b, size_t m, size_
                      const double *alpha, const double *a, size_t lda, const double *b, size_t ldb,
                      const double *beta, double *c, size_t ldc, int compute_mode);
 
+/* ---------------------------------------------------------------------------------------
+ * 3. Multi-GPU (one process per GPU; not in the reference, which is single-GPU -- SURVEY 8e, BASELINE config 4)
+ *
+ * Rank g owns a row block of A and of C (ozimmu_row_block), B is replicated from its owner rank by NCCL broadcasts
+ * over NVLink / NVSwitch, every rank runs the single-GPU path on its block: no reduction between ranks (K is never
+ * split), so each block is bit-identical to the same rows of a single-GPU ozimmu_gemm.  NCCL is resolved at run time
+ * (the libnccl the process has loaded, else libnccl.so.2); the library has no link-time dependency on it.
+ * ------------------------------------------------------------------------------------- */
+typedef struct ozimmu_comm_s *ozimmu_comm_t;
+/* rank 0: 128 bytes to hand to every rank (ncclGetUniqueId) by whatever means the application has */
+int ozimmu_comm_unique_id(void *id128);
+/* collective: this process joins as `rank` of `nranks` on its current CUDA device (ncclCommInitRank) */
+int ozimmu_comm_create(ozimmu_comm_t *comm, int nranks, int rank, const void *id128);
+/* wrap a ncclComm_t the application already owns (not destroyed by ozimmu_comm_destroy) */
+int ozimmu_comm_adopt(ozimmu_comm_t *comm, void *nccl_comm);
+int ozimmu_comm_destroy(ozimmu_comm_t comm);
+int ozimmu_comm_rank(ozimmu_comm_t comm);
+int ozimmu_comm_size(ozimmu_comm_t comm);
+/* rows [*row0, *row0 + *rows) of an m-row matrix that rank `rank` of `nranks` owns: blocks of ceil(m / nranks) rows,
+ * the last one short (possibly empty) */
+void ozimmu_row_block(size_t m, int nranks, int rank, size_t *row0, size_t *rows);
+
+/* C_block = alpha * op(A_block) * op(B) + beta * C_block on every rank, device operands, asynchronous on the handle's
+ * stream.  a_block / c_block: this rank's m_local rows (column-major); b: a device buffer for the full B on every
+ * rank whose CONTENT is taken from rank src_rank (the broadcast overwrites the other ranks' copies).  max_panels > 1
+ * (op_n B, fp64_int8_S): B travels in up to max_panels column panels on the communicator's stream and each panel of C
+ * starts as soon as its columns have landed; max_panels <= 1: one broadcast, then one product launch.  Collective. */
+int ozimmu_gemm_sharded(ozimmu_handle_t handle, ozimmu_comm_t comm, int op_a, int op_b, size_t m_local, size_t n, size_t k,
+                        const double *alpha, const double *a_block, size_t lda, double *b, size_t ldb, const double *beta,
+                        double *c_block, size_t ldc, int compute_mode, int src_rank, unsigned max_panels);
+
+/* The same with HOST operands (pinned for full speed): a_block / c_block are this rank's rows in host memory, b is read
+ * on rank src_rank only (NULL elsewhere).  Every rank uploads its blocks of A over its own PCIe link; the owner uploads
+ * B block by block in between and broadcasts each block over NVLink as it lands; products start per block pair as in
+ * ozimmu_gemm_host.  Returns when this rank's block of C is complete.  Collective. */
+int ozimmu_gemm_sharded_host(ozimmu_handle_t handle, ozimmu_comm_t comm, int op_a, int op_b, size_t m_local, size_t n,
+                             size_t k, const double *alpha, const double *a_block, size_t lda, const double *b, size_t ldb,
+                             const double *beta, double *c_block, size_t ldc, int compute_mode, int src_rank);
+
+/* Diagnostic: the column-panel boundaries ozimmu_gemm_sharded broadcasts B in (ascending, edges[0] = 0, last = n, inner
+ * edges multiples of 256).  Writes min(count, capacity) entries, returns count. */
+size_t ozimmu_sharded_panel_edges(size_t n, size_t max_panels, size_t *edges, size_t capacity);
+
 /* Diagnostic: the block boundaries ozimmu_gemm_host cuts an operand of `extent` rows into for a requested block
  * edge `want` (0 = one block) -- ascending, edges[0] = 0, last = extent, inner edges multiples of 256, at most 17
  * entries.  Writes min(count, capacity) entries, returns count. */

@@ -6,7 +6,7 @@ Python mirror of the reference's public interface over that C-ABI.
 """
 from ._lib import LIB_PATH, build, lib  # noqa: F401
 from .api import *  # noqa: F401,F403
-from .sharded import column_panels, row_block, sharded_gemm  # noqa: F401
+from .sharded import Comm, column_panels, comm_create, row_block, sharded_gemm, sharded_gemm_host  # noqa: F401
 from .api import (auto_mode_select, compute_mode_t, create, destroy, element_kind_t, fp64_int8, gemm, gemm_host,  # noqa: F401
                   gemm_strided_batched, gemm_streamed_b,
                   get_bits_per_int8, get_compute_mode_name_str, handle_t, launch_count, malloc_mode_t, num_split_of,

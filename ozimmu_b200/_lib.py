@@ -85,6 +85,19 @@ PROTOTYPES = {
     "ozimmu_gemm_host": (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t,
                                  c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int]),
     "ozimmu_host_block_edges": (c_size_t, [c_size_t, c_size_t, c_int, c_void_p, c_size_t]),
+    "ozimmu_comm_unique_id": (c_int, [c_void_p]),
+    "ozimmu_comm_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_void_p]),
+    "ozimmu_comm_adopt": (c_int, [C.POINTER(c_void_p), c_void_p]),
+    "ozimmu_comm_destroy": (c_int, [c_void_p]),
+    "ozimmu_comm_rank": (c_int, [c_void_p]),
+    "ozimmu_comm_size": (c_int, [c_void_p]),
+    "ozimmu_row_block": (None, [c_size_t, c_int, c_int, C.POINTER(c_size_t), C.POINTER(c_size_t)]),
+    "ozimmu_gemm_sharded": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p,
+                                    c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_int, c_uint]),
+    "ozimmu_gemm_sharded_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_void_p,
+                                         c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int,
+                                         c_int]),
+    "ozimmu_sharded_panel_edges": (c_size_t, [c_size_t, c_size_t, c_void_p, c_size_t]),
     "ozimmu_launch_count": (C.c_ulonglong, []),
 }
 

@@ -27,6 +27,7 @@
 #include "host.hpp"
 #include "oz_common.cuh"
 #include "ozimmu_b200.h"
+#include "sharded.hpp"
 
 using namespace mtk::ozimmu;
 namespace H = oz::host;
@@ -113,14 +114,22 @@ void copy_matrix(double *dst, const double *src, std::size_t ld, std::size_t row
   }
 }
 
+// comm == nullptr (or a communicator of one rank): the single-GPU entry.  Otherwise this rank's row block of the
+// sharded product (m = its rows of op(A) and C): B lives in the HOST memory of rank `src` only (b is ignored elsewhere);
+// the owner uploads it block by block between its own blocks of A and broadcasts every block over NVLink as soon as it
+// has landed, the other ranks receive the blocks on the communicator's stream while their own blocks of A arrive over
+// their own PCIe links.  Each rank then runs exactly the single-GPU block pipeline, with "block of B has arrived"
+// signalled by the broadcast instead of the H2D copy.
 int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, std::size_t n, std::size_t k,
                    double alpha, const double *a, std::size_t lda, const double *b, std::size_t ldb, double beta,
-                   double *c, std::size_t ldc, compute_mode_t mode) {
-  if ((op_a == op_n ? m : k) > lda || (op_b == op_n ? k : n) > ldb || m > ldc) {
-    H::log_error("ozimmu_gemm_host: leading dimension smaller than the matrix");
+                   double *c, std::size_t ldc, compute_mode_t mode, H::Comm *comm = nullptr, int src = 0) {
+  const bool sharded = comm != nullptr && comm->size > 1;
+  const bool owner = !sharded || comm->rank == src;   // B's host copy is here
+  if ((op_a == op_n ? m : k) > lda || (op_b == op_n ? k : n) > ldb || m > ldc || (sharded && (src < 0 || src >= comm->size))) {
+    H::log_error("ozimmu_gemm_host: leading dimension smaller than the matrix (or bad owner rank)");
     return 1;
   }
-  if (m == 0 || n == 0) return 0;
+  if (n == 0 || (m == 0 && !sharded)) return 0;
   H::ensure_pipeline_streams(h);
   H::ensure_streams(h);
   const std::size_t a_rows = (op_a == op_n) ? m : k, a_cols = (op_a == op_n) ? k : m;
@@ -135,9 +144,14 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
 
   const bool pipelined = H::is_int8_mode(mode) && k > 0 && !h->profiler.enabled;
   if (!pipelined) {
-    // one-shot: copy in, run the device entry, copy out
+    // one-shot: copy in (sharded: B from its owner, then one broadcast), run the device entry, copy out
     copy_matrix(da, a, lda, a_rows, a_cols, cudaMemcpyHostToDevice, sc);
-    copy_matrix(db, b, ldb, b_rows, b_cols, cudaMemcpyHostToDevice, sc);
+    if (owner) copy_matrix(db, b, ldb, b_rows, b_cols, cudaMemcpyHostToDevice, sc);
+    if (sharded) H::comm_broadcast_f64(comm, db, b_cols == 0 ? 0 : ldb * (b_cols - 1) + b_rows, src, sc);
+    if (m == 0) {
+      OZ_CUDA_CHECK(cudaStreamSynchronize(sc));
+      return 0;
+    }
     if (beta != 0) copy_matrix(dc, c, ldc, m, n, cudaMemcpyHostToDevice, sc);
     cudaStream_t saved = h->cuda_stream;
     h->cuda_stream = sc;
@@ -166,9 +180,13 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   // OZIMMU_B200_E2E_TAPER=1 halves the last blocks (less work behind the last byte); measured +-0 at the default
   // edge of 768, +0.5 ms better at 1024 (profiles/r1_e2e_block_sweep.txt): off by default.
   const bool taper = env_size("OZIMMU_B200_E2E_TAPER", 0) != 0;
-  const std::vector<std::size_t> be = block_edges(n, want_cols == 0 ? n : want_cols, taper && want_cols != 0);
-  const std::vector<std::size_t> ae = block_edges(m, want_rows == 0 ? m : want_rows, taper && want_rows != 0);
-  const std::size_t nbb = be.size() - 1, nab = ae.size() - 1;
+  // sharded: a block of B is one broadcast, so it must be contiguous -- column panels of an op_n B; an op_t B (its
+  // column panels are row ranges of the stored matrix) travels in one piece
+  const bool b_whole = want_cols == 0 || (sharded && op_b != op_n);
+  const std::vector<std::size_t> be = block_edges(n, b_whole ? n : want_cols, taper && !b_whole);
+  const std::vector<std::size_t> ae = m == 0 ? std::vector<std::size_t>{0, 0}
+                                             : block_edges(m, want_rows == 0 ? m : want_rows, taper && want_rows != 0);
+  const std::size_t nbb = be.size() - 1, nab = m == 0 ? 0 : ae.size() - 1;
 
   const H::WorkspaceLayout w = H::workspace_layout(m, n, k, s);
   reallocate_working_memory(h, w.total);
@@ -190,15 +208,37 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     }
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[0][i], sin));
   };
+  // the element range of db that holds block j of op(B) when blocks are broadcast (contiguous by construction)
+  auto b_block_range = [&](std::size_t j, std::size_t &first, std::size_t &count) {
+    const std::size_t j0 = be[j], nj = be[j + 1] - j0;
+    if (op_b == op_n) {
+      first = j0 * ldb;
+      count = (j + 1 == nbb) ? (nj - 1) * ldb + k : nj * ldb;
+    } else {   // one block: the whole stored n x k matrix
+      first = 0;
+      count = ldb * (k - 1) + n;
+    }
+  };
   auto copy_b_block = [&](std::size_t j) {
     const std::size_t j0 = be[j], nj = be[j + 1] - j0;
-    if (op_b == op_n) {  // k x n column-major: a column panel is contiguous
-      copy_matrix(db + j0 * ldb, b + j0 * ldb, ldb, k, nj, cudaMemcpyHostToDevice, sin);
-    } else {             // n x k column-major: rows j0..j0+nj of every column
-      copy_matrix(db + j0, b + j0, ldb, nj, k, cudaMemcpyHostToDevice, sin);
+    if (owner) {
+      if (op_b == op_n) {  // k x n column-major: a column panel is contiguous
+        copy_matrix(db + j0 * ldb, b + j0 * ldb, ldb, k, nj, cudaMemcpyHostToDevice, sin);
+      } else {             // n x k column-major: rows j0..j0+nj of every column
+        copy_matrix(db + j0, b + j0, ldb, nj, k, cudaMemcpyHostToDevice, sin);
+      }
     }
-    if (beta != 0) copy_matrix(dc + j0 * ldc, c + j0 * ldc, ldc, m, nj, cudaMemcpyHostToDevice, sin);
+    if (beta != 0 && m != 0) copy_matrix(dc + j0 * ldc, c + j0 * ldc, ldc, m, nj, cudaMemcpyHostToDevice, sin);
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[1][j], sin));
+    if (sharded) {
+      // the owner forwards the block as soon as it is on its GPU; everybody else's copy arrives here.  All ranks
+      // issue the broadcasts in block order on their communicator stream.
+      std::size_t first, count;
+      b_block_range(j, first, count);
+      OZ_CUDA_CHECK(cudaStreamWaitEvent(comm->stream, h->ev_block_in[1][j], 0));  // owner: H2D done; others: C panel (beta)
+      H::comm_broadcast_f64(comm, db + first, count, src, comm->stream);
+      if (!owner) OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[1][j], comm->stream));
+    }
   };
   auto split_a_block = [&](std::size_t i) {
     const std::size_t i0 = ae[i], mi = ae[i + 1] - i0;
@@ -262,14 +302,21 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   };
 
   // arrival order: B0, A0, B1, A1, ... (the longer operand's remaining blocks follow at the end); queue every
-  // copy first so the H2D engine never waits for the host
+  // copy first so the H2D engine never waits for the host.  A rank that receives B by broadcast has its PCIe link to
+  // itself for A, while B arrives at the pace of the owner's alternating uploads: two blocks of A per block of B.
   struct Arrival { int which; std::size_t idx; };
   std::vector<Arrival> order;
+  const std::size_t a_per_b = owner ? 1 : 2;
   for (std::size_t ia = 0, ib = 0; ia < nab || ib < nbb;) {
-    if (ib < nbb && (ib <= ia || ia >= nab)) order.push_back({1, ib++});
+    if (ib < nbb && (ib * a_per_b <= ia || ia >= nab)) order.push_back({1, ib++});
     else order.push_back({0, ia++});
   }
 
+  if (sharded) {
+    // the communicator stream joins this call: the previous call's last broadcast is already ordered before it
+    OZ_CUDA_CHECK(cudaEventRecord(comm->ev_begin, sc));
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(comm->stream, comm->ev_begin, 0));
+  }
   for (const Arrival &x : order) x.which ? copy_b_block(x.idx) : copy_a_block(x.idx);
 
   std::size_t have_a = 0, have_b = 0;  // blocks split so far
@@ -290,6 +337,10 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_product_tail[r], h->product_stream[r]));
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, h->ev_product_tail[r], 0));
   }
+  if (sharded) {
+    OZ_CUDA_CHECK(cudaEventRecord(comm->ev_end, comm->stream));   // the owner's sends read db until here
+    OZ_CUDA_CHECK(cudaStreamWaitEvent(sc, comm->ev_end, 0));
+  }
   OZ_CUDA_CHECK(cudaEventRecord(h->ev_done, sc));
   h->has_pending = true;
   h->last_stream = sc;
@@ -299,6 +350,26 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
 }
 
 }  // namespace
+
+// Row block of a sharded DGEMM with HOST operands (see gemm_host_impl): a_block / c_block are this rank's rows, b is
+// read on rank src_rank only.  Collective over the communicator; returns when this rank's block of C is complete.
+extern "C" int ozimmu_gemm_sharded_host(ozimmu_handle_t handle, ozimmu_comm_t comm, int op_a, int op_b, size_t m_local,
+                                        size_t n, size_t k, const double *alpha, const double *a_block, size_t lda,
+                                        const double *b, size_t ldb, const double *beta, double *c_block, size_t ldc,
+                                        int compute_mode, int src_rank) {
+  if (handle == nullptr || alpha == nullptr || beta == nullptr || compute_mode < 0 ||
+      compute_mode > OZIMMU_FP64_INT8_AUTO)
+    return 1;
+  try {
+    return gemm_host_impl(reinterpret_cast<handle_t>(handle), static_cast<operation_t>(op_a != 0),
+                          static_cast<operation_t>(op_b != 0), m_local, n, k, *alpha, a_block, lda, b, ldb, *beta, c_block,
+                          ldc, static_cast<compute_mode_t>(compute_mode), reinterpret_cast<H::Comm *>(comm), src_rank);
+  } catch (const std::exception &e) {
+    cudaDeviceSynchronize();
+    H::log_error(e.what());
+    return -1;
+  }
+}
 
 // Diagnostic: the block boundaries ozimmu_gemm_host uses for one operand (CPU-testable host logic).
 extern "C" size_t ozimmu_host_block_edges(size_t extent, size_t want, int taper, size_t *edges, size_t capacity) {

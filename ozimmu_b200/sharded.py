@@ -1,179 +1,104 @@
-"""Row-block sharding of one DGEMM over the GPUs of a box: rank g owns the rows
-[g*bm, min(m, (g+1)*bm)) of A and C, B is replicated by ONE broadcast from the owner rank
-(NCCL over NVLink 5 / NVSwitch through torch.distributed), and every rank runs the single-GPU path
-on its block.  Bit-identical to the one-GPU result: the split scales A per row and B per column and
-K is never partitioned, so no cross-shard reduction exists.
+"""Row-block sharding of one DGEMM over the GPUs of a box (BASELINE config 4) -- a thin mirror of the
+multi-GPU section of the C-ABI (include/ozimmu_b200.h, csrc/sharded.cpp, csrc/host_e2e.cu).
 
-`pipeline=True` (op_n B) sends B in contiguous column panels and hands the panels' arrival events to
-`gemm_streamed_b`: split(A) runs while the first panel is on the wire, and every panel of C is computed as soon
-as its columns of B have landed (the fused launches rotate over several streams, so a launch back-fills the SMs
-its predecessor leaves idle in its last round of tiles).  `pipeline=False` (default) is one broadcast followed
-by one product launch.  Measured on 2 x B200 at 8192 rows per rank the pipeline is SLOWER (21.1 vs 19.1 ms per step,
-profiles/r1_bench_2gpu_streamed_b.txt): NCCL's broadcast kernels need SMs of their own, the persistent product
-kernel occupies every SM, so each later panel's broadcast waits for a whole round of tiles to drain.  It pays only
-when the transport does not need SMs (copy-engine peer copies, host staging) -- kept for those callers.
+Rank g owns the rows [g*bm, min(m, (g+1)*bm)) of A and C, B is replicated from its owner rank by NCCL broadcasts over
+NVLink 5 / NVSwitch (in column panels, each panel of C starting as soon as its columns have landed), and every rank
+runs the single-GPU path on its block.  Bit-identical to the one-GPU result: the split scales A per row and B per
+column and K is never partitioned, so no cross-shard reduction exists.
+
+The communicator is the library's own (ncclCommInitRank inside libozimmu.so, NCCL resolved at run time); Python only
+ships the 128-byte NCCL unique id from rank 0 to the other ranks -- here through torch.distributed, which an
+application would replace by whatever bootstrap it has (MPI, a file, a socket).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Optional, Tuple
 
-from . import api
+from . import _lib, api
 
 
 def row_block(m: int, world_size: int, rank: int) -> Tuple[int, int]:
     """(first row, number of rows) of rank's block; blocks are ceil(m / world) tall, the last one short."""
     if world_size <= 0 or not 0 <= rank < world_size:
         raise ValueError("bad rank / world size")
-    bm = -(-m // world_size)
-    r0 = min(m, rank * bm)
-    return r0, max(0, min(bm, m - r0))
+    r0, rows = C.c_size_t(), C.c_size_t()
+    _lib.lib().ozimmu_row_block(m, world_size, rank, C.byref(r0), C.byref(rows))
+    return int(r0.value), int(rows.value)
 
 
-def column_panels(n: int, max_panels: int = 4, min_width: int = 1024) -> List[Tuple[int, int]]:
-    """(first column, width) of the broadcast panels: equal widths, multiples of 256 (the kernel's tile and the
-    block-wise split's granularity), at least min_width."""
-    panels = max(1, min(max_panels, n // max(1, min_width)))
-    w = -(-n // panels)
-    w = -(-w // 256) * 256
-    out = []
-    j = 0
-    while j < n:
-        out.append((j, min(w, n - j)))
-        j += w
-    return out
+def column_panels(n: int, max_panels: int = 8) -> List[Tuple[int, int]]:
+    """(first column, width) of the panels B is broadcast in: equal widths, multiples of 256 (the kernel's tile and the
+    block-wise split's granularity), at least 1024 wide."""
+    edges = (C.c_size_t * 32)()
+    cnt = int(_lib.lib().ozimmu_sharded_panel_edges(n, max_panels, C.addressof(edges), 32))
+    e = [int(edges[i]) for i in range(cnt)]
+    return [(a, b - a) for a, b in zip(e, e[1:])]
 
 
-def sharded_gemm(handle: api.handle_t, op_A: int, op_B: int, m_local: int, n: int, k: int, alpha: float, a_block,
-                 lda: int, b, ldb: int, beta: float, c_block, ldc: int, compute_mode, *, src: int = 0, group=None,
-                 pipeline: bool = False, transport: str = "nccl") -> int:
-    """C_block = alpha * op(A_block) * op(B) + beta * C_block on every rank.
+class Comm:
+    """One communicator of the library (ozimmu_comm_t) on the current CUDA device."""
 
-    a_block / c_block: this rank's rows (device, column-major).  b: device buffer of the full B on every
-    rank; its CONTENT is taken from rank `src` (the broadcast overwrites the other ranks' copies).
-    Without an initialised process group (single GPU) this is a plain api.gemm.
+    def __init__(self, raw: int, rank: int, size: int):
+        self.raw, self.rank, self.size = raw, rank, size
 
-    transport="nccl": B is replicated by a NCCL broadcast (`pipeline` = in column panels feeding gemm_streamed_b).
-    transport="peer" (op_n B): every rank PULLS B's column panels from the owner's buffer over NVLink with the copy
-    engines (CUDA IPC mapping of the owner's allocation, established on first use of a buffer) and computes each
-    panel of C as it lands -- no SMs are needed for the transfer, so it overlaps the persistent product kernel.
-    The owner must not overwrite B before its next collective call on the same group.
-    """
-    import torch
+    def destroy(self) -> None:
+        if self.raw:
+            _lib.lib().ozimmu_comm_destroy(self.raw)
+            self.raw = 0
+
+
+def exchange_unique_id(make_id, rank: int, group=None, src: int = 0) -> bytes:
+    """rank `src` calls make_id() -> 128 bytes; every rank of the torch.distributed group returns those bytes"""
     import torch.distributed as dist
+    payload = [make_id() if rank == src else None]
+    dist.broadcast_object_list(payload, src=src, group=group)
+    uid = bytes(payload[0])
+    if len(uid) != 128:
+        raise RuntimeError("NCCL unique id must be 128 bytes")
+    return uid
 
+
+def _make_unique_id() -> bytes:
+    buf = (C.c_ubyte * 128)()
+    api._check(_lib.lib().ozimmu_comm_unique_id(C.addressof(buf)), "comm_unique_id")
+    return bytes(buf)
+
+
+def comm_create(group=None) -> Optional[Comm]:
+    """Collective over a torch.distributed group (one process per GPU, torch.cuda current device = this rank's GPU):
+    the library's own NCCL communicator for the group.  None without an initialised group / with one rank."""
+    import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return api.gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
-                        compute_mode)
-    flat = b.view(-1)
-    if transport == "peer" and int(op_B) == int(api.op_n) and n >= 2 * _MIN_PANEL:
-        return _peer_pull_gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
-                               compute_mode, src, group)
-    if not pipeline or int(op_B) != int(api.op_n) or m_local == 0 or n < 2 * _MIN_PANEL:
-        dist.broadcast(flat, src=src, group=group)
-        if m_local == 0:
-            return 0
-        return api.gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
-                        compute_mode)
-    # op_n B: k x n column-major, panel [j0, j0 + w) is the contiguous range [j0*ldb, (j0+w)*ldb)
-    panels = column_panels(n, max_panels=8, min_width=_MIN_PANEL)
-    side = _side_stream()
-    side.wait_stream(torch.cuda.current_stream())     # whatever produced / last read `b` on this stream
-    events = []
-    with torch.cuda.stream(side):
-        for (j0, w) in panels:
-            hi = min(flat.numel(), (j0 + w) * ldb)
-            work = dist.broadcast(flat[j0 * ldb:hi], src=src, group=group, async_op=True)
-            work.wait()                               # orders `side` after this panel's broadcast
-            ev = torch.cuda.Event()
-            ev.record(side)
-            events.append(ev)
-    edges = [j0 for (j0, _) in panels] + [n]
-    rc = api.gemm_streamed_b(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
-                             compute_mode, edges, [ev.cuda_event for ev in events])
-    _keep_alive(events)
-    return rc
+        return None
+    rank, size = dist.get_rank(group), dist.get_world_size(group)
+    uid = exchange_unique_id(_make_unique_id, rank, group)
+    raw = C.c_void_p()
+    buf = (C.c_ubyte * 128).from_buffer_copy(uid)
+    api._check(_lib.lib().ozimmu_comm_create(C.byref(raw), size, rank, C.addressof(buf)), "comm_create")
+    return Comm(raw.value, rank, size)
 
 
-_MIN_PANEL = 1024
-_side = {}
-_live_events: list = []
+def sharded_gemm(handle: api.handle_t, comm: Optional[Comm], op_A: int, op_B: int, m_local: int, n: int, k: int,
+                 alpha: float, a_block, lda: int, b, ldb: int, beta: float, c_block, ldc: int, compute_mode, *,
+                 src: int = 0, max_panels: int = 8) -> int:
+    """C_block = alpha * op(A_block) * op(B) + beta * C_block on every rank (device operands, asynchronous on the
+    handle's stream).  b: device buffer of the full B on every rank; its CONTENT is taken from rank `src`.
+    comm=None: a plain single-GPU gemm."""
+    al, be = C.c_double(alpha), C.c_double(beta)
+    rc = _lib.lib().ozimmu_gemm_sharded(handle.raw, comm.raw if comm else None, int(op_A), int(op_B), m_local, n, k,
+                                        C.addressof(al), api._ptr(a_block), lda, api._ptr(b), ldb, C.addressof(be),
+                                        api._ptr(c_block), ldc, int(compute_mode), src, max_panels)
+    return api._check(rc, "gemm_sharded")
 
 
-def _side_stream():
-    """one broadcast-ordering stream per device"""
-    import torch
-    dev = torch.cuda.current_device()
-    if dev not in _side:
-        _side[dev] = torch.cuda.Stream(device=dev)
-    return _side[dev]
-
-
-def _keep_alive(events) -> None:
-    """the library's streams still wait on these events after this call returns: keep the last two calls' events"""
-    _live_events.append(events)
-    del _live_events[:-2]
-
-
-_peer_views: dict = {}
-
-
-def _peer_view(b, src: int, group):
-    """the owner's B buffer mapped into this process (CUDA IPC), established once per buffer; collective"""
-    import torch
-    import torch.distributed as dist
-    from torch.multiprocessing.reductions import reduce_tensor
-
-    key = (b.data_ptr(), b.numel(), src, id(group))
-    if key not in _peer_views:
-        rank = dist.get_rank(group)
-        payload = [reduce_tensor(b.view(-1)) if rank == src else None]
-        dist.broadcast_object_list(payload, src=src, group=group)
-        if rank == src:
-            view = b.view(-1)
-        else:
-            rebuild, args = payload[0]
-            view = rebuild(*args)          # a tensor on the owner's device, readable from here over NVLink
-        _peer_views[key] = view
-    return _peer_views[key]
-
-
-def _peer_pull_gemm(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc, compute_mode,
-                    src, group) -> int:
-    import torch
-    import torch.distributed as dist
-
-    rank = dist.get_rank(group)
-    flat = b.view(-1)
-    peer = _peer_view(b, src, group)
-    # the owner's B is final once every rank has passed this point in stream order (and the previous call's pulls
-    # have completed: each rank's stream waited for them before it got here)
-    dist.barrier(group=group)
-    panels = column_panels(n, max_panels=8, min_width=_MIN_PANEL)
-    cur = torch.cuda.current_stream()
-    events = []
-    if rank == src:
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        events = [ev] * len(panels)
-    else:
-        side = _side_stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for (j0, w) in panels:
-                hi = min(flat.numel(), (j0 + w) * ldb)
-                flat[j0 * ldb:hi].copy_(peer[j0 * ldb:hi], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(side)
-                events.append(ev)
-    if m_local == 0:
-        rc = 0
-        for ev in events:
-            cur.wait_event(ev)
-    else:
-        edges = [j0 for (j0, _) in panels] + [n]
-        rc = api.gemm_streamed_b(handle, op_A, op_B, m_local, n, k, alpha, a_block, lda, b, ldb, beta, c_block, ldc,
-                                 compute_mode, edges, [ev.cuda_event for ev in events])
-        if rank != src:
-            cur.wait_event(events[-1])   # the next call's barrier is ordered after this call's last pull
-    _keep_alive(events)
-    return rc
+def sharded_gemm_host(handle: api.handle_t, comm: Optional[Comm], op_A: int, op_B: int, m_local: int, n: int, k: int,
+                      alpha: float, a_block_host, lda: int, b_host, ldb: int, beta: float, c_block_host, ldc: int,
+                      compute_mode, *, src: int = 0) -> int:
+    """The same with HOST operands (pinned CPU tensors / numpy arrays): b_host is read on rank `src` only (may be None
+    elsewhere); returns when this rank's block of C is complete."""
+    al, be = C.c_double(alpha), C.c_double(beta)
+    rc = _lib.lib().ozimmu_gemm_sharded_host(handle.raw, comm.raw if comm else None, int(op_A), int(op_B), m_local, n, k,
+                                             C.addressof(al), api._ptr(a_block_host), lda, api._ptr(b_host), ldb,
+                                             C.addressof(be), api._ptr(c_block_host), ldc, int(compute_mode), src)
+    return api._check(rc, "gemm_sharded_host")

@@ -1,5 +1,6 @@
-"""-m gpu: the multi-GPU path on real devices (skipped with fewer than 2 GPUs): 2 ranks, NCCL broadcast of
-B, row blocks of A/C -- the concatenated result equals the single-GPU product bit for bit."""
+"""-m gpu: the multi-GPU path on real devices (skipped with fewer than 2 GPUs): 2 ranks, the library's own NCCL
+communicator, row blocks of A/C, B broadcast whole / in column panels / block by block from the owner's host memory --
+every variant's concatenated result equals the single-GPU product bit for bit."""
 import os
 import subprocess
 import sys
@@ -18,30 +19,46 @@ import ozimmu_b200 as oz, oracle_lib
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+comm = oz.comm_create()
+assert comm is not None and comm.rank == rank and comm.size == world
 m, n, k, s = 1100, 2300, 700, 9
 A = torch.from_numpy(oracle_lib.gen_matrix("exp_rand-1", m * k, 5)).view(k, m)   # column-major m x k
 r0, rows = oz.row_block(m, world, rank)
-a_blk = A[:, r0:r0 + rows].contiguous().cuda()
-b = (torch.from_numpy(oracle_lib.gen_matrix("exp_rand-1", k * n, 6)) if rank == 0 else torch.zeros(k * n, dtype=torch.float64)).cuda()
+a_host = A[:, r0:r0 + rows].contiguous().pin_memory()
+a_blk = a_host.cuda()
+b_host = torch.from_numpy(oracle_lib.gen_matrix("exp_rand-1", k * n, 6)).pin_memory() if rank == 0 else None
+b = b_host.cuda() if rank == 0 else torch.zeros(k * n, dtype=torch.float64, device="cuda")
 c_blk = torch.zeros(n, rows, dtype=torch.float64, device="cuda")
 h = oz.create()
-assert oz.sharded_gemm(h, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_blk, rows, oz.fp64_int8(s), src=0) == 0
+# one broadcast, then one product launch
+assert oz.sharded_gemm(h, comm, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_blk, rows, oz.fp64_int8(s), src=0, max_panels=1) == 0
 torch.cuda.synchronize()
-c_pipe = torch.zeros_like(c_blk)
-if rank != 0:
-    b.zero_()
-assert oz.sharded_gemm(h, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_pipe, rows, oz.fp64_int8(s), src=0, pipeline=True) == 0
-torch.cuda.synchronize()
-assert torch.equal(c_pipe.view(torch.int64), c_blk.view(torch.int64)), "panel-pipelined broadcast differs"
-for rep in range(2):   # second call reuses the cached IPC mapping of B
-    c_peer = torch.zeros_like(c_blk)
+# B in column panels, every panel of C as soon as its columns have landed (twice: events and buffers are reused)
+for rep in range(2):
+    c_pipe = torch.zeros_like(c_blk)
     if rank != 0:
         b.zero_()
-    assert oz.sharded_gemm(h, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_peer, rows, oz.fp64_int8(s), src=0, transport="peer") == 0
+    assert oz.sharded_gemm(h, comm, 0, 0, rows, n, k, 1.0, a_blk, rows, b, k, 0.0, c_pipe, rows, oz.fp64_int8(s), src=0, max_panels=2) == 0
     torch.cuda.synchronize()
-    assert torch.equal(c_peer.view(torch.int64), c_blk.view(torch.int64)), "peer-pull transport differs"
+    assert torch.equal(c_pipe.view(torch.int64), c_blk.view(torch.int64)), "panel-pipelined broadcast differs"
+# host operands: every rank uploads its rows of A, rank 0 uploads and forwards B block by block
+for env in ({}, {"OZIMMU_B200_E2E_PANEL": "1024", "OZIMMU_B200_E2E_ROWBLOCK": "256"}):
+    os.environ.update(env)
+    c_host = torch.zeros(n, rows, dtype=torch.float64).pin_memory()
+    assert oz.sharded_gemm_host(h, comm, 0, 0, rows, n, k, 1.0, a_host, rows, b_host, k, 0.0, c_host, rows, oz.fp64_int8(s), src=0) == 0
+    assert torch.equal(c_host.view(torch.int64), c_blk.cpu().view(torch.int64)), "host-operand sharded entry differs"
+# op_t B (one block, one broadcast) and beta != 0 through the host entry
+Bt = torch.from_numpy(oracle_lib.gen_matrix("exp_rand-1", k * n, 6)).view(n, k).T.contiguous()   # n x k column-major
+bt_host = Bt.pin_memory() if rank == 0 else None
+c0 = torch.from_numpy(oracle_lib.gen_matrix("normal01", n * rows, 7 + rank)).view(n, rows)
+c_dev = c0.cuda()
+assert oz.gemm(h, 0, 0, rows, n, k, 1.5, a_blk, rows, b, k, -0.5, c_dev, rows, oz.fp64_int8(s)) == 0
+c_host = c0.clone().pin_memory()
+assert oz.sharded_gemm_host(h, comm, 0, 1, rows, n, k, 1.5, a_host, rows, bt_host, n, -0.5, c_host, rows, oz.fp64_int8(s), src=0) == 0
+torch.cuda.synchronize()
+assert torch.equal(c_host.view(torch.int64), c_dev.cpu().view(torch.int64)), "op_t B / beta host-operand sharded entry differs"
 torch.save(c_blk.cpu(), os.environ["OZ_OUT"] + f"/c_{rank}.pt")
-dist.barrier(); oz.destroy(h); dist.destroy_process_group()
+dist.barrier(); oz.destroy(h); comm.destroy(); dist.destroy_process_group()
 """
 
 

@@ -1,6 +1,7 @@
-"""CPU: host logic of the multi-GPU path -- the row-block partition covers every row exactly once, and a
-world_size-2 gloo run of the broadcast + per-rank product (the per-rank product stood in for by the CPU
-oracle: no GPU here) reproduces the single-process result bit for bit."""
+"""CPU: host logic of the multi-GPU path -- the row-block partition (ozimmu_row_block) covers every row exactly once,
+the broadcast panels (ozimmu_sharded_panel_edges) tile the columns on the kernel's granularity, the unique-id exchange
+runs over a world_size-2 gloo group, and a world_size-2 gloo run of the panel broadcast + per-rank product (the
+per-rank product stood in for by the CPU oracle: no GPU here) reproduces the single-process result bit for bit."""
 import os
 import socket
 import sys
@@ -29,6 +30,7 @@ def test_row_blocks_partition(m, world):
 @pytest.mark.parametrize("n", [1, 127, 1024, 4096, 8192, 16384, 5000])
 def test_column_panels_cover(n):
     p = column_panels(n)
+    assert 1 <= len(p) <= 8 and all(w >= min(n, 1024) or i == len(p) - 1 for i, (_, w) in enumerate(p))
     assert p[0][0] == 0 and sum(w for _, w in p) == n
     assert all(p[i][0] + p[i][1] == p[i + 1][0] for i in range(len(p) - 1))
     assert all(j0 % 256 == 0 for j0, _ in p)   # inner edges on the kernel tile / block-split granularity
@@ -48,11 +50,14 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
     import torch
     import torch.distributed as dist
     import oracle_lib
-    from ozimmu_b200.sharded import column_panels, row_block
+    from ozimmu_b200.sharded import column_panels, exchange_unique_id, row_block
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the communicator bootstrap: rank 0's 128-byte id reaches every rank (the id itself needs NCCL: a stand-in here)
+    uid = exchange_unique_id(lambda: bytes(range(128)), rank)
+    assert uid == bytes(range(128))
     m, n, k, s = 70, 1500, 48, 9
     A = oracle_lib.gen_matrix("exp_rand-1", m * k, 11).reshape(k, m)   # column-major m x k
     r0, rows = row_block(m, world, rank)
