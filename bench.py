@@ -363,7 +363,7 @@ def run_config4(oz, h, comm, rank, world, steps: int, peaks: dict) -> dict:
         b.zero_()
     c = torch.zeros(max(rows, 1) * n4, dtype=torch.float64, device="cuda")
     mode = oz.fp64_int8(s)
-    panels = int(os.environ.get("OZIMMU_B200_BENCH_PANELS", "8"))
+    panels = int(os.environ.get("OZIMMU_B200_BENCH_PANELS", "1"))
 
     def step():
         assert oz.sharded_gemm(h, comm, oz.op_n, oz.op_n, rows, n4, n4, 1.0, a, max(rows, 1), b, n4, 0.0, c, max(rows, 1),
@@ -392,9 +392,11 @@ def run_ours(args) -> dict:
     h = oz.create()
     L = oz.lib()
     comm = oz.comm_create()              # the library's own NCCL communicator (None on one GPU)
-    # B travels in up to PANELS column panels on the communicator's stream; every panel of C starts as soon as its
-    # columns have landed (PANELS=1: one broadcast, then one product launch)
-    panels = int(os.environ.get("OZIMMU_B200_BENCH_PANELS", "8"))
+    # OZIMMU_B200_BENCH_PANELS=p > 1: B travels in p column panels on the communicator's stream and every panel of C
+    # starts as soon as its columns have landed.  Default 1 (one broadcast overlapped by split(A), then one product
+    # launch): measured faster on 2 x B200 -- 18.4 ms against 19.7 / 20.5 / 21.0 ms for 2 / 4 / 8 panels
+    # (profiles/r2_sharded_probe_2gpu.txt): NCCL's broadcast CTAs hold SMs on both GPUs until both sides run.
+    panels = int(os.environ.get("OZIMMU_B200_BENCH_PANELS", "1"))
 
     def step():
         assert oz.sharded_gemm(h, comm, oz.op_n, oz.op_n, n, n, n, 1.0, a, n, b, n, 0.0, c, n, mode, src=0,
@@ -489,7 +491,7 @@ def run_ours(args) -> dict:
            "data": "synthetic urand01 (0,1], seeded torch.rand on device",
            "config": {"workload": WORKLOAD.format(n=n, s=s),
                       "sharding": "none" if world == 1 else f"one {n}-row block of A and C per GPU (global m={n * world}), B broadcast "
-                                  f"from rank 0 inside every step (library NCCL communicator, {panels} column panels)",
+                                  f"from rank 0 inside every step (library NCCL communicator, {panels} broadcast panel(s), split(A) overlaps the transfer)",
                       "timing": "CUDA events on the call stream, inputs (1 GiB) larger than L2 (126 MB) so no flush",
                       "parallelism": f"rows{world}"},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": base,

@@ -180,6 +180,13 @@ int ozk_scale_c(size_t m, size_t n, double beta, double *c, size_t ldc, void *st
 int ozk_scale_c_ex(size_t m, size_t n, const double beta[2], const double *beta_dev, int complex_c, void *c,
                    size_t ldc, void *stream);
 
+/* Complex GEMM, second form: the four plane products computed as ordinary REAL products into scratch (alpha = 1,
+ * beta = 0), then folded into C here with exactly the operations and order of the fused complex epilogue (reference
+ * src/gemm.cu:160-239,479-518).  x4 = [4][n][m] doubles, plane (A plane) + 2 * (B plane) with 0 = real, 1 = imaginary.
+ * The host picks this form when 4 x as many, 4 x shorter work items fill the GPU's CTA pairs in fewer rounds. */
+int ozk_zgemm_combine(size_t m, size_t n, const double *x4, const double alpha[2], const double beta[2],
+                      const double *alpha_dev, const double *beta_dev, void *c, size_t ldc, void *stream);
+
 /* Test/tuning hook: force the tile width of the fused kernel: (0, w), w in {128, 192, 208, 224, 240, 256}; anything
  * else restores the per-problem choice (256 or 128).  OZIMMU_B200_TILE_N=w does the same from the environment. */
 int ozk_set_cluster_shape(int cm, int cn);

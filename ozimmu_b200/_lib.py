@@ -46,6 +46,8 @@ PROTOTYPES = {
     "ozk_mantissa_loss_strided": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int, c_uint,
                                           c_uint, c_void_p]),
     "ozk_gemm_i8_fused_ex": (c_int, [c_void_p, c_void_p]),
+    "ozk_zgemm_combine": (c_int, [c_size_t, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
     "ozk_scale_c_ex": (c_int, [c_size_t, c_size_t, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "ozk_split_int8_batched_strided": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t,
                                                c_size_t, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_uint, c_uint,

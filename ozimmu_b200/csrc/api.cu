@@ -85,6 +85,27 @@ struct Scalars {
   const double *alpha_dev = nullptr, *beta_dev = nullptr;
 };
 
+// Complex GEMM: fold the four plane products inside the fused launch (every tile runs 4 x P(s) products), or compute
+// them as 4 x as many real work items into scratch and combine afterwards?  The second form fills the CTA pairs in
+// finer grains; it pays when it saves more rounds of tiles than its extra pass over C costs.  Round time from
+// profiles/r2_sweep_tile_width.txt (1.28 ms per round of 256-wide tiles at P = 45, k = 8192), the combine pass at
+// ~100 bytes per element and ~4 TB/s.  OZIMMU_B200_ZGEMM_PLANES_FIRST=0/1 forces the choice.
+bool complex_planes_first(std::size_t m, std::size_t n, std::size_t pitch, unsigned num_split) {
+  const std::string forced = H::env_or("OZIMMU_B200_ZGEMM_PLANES_FIRST", "");
+  if (forced == "0") return false;
+  if (forced == "1") return true;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const std::size_t pairs = std::max(1, sms / 2);
+  const std::size_t tiles = ((m + 255) / 256) * ((n + 255) / 256);
+  const double round_ms = 1.28 * (static_cast<double>(num_split * (num_split + 1) / 2) * static_cast<double>(pitch)) / (45.0 * 8192.0);
+  const double fused = 4.0 * static_cast<double>((tiles + pairs - 1) / pairs) * round_ms;
+  const double split = 2.0 * static_cast<double>((2 * tiles + pairs - 1) / pairs) * round_ms +
+                       100.0 * static_cast<double>(m) * static_cast<double>(n) / 4.0e9;
+  return split < 0.97 * fused;
+}
+
 // The Ozaki path of every fp64_int8_S GEMM -- real (reference src/gemm.cu:344-410 gemm_int8<double>) or complex
 // (:412-521 gemm_int8<cuDoubleComplex>: the real and imaginary planes of each operand are split independently and four
 // real plane products are folded into C), a single product or a strided batch (the reference's interposers run one
@@ -112,7 +133,8 @@ void gemm_int8(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, st
   const H::WorkspaceLayout w = H::workspace_layout(m, n, k, num_split, es);
   const std::size_t limit = std::stoull(H::env_or("OZIMMU_B200_BATCH_WORKSPACE_MB", "8192")) << 20;
   const std::size_t chunk = std::max<std::size_t>(1, std::min<std::size_t>({batch, limit / w.total, 65535}));
-  reallocate_working_memory(h, w.total * chunk);
+  const bool planes_first = es == 2 && batch == 1 && complex_planes_first(m, n, w.pitch, num_split);
+  reallocate_working_memory(h, w.total * chunk + (planes_first ? 4 * sizeof(double) * m * n : 0));
   ensure_streams(h);
   char *ws = static_cast<char *>(h->working_memory_ptr);
   wait_previous(h, s);
@@ -161,6 +183,32 @@ void gemm_int8(handle_t h, operation_t op_a, operation_t op_b, std::size_t m, st
     if (overlap) {
       OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, sb));
       OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    }
+    // A single complex GEMM whose tile count quantises badly: its four plane products as 4 x as many REAL work items
+    // (two grouped launches of two entries each: the planes of A against one plane of B) into scratch, then one
+    // elementwise pass that folds them into C in the reference's order -- e.g. 4096^3: 2 x 7 rounds of tiles instead of
+    // 4 x 4, at the price of ~100 bytes of scratch traffic per element of C.  Same bits either way.
+    if (es == 2 && batch == 1 && complex_planes_first(m, n, w.pitch, num_split)) {
+      double *x4 = reinterpret_cast<double *>(ws + w.total);
+      h->profiler.start("int8tc_accumulate_fused", s);
+      for (unsigned bp = 0; bp < 2; bp++) {
+        ozk_fused_args_t fa{};
+        fa.m = m, fa.n = n, fa.k = k, fa.pitch = w.pitch;
+        fa.a_slices = reinterpret_cast<const std::int8_t *>(ws + w.off_a_slices);
+        fa.b_slices = reinterpret_cast<const std::int8_t *>(ws + w.off_b_slices + bp * w.b_plane);
+        fa.amax = reinterpret_cast<const double *>(ws + w.off_amax);
+        fa.bmax = reinterpret_cast<const double *>(ws + w.off_bmax) + bp * n;
+        fa.num_split = num_split, fa.bits_per_int8 = bits;
+        fa.alpha[0] = 1.0;
+        fa.c = x4 + static_cast<std::size_t>(2 * bp) * m * n;
+        fa.ldc = m;
+        fa.batch = 2;   // entry = plane of A
+        fa.a_batch_bytes = w.a_plane, fa.b_batch_bytes = 0, fa.amax_batch = m, fa.bmax_batch = 0, fa.c_batch = m * n;
+        OZ_KERNEL_CHECK(ozk_gemm_i8_fused_ex(&fa, s));
+      }
+      OZ_KERNEL_CHECK(ozk_zgemm_combine(m, n, x4, sc.alpha, sc.beta, sc.alpha_dev, sc.beta_dev, c, ldc, s));
+      h->profiler.stop("int8tc_accumulate_fused", s);
+      continue;
     }
     ozk_fused_args_t fa{};
     fa.m = m, fa.n = n, fa.k = k, fa.pitch = w.pitch;
@@ -574,8 +622,12 @@ int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const opera
   bool used[handle::kProductStreams] = {};
   // one CTA pair per tile (OZIMMU_B200_STREAMED_ONE_TILE, default 1): the panels' launches interleave tile by tile and
   // whatever carries the next panel (a NCCL broadcast kernel, the panel's split) gets SMs whenever a tile ends
+  // A single panel (B arrives in one piece; only split(A) overlaps its transfer) is the ordinary persistent launch,
+  // paced by the lockstep.
   const unsigned panel_flags =
-      OZK_FUSED_NO_LOCKSTEP | (H::env_or("OZIMMU_B200_STREAMED_ONE_TILE", "1") != "0" ? OZK_FUSED_ONE_TILE_PER_PAIR : 0u);
+      num_panels == 1 ? 0u
+                      : OZK_FUSED_NO_LOCKSTEP |
+                            (H::env_or("OZIMMU_B200_STREAMED_ONE_TILE", "1") != "0" ? OZK_FUSED_ONE_TILE_PER_PAIR : 0u);
   for (std::size_t p = 0; p < num_panels; p++) {
     const std::size_t j0 = col_edges[p], nj = col_edges[p + 1] - j0;
     if (nj == 0) continue;

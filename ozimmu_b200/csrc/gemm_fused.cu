@@ -526,6 +526,45 @@ oz_scale_c_kernel(double *__restrict__ c, const size_t ldc, const uint32_t m, co
   }
 }
 
+// Complex GEMM, "plane products first" variant (ozk_zgemm_combine): the four real plane products x = Re/Im(A) * Re/Im(B)
+// were written to scratch as ordinary real products; this folds them into C exactly as the fused complex epilogue does
+// (same operations in the same order per element, reference src/gemm.cu:160-239,479-518).
+// x4: [4][n][m] doubles, plane e = (A plane) + 2 * (B plane): (re,re), (im,re), (re,im), (im,im).
+__global__ void __launch_bounds__(256)
+oz_zgemm_combine_kernel(const double *__restrict__ x4, const uint32_t m, const uint32_t n, double alpha, double alpha_im,
+                        double beta, double beta_im, const double *__restrict__ alpha_dev,
+                        const double *__restrict__ beta_dev, double2 *__restrict__ c, const size_t ldc) {
+  const uint32_t r = blockIdx.x * 256 + threadIdx.x, col = blockIdx.y;
+  if (r >= m || col >= n) return;
+  if (alpha_dev != nullptr) {
+    alpha = __ldg(alpha_dev), alpha_im = __ldg(alpha_dev + 1);
+    beta = __ldg(beta_dev), beta_im = __ldg(beta_dev + 1);
+  }
+  const size_t plane = static_cast<size_t>(m) * n, at = static_cast<size_t>(col) * m + r;
+  double2 *dst = c + static_cast<size_t>(col) * ldc + r;
+  double2 y = make_double2(0.0, 0.0);
+  if (beta != 0 || beta_im != 0) {
+    y = *dst;
+    const double yx = __fma_rn(y.x, beta, -__dmul_rn(y.y, beta_im));
+    y.y = __fma_rn(y.y, beta, __dmul_rn(y.x, beta_im));
+    y.x = yx;
+  }
+  // (im,im) -> -alpha, (re,re) -> +alpha, (im,re), (re,im) -> i*alpha
+  double x = __ldg(x4 + 3 * plane + at);
+  y.x = __fma_rn(x, -alpha, y.x);
+  y.y = __fma_rn(x, -alpha_im, y.y);
+  x = __ldg(x4 + at);
+  y.x = __fma_rn(x, alpha, y.x);
+  y.y = __fma_rn(x, alpha_im, y.y);
+  x = __ldg(x4 + plane + at);
+  y.x = __fma_rn(x, -alpha_im, y.x);
+  y.y = __fma_rn(x, alpha, y.y);
+  x = __ldg(x4 + 2 * plane + at);
+  y.x = __fma_rn(x, -alpha_im, y.x);
+  y.y = __fma_rn(x, alpha, y.y);
+  *dst = y;
+}
+
 // ---- host side --------------------------------------------------------------------------------
 // One-time, per-device kernel setup (dynamic SMEM opt-in, resident cluster count), safe for concurrent
 // callers and for one process driving several GPUs.
@@ -852,6 +891,24 @@ extern "C" int ozk_scale_c_ex(size_t m, size_t n, const double beta[2], const do
     oz::oz_scale_c_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<double *>(c) + j0 * ldc * es, ldc, static_cast<uint32_t>(m), nj, beta ? beta[0] : 0.0,
         (beta && complex_c) ? beta[1] : 0.0, beta_dev, complex_c != 0);
+    oz::count_launch(1);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ozk_zgemm_combine(size_t m, size_t n, const double *x4, const double alpha[2], const double beta[2],
+                                 const double *alpha_dev, const double *beta_dev, void *c, size_t ldc, void *stream) {
+  if (m == 0 || n == 0) return 0;
+  if (ldc < m || m >= (1ull << 31) || n >= 65536ull * 32768ull || c == nullptr || x4 == nullptr ||
+      (alpha_dev == nullptr) != (beta_dev == nullptr) || (alpha_dev == nullptr && (alpha == nullptr || beta == nullptr)))
+    return static_cast<int>(cudaErrorInvalidValue);
+  for (size_t j0 = 0; j0 < n; j0 += 65535) {
+    const unsigned nj = static_cast<unsigned>(n - j0 < 65535 ? n - j0 : 65535);
+    dim3 grid(static_cast<unsigned>((m + 255) / 256), nj);
+    // the column offset applies to every scratch plane alike: pass the full n so that the plane stride stays m * n
+    oz::oz_zgemm_combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x4 + j0 * m, static_cast<uint32_t>(m), static_cast<uint32_t>(n), alpha ? alpha[0] : 0.0, alpha ? alpha[1] : 0.0,
+        beta ? beta[0] : 0.0, beta ? beta[1] : 0.0, alpha_dev, beta_dev, static_cast<double2 *>(c) + j0 * ldc, ldc);
     oz::count_launch(1);
   }
   return static_cast<int>(cudaGetLastError());

@@ -22,6 +22,7 @@
 // src/split.cu:193-242,277-282).
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "host.hpp"
@@ -114,6 +115,38 @@ void copy_matrix(double *dst, const double *src, std::size_t ld, std::size_t row
   }
 }
 
+// OZIMMU_B200_E2E_TRACE=1: time stamps (CUDA events with timing) of every stage of one host-operand call -- block
+// landed, block split, rectangle multiplied, rectangle copied out -- printed as one line each, relative to the first
+// copy.  A development aid: where does the time between the last byte in and the last byte out go?
+struct E2eTrace {
+  bool on = false;
+  cudaEvent_t t0 = nullptr;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  void begin(cudaStream_t s) {
+    if (!on) return;
+    OZ_CUDA_CHECK(cudaEventCreate(&t0));
+    OZ_CUDA_CHECK(cudaEventRecord(t0, s));
+  }
+  void mark(const std::string &what, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e = nullptr;
+    OZ_CUDA_CHECK(cudaEventCreate(&e));
+    OZ_CUDA_CHECK(cudaEventRecord(e, s));
+    marks.emplace_back(what, e);
+  }
+  void print() {
+    if (!on) return;
+    for (auto &m : marks) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t0, m.second);
+      std::printf("[ozIMMU e2e trace] %8.3f ms  %s\n", ms, m.first.c_str());
+      cudaEventDestroy(m.second);
+    }
+    cudaEventDestroy(t0);
+    std::fflush(stdout);
+  }
+};
+
 // comm == nullptr (or a communicator of one rank): the single-GPU entry.  Otherwise this rank's row block of the
 // sharded product (m = its rows of op(A) and C): B lives in the HOST memory of rank `src` only (b is ignored elsewhere);
 // the owner uploads it block by block between its own blocks of A and broadcasts every block over NVLink as soon as it
@@ -199,6 +232,10 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   auto *a_sl = reinterpret_cast<std::int8_t *>(ws + w.off_a_slices);
   auto *b_sl = reinterpret_cast<std::int8_t *>(ws + w.off_b_slices);
 
+  E2eTrace trace;
+  trace.on = env_size("OZIMMU_B200_E2E_TRACE", 0) != 0;
+  trace.begin(sin);
+
   auto copy_a_block = [&](std::size_t i) {
     const std::size_t i0 = ae[i], mi = ae[i + 1] - i0;
     if (op_a == op_n) {  // m x k column-major: rows i0..i0+mi of every column
@@ -207,6 +244,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
       copy_matrix(da + i0 * lda, a + i0 * lda, lda, k, mi, cudaMemcpyHostToDevice, sin);
     }
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[0][i], sin));
+    trace.mark("A" + std::to_string(i) + " landed", sin);
   };
   // the element range of db that holds block j of op(B) when blocks are broadcast (contiguous by construction)
   auto b_block_range = [&](std::size_t j, std::size_t &first, std::size_t &count) {
@@ -230,6 +268,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     }
     if (beta != 0 && m != 0) copy_matrix(dc + j0 * ldc, c + j0 * ldc, ldc, m, nj, cudaMemcpyHostToDevice, sin);
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_in[1][j], sin));
+    trace.mark("B" + std::to_string(j) + " landed (H2D)", sin);
     if (sharded) {
       // the owner forwards the block as soon as it is on its GPU; everybody else's copy arrives here.  All ranks
       // issue the broadcasts in block order on their communicator stream.
@@ -247,6 +286,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     OZ_KERNEL_CHECK(ozk_split_int8_block(a_sl, w.pitch, m, i0, amax + i0, scr_a + i0, mi, k, src, lda, op_a == op_n, s,
                                          bits, 1, sc));
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[0][i], sc));
+    trace.mark("A" + std::to_string(i) + " split", sc);
   };
   auto split_b_block = [&](std::size_t j) {
     const std::size_t j0 = be[j], nj = be[j + 1] - j0;
@@ -255,6 +295,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     OZ_KERNEL_CHECK(ozk_split_int8_block(b_sl, w.pitch, n, j0, bmax + j0, scr_b + j0, nj, k, src, ldb, op_b != op_n, s,
                                          bits, 1, sc));
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_block_split[1][j], sc));
+    trace.mark("B" + std::to_string(j) + " split", sc);
   };
   // C[i0 : i0+mi, j0 : j0+nj] once `ready` (the split that completed its operands; the compute stream runs the
   // splits in arrival order, so it implies every earlier one) has fired.  OZIMMU_B200_E2E_ONE_TILE (default 1): the
@@ -284,8 +325,11 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     OZ_KERNEL_CHECK(ozk_gemm_i8_fused_block(mi, nj, k, a_sl, m, i0, b_sl, n, j0, w.pitch, amax + i0, bmax + j0, s, bits,
                                             alpha, beta, dblk, ldc, fused_flags, sp));
     OZ_CUDA_CHECK(cudaEventRecord(h->ev_rect_out[rects], sp));
+    const std::string name = "C[" + std::to_string(i0) + "+" + std::to_string(mi) + ", " + std::to_string(j0) + "+" + std::to_string(nj) + "]";
+    trace.mark(name + " multiplied", sp);
     OZ_CUDA_CHECK(cudaStreamWaitEvent(sout, h->ev_rect_out[rects], 0));
     copy_matrix(c + j0 * ldc + i0, dblk, ldc, mi, nj, cudaMemcpyDeviceToHost, sout);
+    trace.mark(name + " copied out", sout);
     rects++;
   };
   auto product_rect = [&](std::size_t i0, std::size_t mi, std::size_t j0, std::size_t nj, cudaEvent_t ready) {
@@ -346,6 +390,7 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   h->last_stream = sc;
   OZ_CUDA_CHECK(cudaStreamSynchronize(sout));
   OZ_CUDA_CHECK(cudaStreamSynchronize(sc));
+  trace.print();
   return 0;
 }
 

@@ -166,9 +166,19 @@ int gemm_sharded_impl(handle_t h, H::Comm *c, operation_t op_a, operation_t op_b
   const bool pipelined = max_panels > 1 && op_b == op_n && H::is_int8_mode(mode) && k > 0 && n >= 2 * min_panel &&
                          !h->profiler.enabled;
   if (!pipelined) {
-    // one broadcast, then the plain call (op_t B: a column panel of op(B) is not contiguous; auto mode looks at all of B)
+    // one broadcast (op_t B: a column panel of op(B) is not contiguous; auto mode looks at all of B; max_panels <= 1)
     H::comm_broadcast_f64(c, b, total, src, c->stream);
     OZ_CUDA_CHECK(cudaEventRecord(c->ev_end, c->stream));
+    int rc = 0;
+    if (m_local != 0 && H::is_int8_mode(mode) && k > 0 && n > 0 && !h->profiler.enabled) {
+      // B as ONE panel guarded by the broadcast's event: split(A) runs while B is on the wire, then the ordinary
+      // single product launch
+      const std::size_t edges[2] = {0, n};
+      const cudaEvent_t ready = (c->rank == src) ? c->ev_begin : c->ev_end;
+      rc = gemm_streamed_b(h, op_a, op_b, m_local, n, k, alpha, a, lda, b, ldb, beta, cc, ldc, mode, 1, edges, &ready);
+      OZ_CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_end, 0));
+      return rc;
+    }
     OZ_CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_end, 0));
     if (m_local == 0) return 0;
     return gemm(h, op_a, op_b, m_local, n, k, alpha, a, lda, b, ldb, beta, cc, ldc, mode, real);

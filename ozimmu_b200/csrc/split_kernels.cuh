@@ -18,6 +18,7 @@
 // Output layout: the blocked, pre-swizzled [slice][row tile][k block][128][128] layout of oz_common.cuh
 // (slice_chunk_offset); pitch = k rounded up to 128, rows padded to 256, padding zero.
 #pragma once
+#include <mutex>
 #include "oz_common.cuh"
 #include "ozimmu_b200.h"
 
@@ -299,30 +300,87 @@ rowmax_cols_kernel(uint32_t *__restrict__ emax_, const size_t rows, const uint32
 // stores over 32 rows per instruction.
 constexpr int kColsRows = 32, kColsK = 128;
 
+// ONE launch does both passes, band by band: the matrix is cut into bands of kBandRows rows (32 MB of FP64 at
+// k = 8192), and the CTAs of a band are, in blockIdx order, first its row-max CTAs (256 rows x 64 columns each, as
+// rowmax_cols_kernel) and then its cut CTAs.  A cut CTA waits until the band's row-max CTAs have all arrived (a counter
+// in global memory; they have lower block indices, so they were dispatched earlier and the wait cannot deadlock -- the
+// same dependency direction as a decoupled look-back scan), then re-reads its 32 x 128 elements -- from L2, where the
+// band still sits: the matrix crosses HBM once instead of twice (two separate launches over 512 MiB: the second pass
+// finds nothing of the first in the 126 MB L2).
+constexpr uint32_t kBandRows = 512;
+
+struct ColsBands {
+  uint32_t bands, p1_per_band, p2_per_band;   // CTAs per band: row-max pass, cut pass
+  uint32_t rchunks, rtiles;                   // 256-row chunks (pass 1) and 32-row tiles (pass 2) per full band
+  uint32_t *band_done;                        // [batch][bands], zeroed before the launch
+};
+
 template <int S>
 __global__ void __launch_bounds__(256)
 split_cols_kernel(int8_t *__restrict__ out_, const size_t pitch, double *__restrict__ max_exp_,
-                  const uint32_t *__restrict__ emax_, const size_t rows, const uint32_t len,
+                  uint32_t *__restrict__ emax_, const size_t rows, const uint32_t len,
                   const double *__restrict__ in_, const size_t ld, const unsigned L, const uint32_t es,
-                  const size_t slice_stride, const SplitBatch bt) {
+                  const size_t slice_stride, const SplitBatch bt, const ColsBands cb) {
   int8_t *__restrict__ out = out_ + blockIdx.z * bt.out_stride;
   double *__restrict__ max_exp = max_exp_ + blockIdx.z * bt.max_stride;
-  const uint32_t *__restrict__ emax = emax_ + blockIdx.z * bt.scr_stride;
+  uint32_t *__restrict__ emax = emax_ + blockIdx.z * bt.scr_stride;
   const double *__restrict__ in = in_ + blockIdx.z * bt.in_stride;
+  uint32_t *done = cb.band_done + blockIdx.z * cb.bands;
   extern __shared__ uint4 s_out[];  // [S][32 rows][8 chunks of 16 B], chunk index ^ (row & 7)
+  // block order: max(0), max(1), cut(0), max(2), cut(1), ..., max(B-1), cut(B-2), cut(B-1) -- the row-max pass of band
+  // b + 1 is issued before the cut pass of band b, so it runs while that one still occupies the SMs (a cut CTA only ever
+  // waits for CTAs with lower block indices)
+  const uint32_t per_band = cb.p1_per_band + cb.p2_per_band;
+  uint32_t band, j;   // j < p1: row-max CTA j of the band, else cut CTA j - p1
+  if (blockIdx.x < cb.p1_per_band) {
+    band = 0, j = blockIdx.x;
+  } else {
+    const uint32_t idx = blockIdx.x - cb.p1_per_band, g = idx / per_band, r = idx - g * per_band;
+    if (g + 1 < cb.bands) {
+      if (r < cb.p1_per_band) band = g + 1, j = r;
+      else band = g, j = r;
+    } else {
+      band = g, j = cb.p1_per_band + r;
+    }
+  }
+  const size_t row_lo = static_cast<size_t>(band) * kBandRows;
+  if (j < cb.p1_per_band) {
+    // ---- pass 1: exponent maximum of 256 rows over 64 columns (thread <-> row: coalesced column segments) ----
+    const size_t r = row_lo + static_cast<size_t>(j % cb.rchunks) * 256 + threadIdx.x;
+    const uint32_t c0 = (j / cb.rchunks) * kColChunk;
+    if (r < rows && r < row_lo + kBandRows && c0 < len) {
+      const uint32_t c1 = min(len, c0 + kColChunk);
+      uint32_t e = 0;
+#pragma unroll 8
+      for (uint32_t c = c0; c < c1; c++) e = max(e, exp_field(__ldg(in + (static_cast<size_t>(c) * ld + r) * es)));
+      atomicMax(emax + r, e);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(done + band, 1u);
+    return;
+  }
+  // ---- pass 2: cut 32 rows x 128 K-positions once the band's row maxima are final ----
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<volatile uint32_t *>(done + band) < cb.p1_per_band) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+  const uint32_t jj = j - cb.p1_per_band;
   const uint32_t rl = threadIdx.x & 31, cg = threadIdx.x >> 5;
-  const size_t r = static_cast<size_t>(blockIdx.x) * kColsRows + rl;
-  const uint32_t kbase = blockIdx.y * kColsK;
+  const size_t tile_row = row_lo + static_cast<size_t>(jj % cb.rtiles) * kColsRows;
+  const size_t r = tile_row + rl;
+  const uint32_t kbase = (jj / cb.rtiles) * kColsK;
   const uint32_t cbase = kbase + cg * 16;
   if (r < rows && cbase < pitch) {
-    const double mx = max_exp_from_field(emax[r]);
+    const double mx = max_exp_from_field(__ldcg(emax + r));
     const uint64_t mx_bits = static_cast<uint64_t>(__double_as_longlong(mx));
-    if (blockIdx.y == 0 && cg == 0) max_exp[r] = mx;
+    if (kbase == 0 && cg == 0) max_exp[r] = mx;
     double v[16];
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const uint32_t c = cbase + j;
-      v[j] = (c < len) ? __ldg(in + (static_cast<size_t>(c) * ld + r) * es) : 0.0;
+    for (int jx = 0; jx < 16; jx++) {
+      const uint32_t c = cbase + jx;
+      v[jx] = (c < len) ? __ldg(in + (static_cast<size_t>(c) * ld + r) * es) : 0.0;
     }
     uint32_t w[S][4];
     cut16_any<S>(v, mx_bits, L, w);
@@ -333,7 +391,7 @@ split_cols_kernel(int8_t *__restrict__ out_, const size_t pitch, double *__restr
   __syncthreads();
   // write-out: 8 consecutive threads cover one row's 128-byte line of one slice
   const uint32_t orow = threadIdx.x >> 3, chunk = threadIdx.x & 7;
-  const size_t gr = static_cast<size_t>(blockIdx.x) * kColsRows + orow;
+  const size_t gr = tile_row + orow;
   const uint32_t gk = kbase + chunk * 16;
   if (gr < rows && gk < pitch) {
     int8_t *__restrict__ dst = out + slice_chunk_offset(gr, gk >> 4, pitch / kTileK);
@@ -421,6 +479,33 @@ loss_cols_kernel(unsigned long long *__restrict__ counters_, const uint32_t *__r
   loss_block_reduce(cnt, counters);
 }
 
+// Band counters of the strided split: a ring of small zeroed device buffers per device (a launch zeroes its buffer in
+// stream order; kBandRing launches may be in flight per device before a buffer is reused, and reuse is ordered by the
+// memset only on the same stream -- concurrent splits on more streams than that would share counters, so the ring is
+// sized well above the handful of streams the host pipelines use).
+inline uint32_t *band_counters(size_t count, cudaStream_t stream) {
+  constexpr int kMaxDev = 64, kBandRing = 16;
+  constexpr size_t kBandCap = 1 << 16;   // counters per buffer (bands x batch entries of one launch)
+  static std::mutex mu;
+  static uint32_t *pool[kMaxDev] = {};   // kBandRing buffers, ONE allocation per device on first use (a later call
+  static int next[kMaxDev] = {};         // may be inside a CUDA graph capture, where cudaMalloc is not allowed)
+  int dev = 0;
+  if (count > kBandCap || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  uint32_t *buf = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (pool[dev] == nullptr && cudaMalloc(&pool[dev], kBandRing * kBandCap * sizeof(uint32_t)) != cudaSuccess) {
+      pool[dev] = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+    buf = pool[dev] + static_cast<size_t>(next[dev]) * kBandCap;
+    next[dev] = (next[dev] + 1) % kBandRing;
+  }
+  if (cudaMemsetAsync(buf, 0, count * sizeof(uint32_t), stream) != cudaSuccess) return nullptr;
+  return buf;
+}
+
 template <int S>
 int launch_split(int8_t *out, size_t pitch, size_t plane_rows, double *max_exp, uint32_t *scratch, size_t rows,
                  size_t len, const double *in, size_t ld, int col_major, unsigned L, uint32_t es,
@@ -434,17 +519,24 @@ int launch_split(int8_t *out, size_t pitch, size_t plane_rows, double *max_exp, 
       OZ_CUDA_TRY(cudaMemsetAsync(scratch, 0, rows * sizeof(uint32_t), stream));
     else
       OZ_CUDA_TRY(cudaMemset2DAsync(scratch, bt.scr_stride * sizeof(uint32_t), 0, rows * sizeof(uint32_t), bt.count, stream));
-    dim3 g1(static_cast<unsigned>((rows + 255) / 256), ceil_div_u32(static_cast<uint32_t>(len), kColChunk), bt.count);
-    rowmax_cols_kernel<<<g1, 256, 0, stream>>>(scratch, rows, static_cast<uint32_t>(len), in, ld, es, bt);
-    dim3 g2(static_cast<unsigned>((rows + kColsRows - 1) / kColsRows), static_cast<unsigned>((pitch + kColsK - 1) / kColsK),
-            bt.count);
+    // [rows] exponent maxima, followed by the band counters (the caller's scratch holds rows entries; the counters
+    // live in a small per-device pool)
+    ColsBands cb{};
+    cb.bands = static_cast<uint32_t>((rows + kBandRows - 1) / kBandRows);
+    cb.rchunks = kBandRows / 256;
+    cb.rtiles = kBandRows / kColsRows;
+    cb.p1_per_band = cb.rchunks * ceil_div_u32(static_cast<uint32_t>(len), kColChunk);
+    cb.p2_per_band = cb.rtiles * static_cast<uint32_t>((pitch + kColsK - 1) / kColsK);
+    cb.band_done = band_counters(static_cast<size_t>(cb.bands) * bt.count, stream);
+    if (cb.band_done == nullptr) return static_cast<int>(cudaErrorMemoryAllocation);
+    dim3 g2(cb.bands * (cb.p1_per_band + cb.p2_per_band), 1, bt.count);
     const size_t smem_cols = static_cast<size_t>(S) * kColsRows * kColsK;
     if (smem_cols > 48 * 1024)  // per device and cheap: no caching
       OZ_CUDA_TRY(cudaFuncSetAttribute(split_cols_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_cols)));
     split_cols_kernel<S><<<g2, 256, smem_cols, stream>>>(out, pitch, max_exp, scratch, rows,
-                                                         static_cast<uint32_t>(len), in, ld, L, es, slice_stride, bt);
-    count_launch(2);
+                                                         static_cast<uint32_t>(len), in, ld, L, es, slice_stride, bt, cb);
+    count_launch(1);
   } else if (es == 1 && len <= 16384) {
     // register-resident rows: (threads, 16-element groups per thread) sized to the row
     const dim3 nrows(static_cast<unsigned>(rows), bt.count);
