@@ -346,14 +346,22 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   };
 
   // arrival order: B0, A0, B1, A1, ... (the longer operand's remaining blocks follow at the end); queue every
-  // copy first so the H2D engine never waits for the host.  A rank that receives B by broadcast has its PCIe link to
-  // itself for A, while B arrives at the pace of the owner's alternating uploads: two blocks of A per block of B.
+  // copy first so the H2D engine never waits for the host.
+  // Sharded: the owner uploads ALL of B first and forwards every block as it lands, then its own A.  While B is in
+  // flight no rank has much to multiply yet, so NCCL's broadcast kernels find free SMs at once on every GPU; with B
+  // interleaved behind A on the owner, each of its broadcasts had to wait for SMs on eight busy GPUs and the step grew
+  // with the rank count (8 GPUs: 72 ms, profiles/r2_bench_8gpu_call8.json).  The other ranks receive B at the rate
+  // their own blocks of A arrive over their own PCIe links: blocks alternate as on a single GPU.
   struct Arrival { int which; std::size_t idx; };
   std::vector<Arrival> order;
-  const std::size_t a_per_b = owner ? 1 : 2;
-  for (std::size_t ia = 0, ib = 0; ia < nab || ib < nbb;) {
-    if (ib < nbb && (ib * a_per_b <= ia || ia >= nab)) order.push_back({1, ib++});
-    else order.push_back({0, ia++});
+  if (sharded && owner) {
+    for (std::size_t ib = 0; ib < nbb; ib++) order.push_back({1, ib});
+    for (std::size_t ia = 0; ia < nab; ia++) order.push_back({0, ia});
+  } else {
+    for (std::size_t ia = 0, ib = 0; ia < nab || ib < nbb;) {
+      if (ib < nbb && (ib <= ia || ia >= nab)) order.push_back({1, ib++});
+      else order.push_back({0, ia++});
+    }
   }
 
   if (sharded) {

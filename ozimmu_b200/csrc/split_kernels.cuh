@@ -300,14 +300,14 @@ rowmax_cols_kernel(uint32_t *__restrict__ emax_, const size_t rows, const uint32
 // stores over 32 rows per instruction.
 constexpr int kColsRows = 32, kColsK = 128;
 
-// ONE launch does both passes, band by band: the matrix is cut into bands of kBandRows rows (32 MB of FP64 at
+// ONE launch does both passes, band by band: the matrix is cut into bands of kBandRows rows (16 MB of FP64 at
 // k = 8192), and the CTAs of a band are, in blockIdx order, first its row-max CTAs (256 rows x 64 columns each, as
 // rowmax_cols_kernel) and then its cut CTAs.  A cut CTA waits until the band's row-max CTAs have all arrived (a counter
 // in global memory; they have lower block indices, so they were dispatched earlier and the wait cannot deadlock -- the
 // same dependency direction as a decoupled look-back scan), then re-reads its 32 x 128 elements -- from L2, where the
 // band still sits: the matrix crosses HBM once instead of twice (two separate launches over 512 MiB: the second pass
 // finds nothing of the first in the 126 MB L2).
-constexpr uint32_t kBandRows = 512;
+constexpr uint32_t kBandRows = 256;
 
 struct ColsBands {
   uint32_t bands, p1_per_band, p2_per_band;   // CTAs per band: row-max pass, cut pass
@@ -380,7 +380,7 @@ split_cols_kernel(int8_t *__restrict__ out_, const size_t pitch, double *__restr
 #pragma unroll
     for (int jx = 0; jx < 16; jx++) {
       const uint32_t c = cbase + jx;
-      v[jx] = (c < len) ? __ldg(in + (static_cast<size_t>(c) * ld + r) * es) : 0.0;
+      v[jx] = (c < len) ? __ldcs(in + (static_cast<size_t>(c) * ld + r) * es) : 0.0;   // last use: evict first
     }
     uint32_t w[S][4];
     cut16_any<S>(v, mx_bits, L, w);
@@ -397,7 +397,7 @@ split_cols_kernel(int8_t *__restrict__ out_, const size_t pitch, double *__restr
     int8_t *__restrict__ dst = out + slice_chunk_offset(gr, gk >> 4, pitch / kTileK);
 #pragma unroll
     for (int t = 0; t < S; t++)
-      *reinterpret_cast<uint4 *>(dst + t * slice_stride) = s_out[(t * kColsRows + orow) * 8 + (chunk ^ (orow & 7))];
+      __stcs(reinterpret_cast<uint4 *>(dst + t * slice_stride), s_out[(t * kColsRows + orow) * 8 + (chunk ^ (orow & 7))]);
   }
 }
 

@@ -1,5 +1,5 @@
 """Development probe (not the bench): the sharded step on N GPUs for several panel counts, device and host operands.
-torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/sharded_probe.py [n] [rows_per_rank]"""
+torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/sharded_probe.py [n] [rows_per_rank] [panels=1,2,4] [nohost]"""
 import os
 import sys
 from pathlib import Path
@@ -16,6 +16,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else n
+extra = sys.argv[3:]
+panel_list = [int(x) for x in next((e.split("=")[1] for e in extra if e.startswith("panels=")), "1,2,4,8,16").split(",")]
 g = torch.Generator(device="cuda").manual_seed(rank)
 a = torch.rand(rows * n, dtype=torch.float64, device="cuda", generator=g)
 b = torch.rand(n * n, dtype=torch.float64, device="cuda", generator=g)
@@ -49,13 +51,16 @@ def report(name, per_rank):
 
 report("product alone (no broadcast)", timed(lambda: oz.gemm(h, 0, 0, rows, n, n, 1.0, a, rows, b, n, 0.0, c, rows, mode)))
 for rep in range(2):
-    for panels in (1, 2, 4, 8, 16):
-        for one_tile in ("1", "0"):
+    for panels in panel_list:
+        for one_tile in ("1", "0") if panels > 1 else ("1",):
             os.environ["OZIMMU_B200_STREAMED_ONE_TILE"] = one_tile
             report(f"sharded_gemm panels={panels} one_tile={one_tile}",
                    timed(lambda: oz.sharded_gemm(h, comm, 0, 0, rows, n, n, 1.0, a, rows, b, n, 0.0, c, rows, mode, src=0,
                                                  max_panels=panels)))
 os.environ["OZIMMU_B200_STREAMED_ONE_TILE"] = "1"
+if "nohost" in extra:
+    oz.destroy(h); comm.destroy(); dist.destroy_process_group()
+    sys.exit(0)
 ha = a.cpu().pin_memory()
 hb = b.cpu().pin_memory() if rank == 0 else None
 hc = torch.zeros(rows * n, dtype=torch.float64).pin_memory()

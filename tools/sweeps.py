@@ -69,9 +69,12 @@ def split_sweep(n):
 
 
 def auto_sweep(n):
+    from gpu_util import Reference
+    ref_lib = Reference() if oracle_lib.reference() is not None else None
     h = oz.create()
     flop = 2.0 * n ** 3
-    print("phi,threshold,selected_mode,avg_loss_at_selected,max_rel_err_vs_dgemm,rel_residual,tflops,counters_3..18")
+    print("phi,threshold,selected_mode,avg_loss_at_selected,max_rel_err_vs_dgemm,rel_residual,tflops,"
+          "ref_selected_mode,counters_3..10_equal_reference,selection_equal_reference,counters_3..18")
     for phi in (0.0, 0.5, 1.0, 2.0, 4.0, 8.0):
         g = torch.Generator(device="cuda").manual_seed(1)
         a, b = gen(f"exp_rand-{phi}", n * n, g), gen(f"exp_rand-{phi}", n * n, g)
@@ -85,8 +88,19 @@ def auto_sweep(n):
             mx, rr = errors(c, dg)
             name = oz.get_compute_mode_name_str(mode)
             avg = cnt[int(mode) - 2] / (2.0 * n * n) if name != "dgemm" else float("nan")
-            print(f"{phi},{thr},{name},{avg:.4f},{mx:.3e},{rr:.3e},{flop / ms / 1e9:.2f},{' '.join(str(v) for v in cnt)}", flush=True)
+            ref_name, cnt_same, sel_same = "", "", ""
+            if ref_lib is not None:
+                # the reference keeps 8 counters (fp64_int8_3..10): beyond them its selection is undefined
+                ref_mode, ref_cnt = ref_lib.auto_mode_select(0, 0, n, n, n, a, n, b, n, thr)
+                in_range = int(oz.compute_mode_t.fp64_int8_3) <= ref_mode <= int(oz.compute_mode_t.fp64_int8_10)
+                ref_name = oz.get_compute_mode_name_str(oz.compute_mode_t(ref_mode)) if 0 <= ref_mode <= 18 else str(ref_mode)
+                cnt_same = cnt[:8] == ref_cnt
+                sel_same = (int(mode) == ref_mode) if in_range else "n/a (reference has no counter beyond fp64_int8_10)"
+            print(f"{phi},{thr},{name},{avg:.4f},{mx:.3e},{rr:.3e},{flop / ms / 1e9:.2f},{ref_name},{cnt_same},{sel_same},"
+                  f"{' '.join(str(v) for v in cnt)}", flush=True)
     oz.destroy(h)
+    if ref_lib is not None:
+        ref_lib.close()
 
 
 if __name__ == "__main__":
