@@ -196,9 +196,12 @@ int gemm_sharded_impl(handle_t h, H::Comm *c, operation_t op_a, operation_t op_b
   }
   OZ_CUDA_CHECK(cudaEventRecord(c->ev_end, c->stream));
   int rc = 0;
+  // what a landed panel triggers: its split only, with ONE product launch after the last panel (default: the broadcast
+  // hides split(B) and nothing is paid for a cut product), or its own product launch (OZIMMU_B200_SHARDED_PANEL_PRODUCTS=1)
+  const bool one_product = H::env_or("OZIMMU_B200_SHARDED_PANEL_PRODUCTS", "0") != "1";
   if (m_local != 0)
-    rc = gemm_streamed_b(h, op_a, op_b, m_local, n, k, alpha, a, lda, b, ldb, beta, cc, ldc, mode, np, edges.data(),
-                         ready.data());
+    rc = H::gemm_streamed_b_impl(h, op_a, op_b, m_local, n, k, alpha, a, lda, b, ldb, beta, cc, ldc, mode, np, edges.data(),
+                                 ready.data(), one_product);
   // B must stay untouched until the owner's sends are done / is complete on the receivers when the call's work is
   OZ_CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_end, 0));
   return rc;
