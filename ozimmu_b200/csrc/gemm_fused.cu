@@ -579,6 +579,17 @@ struct PerDeviceOnce {
 int g_tile_override = 0;
 
 // ---- tuning knob (read once; OZIMMU_B200_LOCKSTEP overrides) ----
+// rasterisation band height in tiles (OZIMMU_B200_GROUP_M, read once; default 8: a wave of 74 pairs covers 8 x 9.25
+// tiles, the squarest block and with it the smallest panel footprint per product pass)
+uint32_t raster_group_m() {
+  static const uint32_t g = [] {
+    uint32_t v = 8;
+    if (const char *e = std::getenv("OZIMMU_B200_GROUP_M")) v = static_cast<uint32_t>(std::atoi(e));
+    return v == 0 ? 8u : v;
+  }();
+  return g;
+}
+
 uint32_t lockstep_window() {
   static const uint32_t w = [] {
     uint32_t v = 2;
@@ -617,7 +628,7 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   FusedParams p = p0;
   p.tiles_m = ceil_div_u32(p.m, 2 * BM);
   p.tiles_n = ceil_div_u32(p.n, BN_);
-  p.group_m = 8;
+  p.group_m = raster_group_m();
   if (p.rt_a == 0) p.rt_a = static_cast<uint32_t>(slice_row_tiles(p.m));  // != 0: block of a larger plane
   if (p.rt_b == 0) p.rt_b = static_cast<uint32_t>(slice_row_tiles(p.n));
   if (p.b_rows == 0) p.b_rows = p.rt_b * static_cast<uint32_t>(kTileRows);

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--zgemm", action="store_true", help="also time a complex GEMM of the same size")
     ap.add_argument("--no-extras", action="store_true", help="skip the stage profile and the cuBLAS comparisons")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--graph", action="store_true",
+                    help="also time the call replayed from a CUDA graph (no host launch cost: what the GPU itself needs)")
     args = ap.parse_args()
     n, s = args.n, args.s
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -52,6 +54,20 @@ def main():
         ms = timed(lambda: oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(s)), args.iters)
         print(f"ozimmu_b200 n={n} s={s} cluster={cm}x{cn}: {ms:.3f} ms  {flop / ms / 1e9:.2f} TFLOP/s-equiv  "
               f"int8 {pairs * flop / ms / 1e12:.3f} Pop/s", flush=True)
+        if args.graph:
+            st = torch.cuda.Stream()
+            oz.set_cuda_stream(h, st)
+            with torch.cuda.stream(st):
+                oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(s))   # sizes the workspace
+                st.synchronize()
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=st):
+                    for _ in range(10):
+                        oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(s))
+                ms = timed(g_.replay, args.iters) / 10
+            oz.set_cuda_stream(h, None)
+            print(f"ozimmu_b200 n={n} s={s} cluster={cm}x{cn} (CUDA graph of 10 calls): {ms:.4f} ms per call  "
+                  f"{flop / ms / 1e9:.2f} TFLOP/s-equiv", flush=True)
     L.ozk_set_cluster_shape(0, 0)
     if args.zgemm:
         za = torch.randn(n * n, dtype=torch.complex128, device="cuda", generator=g)
