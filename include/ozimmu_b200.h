@@ -187,8 +187,9 @@ int ozk_scale_c_ex(size_t m, size_t n, const double beta[2], const double *beta_
 int ozk_zgemm_combine(size_t m, size_t n, const double *x4, const double alpha[2], const double beta[2],
                       const double *alpha_dev, const double *beta_dev, void *c, size_t ldc, void *stream);
 
-/* Test/tuning hook: force the tile width of the fused kernel: (0, w), w in {128, 192, 208, 224, 240, 256}; anything
- * else restores the per-problem choice (256 or 128).  OZIMMU_B200_TILE_N=w does the same from the environment. */
+/* Test/tuning hook: force the tile of the fused kernel: (0, w), w in {128, 192, 208, 224, 240, 256} = 256 rows x w
+ * columns per CTA pair; (64, 128) = 128 x 128 (64 rows per CTA, UMMA M = 128: the small-problem tile); anything else
+ * restores the per-problem choice.  OZIMMU_B200_TILE_N=w forces a width from the environment. */
 int ozk_set_cluster_shape(int cm, int cn);
 
 /* Debug/verification launcher: the raw int32 product of ONE slice pair (1-based ids), written

@@ -68,11 +68,26 @@ cublasHandle_t private_cublas(handle_t h) {
   return h->cublas_handle;
 }
 
-// Order this call after the previous user of the shared workspace if that one ran on another stream.
+// Order this call after the previous user of the shared workspace if that one ran on another stream.  Work recorded
+// into a CUDA graph is not "pending" in that sense: an event recorded during capture cannot be waited on outside the
+// graph (and vice versa), and whoever replays the graph orders the replays against other users of the handle, as with
+// any captured library call that owns scratch memory.
+bool is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return st != cudaStreamCaptureStatusNone;
+}
 void wait_previous(handle_t h, cudaStream_t s) {
-  if (h->has_pending && h->last_stream != s) OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_done, 0));
+  if (h->has_pending && h->last_stream != s && !is_capturing(s)) OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_done, 0));
 }
 void mark_done(handle_t h, cudaStream_t s) {
+  if (is_capturing(s)) {
+    h->has_pending = false;
+    return;
+  }
   OZ_CUDA_CHECK(cudaEventRecord(h->ev_done, s));
   h->has_pending = true;
   h->last_stream = s;

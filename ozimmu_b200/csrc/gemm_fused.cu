@@ -43,7 +43,7 @@
 namespace oz {
 namespace {
 
-constexpr uint32_t BM = 128, BK = 128;  // rows per CTA, bytes (== int8 elements) of K per stage
+constexpr uint32_t BK = 128;  // bytes (== int8 elements) of K per stage; rows per CTA: template parameter BMC_ (128 or 64)
 constexpr uint32_t kThreads = 384;
 constexpr uint32_t kEpiWarps = 8;
 constexpr uint32_t kUmmaK = 32;
@@ -152,37 +152,52 @@ __device__ __forceinline__ void tile_coords(const FusedParams &p, uint32_t t, ui
   tn = r / rows;
 }
 
-template <uint32_t BN_>
+// BMC_ = rows of C per CTA: 128 (UMMA M = 256, the default) or 64 (UMMA M = 128: twice as many, half as tall tiles for
+// problems that would leave SMs idle, each CTA moving 8 KB of A per k-step instead of 16).  With M = 128 the pair MMA
+// folds a CTA's 64 x N block of D into all 128 TMEM lanes: lanes 0-63 hold columns [0, N/2), lanes 64-127 hold columns
+// [N/2, N) of the same 64 rows (measured: tools/ubench/umma_m128_probe.cu, profiles/r2_umma_m128_probe.txt), so a product
+// occupies N/2 TMEM columns.
+template <uint32_t BN_, uint32_t BMC_ = 128>
 struct PairCfg {
   static_assert(BN_ % 16 == 0 && BN_ >= 128 && BN_ <= 256, "UMMA M=256 needs N % 16 == 0, N <= 256");
+  static_assert(BMC_ == 128 || (BMC_ == 64 && BN_ == 128), "rows per CTA: 128, or 64 with a 128-wide tile");
+  static constexpr uint32_t kABytes = BMC_ * BK;
   static constexpr uint32_t kBRows = BN_ / 2;                        // this CTA's half of the B tile
   static constexpr uint32_t kBBytes = kBRows * BK;
-  static constexpr uint32_t kStageBytes = BM * BK + kBBytes;         // per CTA (a multiple of 1 KB: SW128 atoms)
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;         // per CTA (a multiple of 1 KB: SW128 atoms)
   static constexpr uint32_t kAccBufs = (BN_ == 128) ? 4 : 2;
-  static constexpr uint32_t kBufStride = BN_;                        // TMEM columns between buffers
-  static constexpr uint32_t kColsPerThread = BN_ / 2;                // epilogue: 2 column halves
+  static constexpr uint32_t kBufStride = (BMC_ == 128) ? BN_ : BN_ / 2;   // TMEM columns between buffers
+  // epilogue: 4 lane quarters x 2 warps; BMC_ = 128: the two warps of a quarter take the column halves of the tile;
+  // BMC_ = 64: quarters 2, 3 already are the upper column half, the two warps halve the N/2 TMEM columns
+  static constexpr uint32_t kColsPerThread = (BMC_ == 128) ? BN_ / 2 : BN_ / 4;
   // FP64 accumulators: up to 96 columns per thread in registers (192 registers); a wider tile keeps
   // the rest in shared memory ([column][row] doubles, conflict-free for lane <-> row)
   static constexpr uint32_t kRegCols = kColsPerThread < 96 ? kColsPerThread : 96;
   static constexpr uint32_t kSpillCols = kColsPerThread - kRegCols;
-  static constexpr uint32_t kSpillBytes = 2 * kSpillCols * BM * 8;
-  // the operand ring takes what is left of the 227 KB: BN=256 -> 5 stages, 240 -> 5, 224 -> 6, 208 -> 7, 192 / 128 -> 8
-  static constexpr uint32_t kSmemMax = 227 * 1024, kBarReserve = 320, kAlign = 1024;
+  static constexpr uint32_t kSpillBytes = 2 * kSpillCols * 128 * 8;
+  // the operand ring takes what is left of the 227 KB: BN=256 -> 5 stages, 240 -> 5, 224 -> 6, 208 -> 7, 192 / 128 -> 8;
+  // 16 KB stages (BMC_ = 64): 12
+  static constexpr uint32_t kSmemMax = 227 * 1024, kBarReserve = 512, kAlign = 1024;
   static constexpr uint32_t kStagesFit = (kSmemMax - kSpillBytes - kBarReserve - kAlign) / kStageBytes;
-  static constexpr uint32_t kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr uint32_t kStagesCap = (BMC_ == 128) ? 8 : 12;
+  static constexpr uint32_t kStages = kStagesFit > kStagesCap ? kStagesCap : kStagesFit;
   static constexpr uint32_t kBarBytes = 8 * (3 * kStages + 2 * kAccBufs) + 16;
   static_assert(kBarBytes <= kBarReserve, "barrier block");
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kSpillBytes + kBarBytes + kAlign;
+  // registers to spare for a second TMEM load buffer in the epilogue (acc 128 + 2 x 16 + 16 of 224)
+  static constexpr bool kLdPipe = (BN_ == 128);
   static constexpr uint32_t kRegsOther = (BN_ == 128) ? 56 : 40;
   static constexpr uint32_t kRegsEpi = (BN_ == 128) ? 224 : 232;
 };
 
-template <uint32_t BN_>
+template <uint32_t BN_, uint32_t BMC_>
 __global__ void __launch_bounds__(kThreads, 1)
 oz_gemm_pair_kernel(const FusedParams p) {
-  using Cfg = PairCfg<BN_>;
+  using Cfg = PairCfg<BN_, BMC_>;
+  constexpr uint32_t BM = BMC_;
   constexpr uint32_t kStagesP = Cfg::kStages, kBufs = Cfg::kAccBufs, kCols = Cfg::kColsPerThread;
   constexpr uint32_t kRegCols = Cfg::kRegCols, kSpillCols = Cfg::kSpillCols;
+  constexpr bool kLdPipe = Cfg::kLdPipe;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t spill_base = smem_base + kStagesP * Cfg::kStageBytes;
@@ -250,7 +265,9 @@ oz_gemm_pair_kernel(const FusedParams p) {
         // plane, which lie in one 128-row tile (BN = 256, 128) or straddle two (other widths): up to two linear pieces,
         // each a whole number of 8-row swizzle atoms; rows past the end of the plane are not fetched (their columns of
         // C do not exist)
-        const size_t a_tile = static_cast<size_t>(tm) * 2 + rank;
+        // BM = 128: this CTA's rows are 128-row slice tile 2 tm + rank; BM = 64: half `rank` of slice tile tm
+        const size_t a_tile = BM == 128 ? static_cast<size_t>(tm) * 2 + rank : static_cast<size_t>(tm);
+        const size_t a_sub = BM == 128 ? 0 : static_cast<size_t>(rank) * BM * BK;
         const uint32_t b_row0 = tn * BN_ + rank * Cfg::kBRows;
         const uint32_t b_avail = b_row0 < p.b_rows ? p.b_rows - b_row0 : 0u;
         const uint32_t b_rows1 = min(min(Cfg::kBRows, 128u - (b_row0 & 127u)), b_avail);
@@ -261,7 +278,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
         for (uint32_t grp = 0; grp < p.groups; grp++)
         for (PairIter it(p); it.valid(); it.next()) {
           const int8_t *a_src = a_base + group_plane_a(p, grp) * p.a_plane_bytes +
-                                ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes;
+                                ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes + a_sub;
           const int8_t *b_src = b_base + group_plane_b(p, grp) * p.b_plane_bytes +
                                 ((it.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
           const int8_t *b_src2 = b_src - b_sub + static_cast<size_t>(p.k_blocks) * kTileBytes;  // next row tile
@@ -355,18 +372,22 @@ oz_gemm_pair_kernel(const FusedParams p) {
     // ===================== epilogue (both CTAs): 8 warps, FP64 accumulators in registers (+ SMEM) ==========
     ptx::reg_alloc<Cfg::kRegsEpi>();
     const uint32_t q = warp & 3u;            // TMEM lane quarter this warp may touch
-    const uint32_t half = (warp - 4u) >> 2;  // which column half of the tile
+    const uint32_t half = (warp - 4u) >> 2;  // which half of the quarter's columns
+    // BM = 128: lane = row, TMEM column = tile column.  BM = 64 (UMMA M = 128): quarters 0, 1 hold rows 0-63 x columns
+    // [0, BN/2), quarters 2, 3 the same rows x columns [BN/2, BN), both in TMEM columns [0, BN/2) of the buffer
+    const uint32_t row_in_cta = BM == 128 ? q * 32u + lane : (q & 1u) * 32u + lane;
+    const uint32_t col_in_tile = BM == 128 ? half * kCols : (q >> 1) * (BN_ / 2) + half * kCols;
     const bool raw = p.single_a != 0;
     uint32_t pc = 0;
     for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
       uint32_t tm, tn, entry;
       tile_coords(p, t, tm, tn, entry);
-      const uint32_t row = tm * 2 * BM + rank * BM + q * 32u + lane;
-      const uint32_t col0 = tn * BN_ + half * kCols;
+      const uint32_t row = tm * 2 * BM + rank * BM + row_in_cta;
+      const uint32_t col0 = tn * BN_ + col_in_tile;
       double acc[kRegCols];
       // this thread's spill accumulators: columns [half*kSpillCols, +kSpillCols) of the [col][row] array
       double *spill = reinterpret_cast<double *>(smem_raw + (spill_base - ptx::smem_u32(smem_raw))) +
-                      static_cast<size_t>(half * kSpillCols) * BM + (q * 32u + lane);
+                      static_cast<size_t>(half * kSpillCols) * 128 + (q * 32u + lane);
       // one plane product per group: 1 for a real GEMM, the reference's 4 for a complex one (src/gemm.cu:479-518),
       // each folded into C by its own finalize before the next starts from a zero accumulator
       for (uint32_t grp = 0; grp < p.groups; grp++) {
@@ -379,15 +400,23 @@ oz_gemm_pair_kernel(const FusedParams p) {
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * Cfg::kBufStride + half * kCols;
           const double scale = it.scale(p.bits);
+          // 16 columns per TMEM load; a tile width that is not a multiple of 32 ends with one 8-column load.  A tile whose
+          // accumulators leave registers to spare (kLdPipe) keeps the NEXT load in flight while it folds the current one:
+          // a short product (k <= 2048) otherwise spends more time in four load round trips than in FP64 work.
+          constexpr uint32_t kChunks = (kCols + 15) / 16;
+          uint32_t vbuf[kLdPipe ? 2 : 1][16];
+          auto issue_ld = [&](const uint32_t c, uint32_t (&dst)[16]) {
+            if (c * 16 + 16 <= kCols) ptx::tmem_ld_x16(taddr + c * 16, dst);
+            else ptx::tmem_ld_x8(taddr + c * 16, dst);
+          };
+          if (kLdPipe) issue_ld(0, vbuf[0]);
 #pragma unroll
-          for (uint32_t c = 0; c < (kCols + 15) / 16; c++) {
-            // 16 columns per TMEM load; a tile width that is not a multiple of 32 ends with one 8-column load
-            const bool wide = c * 16 + 16 <= kCols;
-            const uint32_t nv = wide ? 16u : 8u;
-            uint32_t v[16];
-            if (wide) ptx::tmem_ld_x16(taddr + c * 16, v);
-            else ptx::tmem_ld_x8(taddr + c * 16, v);
+          for (uint32_t c = 0; c < kChunks; c++) {
+            const uint32_t nv = (c * 16 + 16 <= kCols) ? 16u : 8u;
+            uint32_t (&v)[16] = vbuf[kLdPipe ? (c & 1u) : 0u];
+            if (!kLdPipe) issue_ld(c, v);
             ptx::tmem_ld_wait();
+            if (kLdPipe && c + 1 < kChunks) issue_ld(c + 1, vbuf[(c + 1) & 1u]);
             if (!raw) {
               // (double)p without I2F.F64 (a quarter-rate conversion, 15/clk/SM measured, that would make the
               // epilogue as slow as the MMAs): 2^52 + 2^31 + p is the bit pattern {0x43300000, p ^ 0x80000000};
@@ -406,7 +435,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
                 } else {
 #pragma unroll
                   for (uint32_t j = 0; j < 8; j++) {
-                    double *sp = spill + static_cast<size_t>(c * 16 + g + j - kRegCols) * BM;
+                    double *sp = spill + static_cast<size_t>(c * 16 + g + j - kRegCols) * 128;
                     *sp = __fma_rn(d[j], scale, first ? 0.0 : *sp);
                   }
                 }
@@ -423,9 +452,12 @@ oz_gemm_pair_kernel(const FusedParams p) {
           first = false;
           ptx::tc_fence_before();
           __syncwarp();
+          // "buffer drained": this warp's TMEM loads have completed (tcgen05.wait::ld above) and there is no memory
+          // write to publish, so the hand-off to the leader's MMA warp needs no release fence -- a .release.cluster
+          // arrive costs an ERRBAR (~1 us per product and warp, profiles/r2_small_products_ncu.txt)
           if (lane == 0) {
             if (rank == 0) ptx::mbar_arrive(tempty_bar(buf));
-            else ptx::mbar_arrive_remote(ptx::mapa(tempty_bar(buf), 0));
+            else ptx::mbar_arrive_remote_relaxed(ptx::mapa(tempty_bar(buf), 0));
           }
         }
         if (!raw && row < p.m) {
@@ -452,7 +484,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
           for (uint32_t j = 0; j < kCols; j++) {
             const uint32_t col = col0 + j;
             if (col < p.n) {
-              const double a_j = (j < kRegCols) ? acc[j % kRegCols] : spill[static_cast<size_t>(j - kRegCols) * BM];
+              const double a_j = (j < kRegCols) ? acc[j % kRegCols] : spill[static_cast<size_t>(j - kRegCols) * 128];
               double x = __dmul_rn(a_j, 0x1p-44);
               x = __dmul_rn(x, am);
               x = __dmul_rn(x, __ldg(bmax + col));
@@ -575,8 +607,11 @@ struct PerDeviceOnce {
   int value[kMaxDevices] = {};
 };
 
-// 0 = default (tile width chosen per problem); 128 / 256 = forced (test/tuning hook, see ozk_set_cluster_shape)
+// 0 = default (tile width chosen per problem); 128 ... 256 = forced (test/tuning hook, see ozk_set_cluster_shape)
 int g_tile_override = 0;
+// 128 x 128 tiles (64 rows per CTA, UMMA M = 128): -1 = chosen per problem, 1 = forced, 0 = never (a forced tile width)
+int g_half_rows_override = -1;
+constexpr uint64_t kHalfRowsCost = 125;   // cost-model units of one 128 x 128 tile (a 256 x BN tile: 55 + BN)
 
 // ---- tuning knob (read once; OZIMMU_B200_LOCKSTEP overrides) ----
 // rasterisation band height in tiles (OZIMMU_B200_GROUP_M, read once; default 8: a wave of 74 pairs covers 8 x 9.25
@@ -622,9 +657,10 @@ uint32_t *next_sync_buffer() {
   return pool[dev][i];
 }
 
-template <uint32_t BN_>
+template <uint32_t BN_, uint32_t BMC_ = 128>
 int launch_pair(const FusedParams &p0, cudaStream_t stream) {
-  using Cfg = PairCfg<BN_>;
+  using Cfg = PairCfg<BN_, BMC_>;
+  constexpr uint32_t BM = BMC_;
   FusedParams p = p0;
   p.tiles_m = ceil_div_u32(p.m, 2 * BM);
   p.tiles_n = ceil_div_u32(p.n, BN_);
@@ -634,7 +670,7 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
   if (p.b_rows == 0) p.b_rows = p.rt_b * static_cast<uint32_t>(kTileRows);
   p.sync_window = lockstep_window();
 
-  auto kern = oz_gemm_pair_kernel<BN_>;
+  auto kern = oz_gemm_pair_kernel<BN_, BMC_>;
   int dev = 0, sms = 0;
   OZ_CUDA_TRY(cudaGetDevice(&dev));
   OZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -664,7 +700,7 @@ int launch_pair(const FusedParams &p0, cudaStream_t stream) {
       cudaGetLastError();
       once.done[dev] = true;
       if (std::getenv("OZIMMU_B200_DEBUG"))
-        std::fprintf(stderr, "[ozimmu_b200] pair kernel BN=%u: %d CTA pairs resident (%d SMs)\n", BN_, once.value[dev], sms);
+        std::fprintf(stderr, "[ozimmu_b200] pair kernel %ux%u: %d CTA pairs resident (%d SMs)\n", 2 * BM, BN_, once.value[dev], sms);
     }
     max_pairs = once.value[dev];
   }
@@ -725,27 +761,35 @@ int env_tile_width() {
 
 int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
   int bn = g_tile_override ? g_tile_override : env_tile_width();
-  if (bn == 0) {
+  bool half_rows = g_half_rows_override > 0;
+  if (bn == 0 && g_half_rows_override <= 0) {
     // A launch costs rounds x (time of one tile) with rounds = ceil(tiles / resident pairs).  Measured at 8192^3, s = 9
     // (profiles/r2_sweep_tile_width.txt): a round of 256 / 240 / 224 / 208 / 192-wide tiles takes 1.28 / 1.19 / 1.20 /
     // 1.08 / 1.02 ms, i.e. time per tile ~ 55 + BN -- between the tensor-pipe time (~ BN) and the operand-delivery time
     // (~ 128 + BN/2): BN = 256 moves the fewest bytes per MAC and wins whenever the tile count quantises alike
     // (8192^3: 14 rounds); a narrower tile wins when it needs fewer rounds x width (4096^3: 192 -> 5 x 247 < 4 x 311).
+    // 128 x 128 tiles (64 rows per CTA): 16 KB per k-step against 24 KB for 256 x 128 -- kHalfRowsCost per tile; they
+    // win when the problem has at most one round of them (1024^3: 64 tiles on 128 SMs instead of 32 on 64).
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint64_t pairs = static_cast<uint64_t>(sms > 1 ? sms / 2 : 1);
+    const uint64_t batch = p.batch ? p.batch : 1;
     uint64_t best_cost = ~0ull;
     for (int cand : kTileWidths) {
-      const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 2 * BM)) * ceil_div_u32(p.n, cand) *
-                             (p.batch ? p.batch : 1);
+      const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 256)) * ceil_div_u32(p.n, cand) * batch;
       const uint64_t cost = ((tiles + pairs - 1) / pairs) * (55 + cand);
       if (cost < best_cost) {   // ties go to the wider tile (kTileWidths is descending)
         best_cost = cost;
         bn = cand;
       }
     }
+    if (g_half_rows_override < 0) {
+      const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 128)) * ceil_div_u32(p.n, 128) * batch;
+      if (((tiles + pairs - 1) / pairs) * kHalfRowsCost < best_cost) half_rows = true;
+    }
   }
+  if (half_rows) return launch_pair<128, 64>(p, stream);
   switch (bn) {
     case 256: return launch_pair<256>(p, stream);
     case 240: return launch_pair<240>(p, stream);
@@ -779,10 +823,11 @@ FusedParams base_params(size_t m, size_t n, size_t pitch, const int8_t *a_slices
 }  // namespace
 }  // namespace oz
 
-// Test/tuning hook: force the tile width of the fused kernel: (0, 128) or (0, 256); anything else restores
-// the per-problem choice.
+// Test/tuning hook: force the tile of the fused kernel (see ozimmu_b200.h); anything else restores the per-problem choice.
 extern "C" int ozk_set_cluster_shape(int cm, int cn) {
   oz::g_tile_override = (cm == 0 && oz::tile_width_ok(cn)) ? cn : 0;
+  // (64, 128): force the 128 x 128 tile (64 rows per CTA); a forced width excludes it; anything else: per-problem choice
+  oz::g_half_rows_override = (cm == 64 && cn == 128) ? 1 : (oz::g_tile_override ? 0 : -1);
   return 0;
 }
 

@@ -222,7 +222,13 @@ def test_cuda_graph_capture(handle):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(c_graph.view(torch.int64), c_eager.view(torch.int64))
+    # an eager call on ANOTHER stream after the capture: the handle must not wait on an event that was only ever
+    # recorded inside the graph (cudaErrorInvalidValue before round 2)
     oz.set_cuda_stream(handle, None)
+    c_after = torch.zeros_like(c_eager)
+    assert oz.gemm(handle, 0, 0, m, n, k, 1.0, a, m, b, k, 0.0, c_after, m, oz.fp64_int8(9)) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(c_after.view(torch.int64), c_eager.view(torch.int64))
 
 
 @pytest.mark.parametrize("op_a,op_b,beta", [(0, 0, 0.0), (1, 0, -0.5), (0, 1, 2.0), (1, 1, 0.0)])

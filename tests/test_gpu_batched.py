@@ -56,7 +56,7 @@ def test_batched_equals_entry_by_entry(handle, op_a, op_b, m, n, k, batch, pad, 
     assert torch.equal(got.view(torch.int64), want.view(torch.int64))   # incl. the untouched gaps between entries
 
 
-@pytest.mark.parametrize("shape", [(0, 256), (0, 128)])
+@pytest.mark.parametrize("shape", [(0, 256), (0, 128), (64, 128)])
 def test_batched_tile_widths_and_shared_operand(handle, shape):
     """both tile widths of the grouped kernel; B shared by all entries (stride 0); more tiles than SM pairs"""
     m, n, k, batch = 512, 768, 384, 40

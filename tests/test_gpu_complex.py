@@ -34,6 +34,28 @@ def test_zgemm_matches_oracle(handle, op_a, op_b, m, n, k, num_split, kind, alph
         f"max ulp distance {ulp_distance(got.view(np.float64), want.view(np.float64))}"
 
 
+@pytest.mark.parametrize("planes_first", ["0", "1"])
+@pytest.mark.parametrize("shape", [(64, 128), (0, 128), (0, 256)])
+def test_zgemm_forced_tiles_match_oracle(handle, shape, planes_first, monkeypatch):
+    """the complex epilogue (four plane products per tile) under every accumulator layout of the fused kernel: 64 rows
+    per CTA (UMMA M = 128, columns folded over the TMEM lanes), 128 rows all in registers, 128 rows with spill columns"""
+    m, n, k, num_split = 300, 270, 200, 9
+    a = oracle_lib.gen_complex("exp_rand-1", m * k, 21)
+    b = oracle_lib.gen_complex("exp_rand-1", k * n, 22)
+    c = oracle_lib.gen_complex("normal01", m * n, 23)
+    alpha, beta = 0.5 - 1.25j, -0.75 + 0.0j
+    want = oracle_lib.oracle_gemm_complex(0, 1, m, n, k, alpha, a, m, b, n, beta, c, m, num_split)
+    da, db, dc = to_dev(a), to_dev(b), to_dev(c)
+    monkeypatch.setenv("OZIMMU_B200_ZGEMM_PLANES_FIRST", planes_first)   # fused four-group launch / planes + combine
+    oz.lib().ozk_set_cluster_shape(*shape)
+    try:
+        assert oz.gemm(handle, 0, 1, m, n, k, alpha, da, m, db, n, beta, dc, m, oz.fp64_int8(num_split), oz.complx) == 0
+        torch.cuda.synchronize()
+    finally:
+        oz.lib().ozk_set_cluster_shape(0, 0)
+    assert np.array_equal(dc.cpu().numpy().view(np.int64), want.view(np.int64))
+
+
 @pytest.mark.parametrize("op_a,op_b", [(0, 0), (1, 1)])
 @pytest.mark.parametrize("m,n,k,num_split", [(1024, 1024, 1024, 9), (1024, 1023, 1025, 12), (2048, 512, 768, 16)])
 def test_zgemm_bit_exact_vs_reference(handle, op_a, op_b, m, n, k, num_split):

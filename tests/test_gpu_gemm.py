@@ -194,7 +194,7 @@ def test_headline_8192_bit_exact_vs_reference(ref, handle):
         f"max ulp distance {ulp_distance(c_ref, c_new)}"
 
 
-@pytest.mark.parametrize("shape", [(0, 256), (0, 240), (0, 224), (0, 208), (0, 192), (0, 128)])
+@pytest.mark.parametrize("shape", [(0, 256), (0, 240), (0, 224), (0, 208), (0, 192), (0, 128), (64, 128)])
 def test_cluster_shapes_same_bits(handle, shape):
     m, n, k = 1000, 900, 2050
     a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 1))

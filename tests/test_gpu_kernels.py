@@ -46,8 +46,9 @@ def test_split_special_rows():
         assert np.array_equal(got[:, :, :length], want[:, :, :length])
 
 
-# (0, BN): force the CTA-pair kernel's tile width; (0, 0): per-problem choice
-@pytest.mark.parametrize("shape", [(0, 256), (0, 240), (0, 224), (0, 208), (0, 192), (0, 128), (0, 0)])
+# (0, BN): force the CTA-pair kernel's tile width; (64, 128): 128 x 128 tiles (64 rows per CTA, UMMA M = 128);
+# (0, 0): per-problem choice
+@pytest.mark.parametrize("shape", [(0, 256), (0, 240), (0, 224), (0, 208), (0, 192), (0, 128), (64, 128), (0, 0)])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 384, 512), (100, 60, 70), (513, 259, 1031), (1, 1, 1),
                                    (1025, 1023, 1024)])
 def test_int8_pair_product_exact(shape, m, n, k):

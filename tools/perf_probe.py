@@ -49,7 +49,8 @@ def main():
     pairs = s * (s + 1) // 2
     for shape in args.shapes.split(","):
         # pNNN = force the tile width of the CTA-pair kernel (128, 192, 208, 224, 240, 256); anything else: default
-        cm, cn = (0, int(shape[1:])) if shape.startswith("p") else (0, 0)
+        # h128 = 128 x 128 tiles (64 rows per CTA)
+        cm, cn = (0, int(shape[1:])) if shape.startswith("p") else ((64, 128) if shape == "h128" else (0, 0))
         L.ozk_set_cluster_shape(cm, cn)
         ms = timed(lambda: oz.gemm(h, 0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, oz.fp64_int8(s)), args.iters)
         print(f"ozimmu_b200 n={n} s={s} cluster={cm}x{cn}: {ms:.3f} ms  {flop / ms / 1e9:.2f} TFLOP/s-equiv  "
