@@ -30,6 +30,7 @@
 //    tile (OZK_FUSED_ONE_TILE_PER_PAIR), which makes the hardware CTA scheduler the tile queue of the block pipelines.
 //    (A device-side tile queue gated by ready flags was built and measured in rounds 1-2 and removed: 28 ms against
 //    26 ms for the multi-launch pipeline at 8192^3 end to end, profiles/r2_e2e_sweep.txt.)
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -611,7 +612,6 @@ struct PerDeviceOnce {
 int g_tile_override = 0;
 // 128 x 128 tiles (64 rows per CTA, UMMA M = 128): -1 = chosen per problem, 1 = forced, 0 = never (a forced tile width)
 int g_half_rows_override = -1;
-constexpr uint64_t kHalfRowsCost = 125;   // cost-model units of one 128 x 128 tile (a 256 x BN tile: 55 + BN)
 
 // ---- tuning knob (read once; OZIMMU_B200_LOCKSTEP overrides) ----
 // rasterisation band height in tiles (OZIMMU_B200_GROUP_M, read once; default 8: a wave of 74 pairs covers 8 x 9.25
@@ -759,34 +759,56 @@ int env_tile_width() {
   return v;
 }
 
+// ---- which tile for which problem ------------------------------------------------------------------------------
+// Measured time of one round of tiles -- 72 of the 74 CTA pairs busy, s = 9 -- per tile shape and k, in microseconds
+// (tools/tile_cost_probe.py, profiles/r2_tile_cost_probe.txt): `first` = a launch of one round, `next` = what a second
+// round adds (128-wide tiles lose ~14 % at k = 8192 once several rounds stream through L2 without lockstep help).  Per
+// area of C the narrow tiles win at small k (the per-product epilogue weighs more than the operand bytes: 128-wide costs
+// 0.79 x of 256-wide at k = 1024) and lose at large k.  Other split counts scale every entry alike.
+struct TileCost {
+  int rows, width;          // rows of C per CTA pair, tile width
+  float first[4], next[4];  // k = 1024, 2048, 4096, 8192
+};
+constexpr TileCost kTileCosts[] = {
+    {256, 256, {250, 360, 634, 1243}, {254, 368, 634, 1256}}, {256, 240, {232, 340, 585, 1150}, {233, 340, 583, 1166}},
+    {256, 224, {195, 315, 558, 1087}, {239, 317, 607, 1076}}, {256, 208, {170, 285, 535, 1024}, {205, 286, 535, 1018}},
+    {256, 192, {155, 257, 498, 946}, {164, 259, 500, 931}},   {256, 128, {99, 157, 321, 631}, {93, 152, 345, 718}},
+    {128, 128, {71, 124, 273, 579}, {81, 157, 368, 770}},
+};
+// piecewise linear in k between the measured points, proportional below the first and along the last slope beyond
+double interp_k(const float (&v)[4], double k) {
+  const double ks[4] = {1024, 2048, 4096, 8192};
+  if (k <= ks[0]) return v[0] * (0.35 + 0.65 * k / ks[0]);   // a tile keeps ~1/3 of its k = 1024 time as k -> 0
+  for (int i = 0; i < 3; i++)
+    if (k <= ks[i + 1]) return v[i] + (v[i + 1] - v[i]) * (k - ks[i]) / (ks[i + 1] - ks[i]);
+  return v[3] + (v[3] - v[2]) * (k - ks[3]) / (ks[3] - ks[2]);
+}
+
 int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
   int bn = g_tile_override ? g_tile_override : env_tile_width();
   bool half_rows = g_half_rows_override > 0;
   if (bn == 0 && g_half_rows_override <= 0) {
-    // A launch costs rounds x (time of one tile) with rounds = ceil(tiles / resident pairs).  Measured at 8192^3, s = 9
-    // (profiles/r2_sweep_tile_width.txt): a round of 256 / 240 / 224 / 208 / 192-wide tiles takes 1.28 / 1.19 / 1.20 /
-    // 1.08 / 1.02 ms, i.e. time per tile ~ 55 + BN -- between the tensor-pipe time (~ BN) and the operand-delivery time
-    // (~ 128 + BN/2): BN = 256 moves the fewest bytes per MAC and wins whenever the tile count quantises alike
-    // (8192^3: 14 rounds); a narrower tile wins when it needs fewer rounds x width (4096^3: 192 -> 5 x 247 < 4 x 311).
-    // 128 x 128 tiles (64 rows per CTA): 16 KB per k-step against 24 KB for 256 x 128 -- kHalfRowsCost per tile; they
-    // win when the problem has at most one round of them (1024^3: 64 tiles on 128 SMs instead of 32 on 64).
+    // A persistent launch costs first + (rounds - 1) x next with rounds = ceil(tiles / resident pairs); a one-tile-per-
+    // pair launch shares the GPU with its neighbours in the block pipelines, so what counts is the SM time of its tiles:
+    // tiles x first / (tiles of the measured round).  (Round 1 / early round 2 used rounds x (55 + width), fitted at k = 8192 only.)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint64_t pairs = static_cast<uint64_t>(sms > 1 ? sms / 2 : 1);
-    const uint64_t batch = p.batch ? p.batch : 1;
-    uint64_t best_cost = ~0ull;
-    for (int cand : kTileWidths) {
-      const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 256)) * ceil_div_u32(p.n, cand) * batch;
-      const uint64_t cost = ((tiles + pairs - 1) / pairs) * (55 + cand);
-      if (cost < best_cost) {   // ties go to the wider tile (kTileWidths is descending)
+    const double pairs = static_cast<double>(sms > 1 ? sms / 2 : 1);
+    const double batch = p.batch ? p.batch : 1, k = static_cast<double>(p.k_blocks) * BK;
+    double best_cost = 1e300;
+    for (const TileCost &t : kTileCosts) {   // ties go to the earlier (wider) entry
+      if (t.rows == 128 && g_half_rows_override == 0) continue;
+      const double tiles = static_cast<double>(ceil_div_u32(p.m, t.rows)) * ceil_div_u32(p.n, t.width) * batch;
+      const double rounds = std::ceil(tiles / pairs);
+      const double probe_tiles = t.rows == 128 ? 64.0 : 72.0;   // tiles in the measured round
+      const double cost = p.one_tile_per_pair ? tiles * interp_k(t.first, k) / probe_tiles
+                                              : interp_k(t.first, k) + (rounds - 1) * interp_k(t.next, k);
+      if (cost < best_cost) {
         best_cost = cost;
-        bn = cand;
+        bn = t.width;
+        half_rows = t.rows == 128;
       }
-    }
-    if (g_half_rows_override < 0) {
-      const uint64_t tiles = static_cast<uint64_t>(ceil_div_u32(p.m, 128)) * ceil_div_u32(p.n, 128) * batch;
-      if (((tiles + pairs - 1) / pairs) * kHalfRowsCost < best_cost) half_rows = true;
     }
   }
   if (half_rows) return launch_pair<128, 64>(p, stream);
