@@ -762,7 +762,8 @@ int env_tile_width() {
 // ---- which tile for which problem ------------------------------------------------------------------------------
 // Measured time of one round of tiles -- 72 of the 74 CTA pairs busy, s = 9 -- per tile shape and k, in microseconds
 // (tools/tile_cost_probe.py, profiles/r2_tile_cost_probe.txt): `first` = a launch of one round, `next` = what a second
-// round adds (128-wide tiles lose ~14 % at k = 8192 once several rounds stream through L2 without lockstep help).  Per
+// round adds (128-wide tiles lose ~14 % at k = 8192 once several rounds stream through L2 without lockstep help; the
+// k = 8192 `next` column is the per-round time of whole 8192^3 products, 14-19 rounds, profiles/r2_sweep_tile_width.txt).  Per
 // area of C the narrow tiles win at small k (the per-product epilogue weighs more than the operand bytes: 128-wide costs
 // 0.79 x of 256-wide at k = 1024) and lose at large k.  Other split counts scale every entry alike.
 struct TileCost {
@@ -770,9 +771,9 @@ struct TileCost {
   float first[4], next[4];  // k = 1024, 2048, 4096, 8192
 };
 constexpr TileCost kTileCosts[] = {
-    {256, 256, {250, 360, 634, 1243}, {254, 368, 634, 1256}}, {256, 240, {232, 340, 585, 1150}, {233, 340, 583, 1166}},
-    {256, 224, {195, 315, 558, 1087}, {239, 317, 607, 1076}}, {256, 208, {170, 285, 535, 1024}, {205, 286, 535, 1018}},
-    {256, 192, {155, 257, 498, 946}, {164, 259, 500, 931}},   {256, 128, {99, 157, 321, 631}, {93, 152, 345, 718}},
+    {256, 256, {250, 360, 634, 1243}, {254, 368, 634, 1280}}, {256, 240, {232, 340, 585, 1150}, {233, 340, 583, 1190}},
+    {256, 224, {195, 315, 558, 1087}, {239, 317, 607, 1200}}, {256, 208, {170, 285, 535, 1024}, {205, 286, 535, 1080}},
+    {256, 192, {155, 257, 498, 946}, {164, 259, 500, 1020}},  {256, 128, {99, 157, 321, 631}, {93, 152, 345, 718}},
     {128, 128, {71, 124, 273, 579}, {81, 157, 368, 770}},
 };
 // piecewise linear in k between the measured points, proportional below the first and along the last slope beyond
