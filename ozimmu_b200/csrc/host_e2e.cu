@@ -332,26 +332,42 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     trace.mark(name + " copied out", sout);
     rects++;
   };
-  auto product_rect = [&](std::size_t i0, std::size_t mi, std::size_t j0, std::size_t nj, cudaEvent_t ready) {
+  // `pieces` > 1 (the last rectangles of the call): cut along the long side into that many launches, so that the
+  // copy-out of the first pieces overlaps the products of the later ones and only one piece's D2H trails the last tile
+  auto product_rect = [&](std::size_t i0, std::size_t mi, std::size_t j0, std::size_t nj, cudaEvent_t ready,
+                          std::size_t pieces = 1) {
     if (mi == 0 || nj == 0) return;
     const std::size_t tm = (mi + 255) / 256, tn = (nj + 255) / 256;
-    if (rect_tiles == 0 || tm * tn <= rect_tiles) return product_piece(i0, mi, j0, nj, ready);
+    std::size_t limit = rect_tiles;
+    if (pieces > 1) {
+      const std::size_t per_piece = std::max<std::size_t>(1, (tm * tn + pieces - 1) / pieces);
+      limit = limit == 0 ? per_piece : std::min(limit, per_piece);
+    }
+    if (limit == 0 || tm * tn <= limit) return product_piece(i0, mi, j0, nj, ready);
     if (tn >= tm) {   // wide: pieces of whole tile columns
-      const std::size_t step = std::max<std::size_t>(1, rect_tiles / tm) * 256;
+      const std::size_t step = std::max<std::size_t>(1, limit / tm) * 256;
       for (std::size_t j = 0; j < nj; j += step) product_piece(i0, mi, j0 + j, std::min(step, nj - j), ready);
     } else {          // tall: pieces of whole tile rows
-      const std::size_t step = std::max<std::size_t>(1, rect_tiles / tn) * 256;
+      const std::size_t step = std::max<std::size_t>(1, limit / tn) * 256;
       for (std::size_t i = 0; i < mi; i += step) product_piece(i0 + i, std::min(step, mi - i), j0, nj, ready);
     }
   };
 
-  // arrival order: B0, A0, B1, A1, ... (the longer operand's remaining blocks follow at the end); queue every
-  // copy first so the H2D engine never waits for the host.
+  // arrival order: A0, B0, A1, B1, ... (the longer operand's remaining blocks follow at the end); queue every
+  // copy first so the H2D engine never waits for the host.  A first, so that the LAST rectangle of C is a column block
+  // (op(A) complete x the last block of op(B)): contiguous in a column-major C, it leaves at the full D2H rate, where a
+  // row block of 768 x 8-byte segments reaches 36 GB/s while the GPU is busy (profiles/r2_ubench_pcie_2d.txt).
+  // OZIMMU_B200_E2E_A_FIRST=0 restores B first: 25.65 -> 25.25 ms at 8192^3 (profiles/r2_e2e_tail_sweep.txt).
+  // OZIMMU_B200_E2E_TAIL_PIECES=p cuts the last two rectangles into p launches each, so that only a fraction of their
+  // copy-out trails the last tile; it pays with block edges of 1024 (p = 4: 25.15 ms) but not at the default edge of 768
+  // (p = 1 / 2 / 4: 25.3 / 25.3 / 25.6 ms): off (1) by default.
   // Sharded: the owner uploads ALL of B first and forwards every block as it lands, then its own A.  While B is in
   // flight no rank has much to multiply yet, so NCCL's broadcast kernels find free SMs at once on every GPU; with B
   // interleaved behind A on the owner, each of its broadcasts had to wait for SMs on eight busy GPUs and the step grew
   // with the rank count (8 GPUs: 72 ms, profiles/r2_bench_8gpu_call8.json).  The other ranks receive B at the rate
   // their own blocks of A arrive over their own PCIe links: blocks alternate as on a single GPU.
+  const bool a_first = !sharded && env_size("OZIMMU_B200_E2E_A_FIRST", 1) != 0;
+  const std::size_t tail_pieces = std::max<std::size_t>(1, env_size("OZIMMU_B200_E2E_TAIL_PIECES", 1));
   struct Arrival { int which; std::size_t idx; };
   std::vector<Arrival> order;
   if (sharded && owner) {
@@ -359,7 +375,8 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
     for (std::size_t ia = 0; ia < nab; ia++) order.push_back({0, ia});
   } else {
     for (std::size_t ia = 0, ib = 0; ia < nab || ib < nbb;) {
-      if (ib < nbb && (ib <= ia || ia >= nab)) order.push_back({1, ib++});
+      const bool take_b = a_first ? (ib < nbb && (ib < ia || ia >= nab)) : (ib < nbb && (ib <= ia || ia >= nab));
+      if (take_b) order.push_back({1, ib++});
       else order.push_back({0, ia++});
     }
   }
@@ -372,14 +389,16 @@ int gemm_host_impl(handle_t h, operation_t op_a, operation_t op_b, std::size_t m
   for (const Arrival &x : order) x.which ? copy_b_block(x.idx) : copy_a_block(x.idx);
 
   std::size_t have_a = 0, have_b = 0;  // blocks split so far
-  for (const Arrival &x : order) {
+  for (std::size_t o = 0; o < order.size(); o++) {
+    const Arrival &x = order[o];
+    const std::size_t pieces = o + 2 >= order.size() ? tail_pieces : 1;
     if (x.which) {
       split_b_block(x.idx);
-      product_rect(0, ae[have_a], be[x.idx], be[x.idx + 1] - be[x.idx], h->ev_block_split[1][x.idx]);
+      product_rect(0, ae[have_a], be[x.idx], be[x.idx + 1] - be[x.idx], h->ev_block_split[1][x.idx], pieces);
       have_b++;
     } else {
       split_a_block(x.idx);
-      product_rect(ae[x.idx], ae[x.idx + 1] - ae[x.idx], 0, be[have_b], h->ev_block_split[0][x.idx]);
+      product_rect(ae[x.idx], ae[x.idx + 1] - ae[x.idx], 0, be[have_b], h->ev_block_split[0][x.idx], pieces);
       have_a++;
     }
   }

@@ -112,15 +112,18 @@ def test_fused_blocks_equal_whole(m, n, k, row_edges, col_edges, beta, width):
     assert torch.equal(got.view(torch.int64), want.view(torch.int64))
 
 
-@pytest.mark.parametrize("panel,rowblock,one_tile,rect_tiles", [
-    ("256", "256", None, None), ("512", "0", "0", None), ("0", "512", None, "2"), ("768", "1024", "0", "3"),
-    ("512", "512", "1", "1"), (None, None, None, None)])
-def test_gemm_host_block_schedules(handle, panel, rowblock, one_tile, rect_tiles, monkeypatch):
+@pytest.mark.parametrize("panel,rowblock,one_tile,rect_tiles,a_first,tail_pieces", [
+    ("256", "256", None, None, None, None), ("512", "0", "0", None, "0", "1"), ("0", "512", None, "2", None, "3"),
+    ("768", "1024", "0", "3", "0", None), ("512", "512", "1", "1", None, "8"), ("256", "512", None, None, "0", "2"),
+    (None, None, None, None, None, None)])
+def test_gemm_host_block_schedules(handle, panel, rowblock, one_tile, rect_tiles, a_first, tail_pieces, monkeypatch):
     """Every block schedule of the host-operand entry (square blocks, column panels only, row blocks only, the
-    default; persistent or one-tile-per-pair launches; rectangles cut into several launches) gives the bits of the
-    device entry; ragged sizes, padded leading dimensions, all op combinations."""
+    default; persistent or one-tile-per-pair launches; rectangles cut into several launches; A or B travelling first;
+    the last rectangles cut into pieces) gives the bits of the device entry; ragged sizes, padded leading dimensions,
+    all op combinations."""
     for name, v in (("OZIMMU_B200_E2E_PANEL", panel), ("OZIMMU_B200_E2E_ROWBLOCK", rowblock),
-                    ("OZIMMU_B200_E2E_ONE_TILE", one_tile), ("OZIMMU_B200_E2E_RECT_TILES", rect_tiles)):
+                    ("OZIMMU_B200_E2E_ONE_TILE", one_tile), ("OZIMMU_B200_E2E_RECT_TILES", rect_tiles),
+                    ("OZIMMU_B200_E2E_A_FIRST", a_first), ("OZIMMU_B200_E2E_TAIL_PIECES", tail_pieces)):
         if v is None:
             monkeypatch.delenv(name, raising=False)
         else:
