@@ -492,7 +492,7 @@ def run_ours(args) -> dict:
         roof = {"bound": "tensor", "achieved": int8_ops / kms / 1e9, "peak": peak, "unit": "TFLOP/s",
                 "frac": int8_ops / kms / 1e9 / peak, "traffic": traffic,
                 "hbm_gbs": (traffic / (kms * 1e-3) / 1e9) if traffic else None, "hbm_peak_gbs": peaks["hbm"],
-                "kernel": "oz_gemm_pair_kernel<256>", "kernel_ms": kms, "launches_timed": len(durs),
+                "kernel": "oz_gemm_pair_kernel<256, 128>", "kernel_ms": kms, "launches_timed": len(durs),
                 "ops_per_launch": int8_ops,
                 "note": f"int8 TOP/s; peak = 2 x bf16_tflops (burst: launches timed one at a time) of MEASURED_PEAKS.json "
                         f"({peaks['src']}); 2 x sustained bf16 = {2.0 * peaks['bf16_sustained'] if peaks['bf16_sustained'] else None}; "
