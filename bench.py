@@ -328,6 +328,21 @@ def timed_loop_ranks(fn, steps: int, warmup: int, world: int, sampler=None):
     return max(per_rank), per_rank
 
 
+def accuracy_vs_cublas(a, b, c, n: int) -> dict:
+    """The second half of BASELINE's metric: max relative error of C against cuBLAS DGEMM (torch.mm in FP64) on the
+    same operands, plus the relative residual in the Frobenius norm.  a, b, c: column-major n x n, flat."""
+    import torch
+    # column-major C = A B  <=>  row-major view: C^T = B^T A^T, and a flat column-major buffer viewed (n, n) IS the transpose
+    ref = torch.mm(b.view(n, n), a.view(n, n)).reshape(-1)
+    diff = (c - ref).abs()
+    out = {"max_rel_err_vs_cublas_dgemm": float((diff / ref.abs().clamp_min(1e-300)).max().item()),
+           "rel_residual_vs_cublas_dgemm": float((torch.linalg.vector_norm(diff) / torch.linalg.vector_norm(ref)).item()),
+           "how": "torch.mm (cuBLAS DGEMM) on the same device operands after the timed region; max |C - C_cublas| / |C_cublas| "
+                  "over all elements, ||C - C_cublas||_F / ||C_cublas||_F"}
+    del ref, diff
+    return out
+
+
 def sharded_parity(oz, h, comm, rank, world, n, k, a, lda, b, c, ldc, rows, mode, sample=256):
     """Bit-compare every rank's first `sample` rows of C (computed by the sharded step, inside its full row block)
     with a SINGLE-GPU product of the same rows of A on rank 0.  Returns {"checked", "max_ulp", "rows_per_rank"}."""
@@ -436,6 +451,8 @@ def run_ours(args) -> dict:
     value = flop_step / ms / 1e9
     parity = sharded_parity(oz, h, comm, rank, world, n, n, a, n, b, c, n, n, mode) if world > 1 else None
     bcast_ms = bcast_alone_ms(comm, oz, b, world) if world > 1 else None
+    # rank 0's block against cuBLAS DGEMM (at N > 1 the other ranks' B is only a receive buffer: step() has filled it)
+    accuracy = accuracy_vs_cublas(a, b, c, n) if rank == 0 else None
 
     # ---- end to end: HOST operands through the C-ABI ------------------------------------------------
     ha = torch.empty(n * n, dtype=torch.float64).pin_memory(); ha.copy_(a)
@@ -520,7 +537,7 @@ def run_ours(args) -> dict:
                       "timing": "CUDA events on the call stream, inputs (1 GiB) larger than L2 (126 MB) so no flush",
                       "parallelism": f"rows{world}"},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": base,
-           "per_rank_ms": per_rank, "bcast_ms": bcast_ms, "parity": parity,
+           "per_rank_ms": per_rank, "bcast_ms": bcast_ms, "parity": parity, "accuracy": accuracy,
            "tc_fraction": int8_ops_rank / ms / 1e9 / (2.0 * peaks["bf16"]), "config4": config4}
     return out if rank == 0 else {}
 
@@ -550,6 +567,7 @@ def run_reference(args) -> dict:
     sampler = ClockSampler(local)
     ms = timed_loop(step, args.steps, args.warmup, 1, sampler)
     clocks = sampler.stop()
+    accuracy = accuracy_vs_cublas(a, b, c, n)
     flop = 2.0 * n * n * n
     ha = torch.empty(n * n, dtype=torch.float64).pin_memory(); ha.copy_(a)
     hb = torch.empty(n * n, dtype=torch.float64).pin_memory(); hb.copy_(b)
@@ -573,7 +591,7 @@ def run_reference(args) -> dict:
             "data": "synthetic urand01 (0,1], seeded torch.rand on device",
             "config": {"workload": WORKLOAD.format(n=n, s=s),
                        "timing": "CUDA events, inputs larger than L2"},
-            "clocks": clocks,
+            "clocks": clocks, "accuracy": accuracy,
             "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": 0, "kind": "reference",
                              "sample": "oracle/_ref/libozref.so: the unmodified reference ozIMMU (its own sources built for sm_100), "
                                        "whole workload per step ON THE GPU -- the reference has no CPU implementation of this path"},

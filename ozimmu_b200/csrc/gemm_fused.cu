@@ -785,6 +785,19 @@ double interp_k(const float (&v)[4], double k) {
   return v[3] + (v[3] - v[2]) * (k - ks[3]) / (ks[3] - ks[2]);
 }
 
+// SM count of the current device (queried once per device: the choice below runs on every launch)
+int current_device_sms() {
+  static int cached[kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  if (cached[dev] == 0) {
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    cached[dev] = sms;   // benign race: every thread writes the same value
+  }
+  return cached[dev];
+}
+
 int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
   int bn = g_tile_override ? g_tile_override : env_tile_width();
   bool half_rows = g_half_rows_override > 0;
@@ -792,9 +805,7 @@ int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
     // A persistent launch costs first + (rounds - 1) x next with rounds = ceil(tiles / resident pairs); a one-tile-per-
     // pair launch shares the GPU with its neighbours in the block pipelines, so what counts is the SM time of its tiles:
     // tiles x first / (tiles of the measured round).  (Round 1 / early round 2 used rounds x (55 + width), fitted at k = 8192 only.)
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = current_device_sms();
     const double pairs = static_cast<double>(sms > 1 ? sms / 2 : 1);
     const double batch = p.batch ? p.batch : 1, k = static_cast<double>(p.k_blocks) * BK;
     double best_cost = 1e300;
