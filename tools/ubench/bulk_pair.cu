@@ -5,9 +5,16 @@
 // mbarrier (shared::cluster address) -- is that legal for non-tensor bulk copies?
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
-constexpr uint32_t kChunk = 16384, kRing = 5;
+#ifndef CHUNK
+#define CHUNK 16384
+#endif
+#ifndef RING
+#define RING 5
+#endif
+constexpr uint32_t kChunk = CHUNK, kRing = RING;   // -DCHUNK=8192 -DRING=12: the stages of the 128 x 128 tile
 constexpr uint32_t kSmem = kRing * 2 * kChunk + 256;
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void wait_parity(uint32_t bar, uint32_t parity) {
@@ -57,17 +64,18 @@ k(const uint8_t *__restrict__ g, uint32_t chunks, uint32_t iters, uint32_t share
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-int main() {
+// usage: bulk_pair [grid (CTAs, even; default: all SMs)] [chunks in the working set (default 4096)]
+int main(int argc, char **argv) {
   int sms;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const uint32_t chunks = 4096;
+  const uint32_t chunks = argc > 2 ? static_cast<uint32_t>(atoi(argv[2])) : 4096;
   uint8_t *g;
   unsigned long long *out, *h = new unsigned long long[512];
   cudaMalloc(&g, static_cast<size_t>(chunks) * kChunk);
   cudaMemset(g, 1, static_cast<size_t>(chunks) * kChunk);
   cudaMalloc(&out, sizeof(unsigned long long) * 512);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-  const int grid = sms / 2 * 2;
+  const int grid = argc > 1 && atoi(argv[1]) > 0 ? atoi(argv[1]) / 2 * 2 : sms / 2 * 2;
   struct Cfg { uint32_t shared; int remote; uint32_t iters; } cfgs[] = {{1, 0, 4000}, {1, 0, 4000}, {8, 0, 4000}, {16, 0, 4000},
                                                                         {1, 1, 5}};  // remote: legality only (one ring pass)
   for (auto c : cfgs) {
@@ -82,8 +90,8 @@ int main() {
     cudaMemcpy(h, out, sizeof(unsigned long long) * 2 * grid, cudaMemcpyDeviceToHost);
     double b = 0, cyc = 0;
     for (int i = 0; i < grid; i++) { b += h[2 * i]; cyc += h[2 * i + 1]; }
-    printf("2 x 16 KB linear bulk copies per stage, 5 stages, %u CTAs share each A chunk, remote-barrier=%d: %s %.3f ms, %.1f B/clk/SM, %.2f TB/s chip\n",
-           c.shared, c.remote, cudaGetErrorString(err), ms, cyc > 0 ? b / cyc : 0.0, b / (ms * 1e-3) / 1e12);
+    printf("2 x %u KB linear bulk copies per stage, %u stages, %d CTAs, working set %.0f MB, %u CTAs share each A chunk, remote-barrier=%d: %s %.3f ms, %.1f B/clk/SM, %.2f TB/s chip\n",
+           kChunk / 1024, kRing, grid, chunks * (kChunk / 1048576.0), c.shared, c.remote, cudaGetErrorString(err), ms, cyc > 0 ? b / cyc : 0.0, b / (ms * 1e-3) / 1e12);
     fflush(stdout);
     if (err != cudaSuccess) break;
   }
