@@ -502,6 +502,26 @@ def run_ours(args) -> dict:
             if i >= 2:
                 durs.append(e0.elapsed_time(e1))
         kms = sum(durs) / len(durs)
+        # the practical int8 peak at the same clocks -- cuBLAS' own int8 GEMM (torch._int_mm, 8192^3) timed the
+        # same way (one launch at a time); it has no FP64 epilogue to run
+        cublas_int8 = None
+        try:
+            ai = torch.randint(-127, 128, (n, n), dtype=torch.int8, device="cuda")
+            bi = torch.randint(-127, 128, (n, n), dtype=torch.int8, device="cuda")
+            cd = []
+            for i in range(8):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch._int_mm(ai, bi.t())
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    cd.append(e0.elapsed_time(e1))
+            cms = sum(cd) / len(cd)
+            cublas_int8 = {"tops": 2.0 * n * n * n / cms / 1e9, "ms": cms, "how": "torch._int_mm 8192^3 (cuBLASLt int8), launches timed one at a time"}
+            del ai, bi
+        except Exception as e:  # noqa: BLE001
+            cublas_int8 = {"unavailable": str(e)[:120]}
         int8_ops = s * (s + 1) / 2 * 2.0 * n * n * n
         peaks = measured_peaks()
         peak = 2.0 * peaks["bf16"]
@@ -510,6 +530,8 @@ def run_ours(args) -> dict:
                 "frac": int8_ops / kms / 1e9 / peak, "traffic": traffic,
                 "hbm_gbs": (traffic / (kms * 1e-3) / 1e9) if traffic else None, "hbm_peak_gbs": peaks["hbm"],
                 "kernel": "oz_gemm_pair_kernel<256, 128>", "kernel_ms": kms, "launches_timed": len(durs),
+                "cublas_int8": cublas_int8,
+                "frac_of_cublas_int8": (int8_ops / kms / 1e9 / cublas_int8["tops"]) if cublas_int8 and "tops" in cublas_int8 else None,
                 "ops_per_launch": int8_ops,
                 "note": f"int8 TOP/s; peak = 2 x bf16_tflops (burst: launches timed one at a time) of MEASURED_PEAKS.json "
                         f"({peaks['src']}); 2 x sustained bf16 = {2.0 * peaks['bf16_sustained'] if peaks['bf16_sustained'] else None}; "
