@@ -8,20 +8,25 @@
 // follows SURVEY App. A.4/A.5 exactly (same FMA sequence => bit-identical C).
 //
 // Design (B200 / sm_100a), see DESIGN.md 3.2 for the measurements behind each choice:
-//  * CTA pair = one 256 x BN tile of C (tcgen05.mma.cta_group::2.kind::i8, UMMA M=256, N=BN, K=32), BN = 256
-//    (default) or 128 (small problems); 192..240 are built for tuning (deeper operand ring, PairCfg).  Each CTA owns 128 x BN outputs for the whole pair list, so the FP64
+//  * CTA pair = one 256 x BN tile of C (tcgen05.mma.cta_group::2.kind::i8, UMMA M=256, N=BN, K=32), BN = 256 for large
+//    problems, 240 ... 128 where the tile count quantises better or k is small (dispatch_fused: a table of measured
+//    per-round times per tile shape and k).  Each CTA owns 128 x BN outputs for the whole pair list, so the FP64
 //    accumulators never leave the SM: 96 columns per epilogue thread in registers, the rest (BN=256: 32) in SMEM.
+//    Small problems: 128 x 128 tiles, 64 rows per CTA (UMMA M=128, template parameter BMC_ = 64): twice as many tiles,
+//    8 KB of A per k-step; the pair MMA then folds a CTA's 64 x 128 block of D over all 128 TMEM lanes (PairCfg).
 //  * Operands: int8 slices in the blocked, pre-swizzled layout of oz_common.cuh -- every 128-row x 128-byte tile
 //    is 16 KB contiguous, so a stage is filled by two linear bulk copies (cp.async.bulk: 54-76 B/clk/SM) rather
-//    than tiled TMA boxes of 128 separate rows (33-48 B/clk/SM): the kernel is bound by operand delivery.
+//    than tiled TMA boxes of 128 separate rows (33-48 B/clk/SM).  What bounds the kernel is the SS-mode MMA itself
+//    (~45 clocks per instruction on top of its tensor time: 80 % of the pipe) and, sustained, power.
 //  * Roles per CTA: warp 0 producer (bulk copies, completing on the CTA's own `full` barrier), warp 1 MMA issuer
 //    (leader CTA only), warp 2 TMEM allocator, warp 3 relay (non-leader CTA: forwards "my stage landed" to the
 //    leader, because a bulk copy can only signal a barrier in the destination CTA), warps 4-11 epilogue.
 //    Role loops run on the uniform datapath (whole warp loops, one elected lane issues).
 //  * int32 products sit in TMEM buffers (BN=256: 2 x 256 columns, BN=128: 4 x 128), so the MMAs of product p+1
 //    overlap the epilogue of product p.  tcgen05.commit multicasts "stage free" / "product ready" to both CTAs.
-//  * Epilogue per product: tcgen05.ld 16 columns, (double)p by the magic-number trick (exact), then
-//    acc = fma(p, 2^(32-rshift), acc).  After the last pair: x = acc*2^-44*amax[r]*bmax[c]; C = alpha*x (+ beta*C).
+//  * Epilogue per product: tcgen05.ld 16 columns (128-wide tiles keep the next load in flight), (double)p by the
+//    magic-number trick (exact), then acc = fma(p, 2^(32-rshift), acc).  After the last pair: x = acc*2^-44*amax[r]*bmax[c];
+//    C = alpha*x (+ beta*C).  The "buffer drained" hand-off to the MMA warp is a relaxed arrive (no release fence).
 //  * Soft lockstep between CTA pairs keeps the pairs of one wave within a few k-steps of each other so that they
 //    share slice panels through L2.
 //  * Tile queue: entry x tiles_m x tiles_n (entry = index in a strided batch, ozk_gemm_i8_fused_batched), static
