@@ -641,25 +641,31 @@ uint32_t lockstep_window() {
 
 constexpr uint32_t kSyncCounters = 1u << 16;  // per buffer: 64 Ki intervals = 1 Mi k-steps per CTA pair
 constexpr int kSyncBuffers = 8;               // launches that may be in flight at once without sharing
-// per device: a small ring of counter buffers, allocated on first use and kept for the life of the process (more
-// than kSyncBuffers launches in flight at once share counters, which only costs pacing time-outs)
+// per device: a small ring of counter buffers, allocated TOGETHER on the first paced launch on that device and kept for
+// the life of the process (allocating them one by one made each of the first eight multi-round launches pay a
+// cudaMalloc, i.e. a device synchronisation: 2048^3 measured 0.56 ms instead of 0.37 ms over its first ten calls,
+// profiles/r2_sizes_vs_reference.txt).  More than kSyncBuffers launches in flight at once share counters, which only
+// costs pacing time-outs.
 uint32_t *next_sync_buffer() {
   static std::mutex mu;
-  static uint32_t *pool[kMaxDevices][kSyncBuffers] = {};
+  static uint32_t *pool[kMaxDevices] = {};
+  static bool failed[kMaxDevices] = {};
   static int next[kMaxDevices] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
-  const int i = next[dev];
-  next[dev] = (i + 1) % kSyncBuffers;
-  if (pool[dev][i] == nullptr) {
-    if (cudaMalloc(&pool[dev][i], kSyncCounters * sizeof(uint32_t)) != cudaSuccess) {
-      pool[dev][i] = nullptr;
+  if (pool[dev] == nullptr) {
+    if (failed[dev]) return nullptr;
+    if (cudaMalloc(&pool[dev], static_cast<size_t>(kSyncBuffers) * kSyncCounters * sizeof(uint32_t)) != cudaSuccess) {
+      pool[dev] = nullptr;
+      failed[dev] = true;
       cudaGetLastError();
       return nullptr;
     }
   }
-  return pool[dev][i];
+  const int i = next[dev];
+  next[dev] = (i + 1) % kSyncBuffers;
+  return pool[dev] + static_cast<size_t>(i) * kSyncCounters;
 }
 
 template <uint32_t BN_, uint32_t BMC_ = 128>
