@@ -277,17 +277,40 @@ oz_gemm_pair_kernel(const FusedParams p) {
         const uint32_t b_row0 = tn * BN_ + rank * Cfg::kBRows;
         const uint32_t b_avail = b_row0 < p.b_rows ? p.b_rows - b_row0 : 0u;
         const uint32_t b_rows1 = min(min(Cfg::kBRows, 128u - (b_row0 & 127u)), b_avail);
-        const uint32_t b_rows2 = min(Cfg::kBRows - b_rows1, b_avail - b_rows1);
+        // (BN = 256 / 128: the half-tile never straddles two slice tiles -- one piece, known at compile time)
+        constexpr bool kTwoPieces = (BN_ != 256 && BN_ != 128);
+        const uint32_t b_rows2 = kTwoPieces ? min(Cfg::kBRows - b_rows1, b_avail - b_rows1) : 0u;
         const size_t b_tile = b_row0 >> 7;
         const size_t b_sub = static_cast<size_t>(b_row0 & 127u) * BK;
         const uint32_t stage_tx = BM * BK + (b_rows1 + b_rows2) * BK;
         for (uint32_t grp = 0; grp < p.groups; grp++)
         for (PairIter it(p); it.valid(); it.next()) {
-          const int8_t *a_src = a_base + group_plane_a(p, grp) * p.a_plane_bytes +
+          // running source pointers: one 16 KB slice tile further per k-step
+          const int8_t *a_ptr = a_base + group_plane_a(p, grp) * p.a_plane_bytes +
                                 ((it.a_id() - 1) * static_cast<size_t>(p.rt_a) + a_tile) * p.k_blocks * kTileBytes + a_sub;
-          const int8_t *b_src = b_base + group_plane_b(p, grp) * p.b_plane_bytes +
+          const int8_t *b_ptr = b_base + group_plane_b(p, grp) * p.b_plane_bytes +
                                 ((it.b_id() - 1) * static_cast<size_t>(p.rt_b) + b_tile) * p.k_blocks * kTileBytes + b_sub;
-          const int8_t *b_src2 = b_src - b_sub + static_cast<size_t>(p.k_blocks) * kTileBytes;  // next row tile
+          const size_t b2_off = static_cast<size_t>(p.k_blocks) * kTileBytes - b_sub;   // same k-step, next row tile
+          auto fill_stage = [&]() {
+            ptx::mbar_wait(empty_bar(stage), ph ^ 1u);
+            const uint32_t dst = smem_base + stage * Cfg::kStageBytes;
+            if (issuer) {
+              ptx::mbar_expect_tx(full_bar(stage), stage_tx);
+              ptx::bulk_load(dst, a_ptr, BM * BK, full_bar(stage));
+              if (b_rows1) ptx::bulk_load(dst + BM * BK, b_ptr, b_rows1 * BK, full_bar(stage));
+              if (kTwoPieces && b_rows2)
+                ptx::bulk_load(dst + BM * BK + b_rows1 * BK, b_ptr + b2_off, b_rows2 * BK, full_bar(stage));
+            }
+            a_ptr += kTileBytes;
+            b_ptr += kTileBytes;
+            if (++stage == kStagesP) { stage = 0; ph ^= 1u; }
+          };
+          if (!lockstep) {
+            // unpaced (single-round launches, block pipelines, batches): nothing but the ring in the loop
+            for (uint32_t kb = 0; kb < p.k_blocks; kb++) fill_stage();
+            g += p.k_blocks;
+            continue;
+          }
           for (uint32_t kb = 0; kb < p.k_blocks; kb++, g++) {
             if (lockstep && (g % kSyncEvery) == 0) {
               const uint32_t j = g / kSyncEvery;
@@ -312,18 +335,7 @@ oz_gemm_pair_kernel(const FusedParams p) {
                 if (!ok) lockstep = false;
               }
             }
-            ptx::mbar_wait(empty_bar(stage), ph ^ 1u);
-            const uint32_t dst = smem_base + stage * Cfg::kStageBytes;
-            if (issuer) {
-              ptx::mbar_expect_tx(full_bar(stage), stage_tx);
-              ptx::bulk_load(dst, a_src + static_cast<size_t>(kb) * kTileBytes, BM * BK, full_bar(stage));
-              if (b_rows1)
-                ptx::bulk_load(dst + BM * BK, b_src + static_cast<size_t>(kb) * kTileBytes, b_rows1 * BK, full_bar(stage));
-              if (b_rows2)
-                ptx::bulk_load(dst + BM * BK + b_rows1 * BK, b_src2 + static_cast<size_t>(kb) * kTileBytes, b_rows2 * BK,
-                               full_bar(stage));
-            }
-            if (++stage == kStagesP) { stage = 0; ph ^= 1u; }
+            fill_stage();
           }
         }
       }
@@ -340,7 +352,10 @@ oz_gemm_pair_kernel(const FusedParams p) {
           const uint32_t d_tmem = tmem_base + buf * Cfg::kBufStride;
           for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
             ptx::mbar_wait(full_bar(stage), ph);            // my tiles landed
-            ptx::mbar_wait_cluster(pfull_bar(stage), ph);   // the peer CTA's tiles landed (relayed)
+            // the peer CTA's tiles landed (relayed with a relaxed remote arrive: there is nothing to acquire -- the
+            // payload was written by the async proxy into the peer's SMEM -- and an acquire.cluster wait costs an L1
+            // invalidate, CCTL.IVALL, per k-step)
+            ptx::mbar_wait(pfull_bar(stage), ph);
             ptx::tc_fence_after();
             const uint32_t a_smem = smem_base + stage * Cfg::kStageBytes;
             const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_smem);
