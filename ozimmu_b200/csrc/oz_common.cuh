@@ -17,8 +17,8 @@ inline void count_launch(unsigned n = 1) { g_launch_count += n; }
 // One operand plane is [slice][row tile][k block][128 rows][128 bytes]: every 128-row x 128-byte tile is
 // 16 KB CONTIGUOUS in HBM and already carries the shared-memory 128-byte swizzle (16-byte chunk c of row r
 // sits at chunk c ^ (r & 7)), so the GEMM kernel stages a tile with ONE linear bulk copy
-// (cp.async.bulk, 54-76 B/clk/SM measured) instead of a tiled TMA box of 128 separate rows (33-48 B/clk/SM;
-// profiles/r1_ubench_sm_ingest.txt, r1_ubench_bulk_pair.txt).  Rows are padded to a multiple of 256 (one CTA
+// (cp.async.bulk, 54-76 B/clk/SM measured; ~115 clocks per copy whatever its size, profiles/r2_ubench_bulk_per_copy.txt)
+// instead of a tiled TMA box of 128 separate rows (33-48 B/clk/SM; profiles/r1_ubench_sm_ingest.txt, r1_ubench_bulk_pair.txt).  Rows are padded to a multiple of 256 (one CTA
 // pair's 2 x 128 rows), k to a multiple of 128; padding is zero.
 constexpr size_t kTileRows = 128, kTileK = 128, kTileBytes = kTileRows * kTileK;
 inline size_t slice_pitch(size_t k) { return (k + kTileK - 1) / kTileK * kTileK; }              // bytes of K per row

@@ -79,10 +79,10 @@ def test_split_block_rejects_misaligned_blocks():
     (900, 1100, 1030, [0, 768, 900], [0, 512, 1024, 1100]),
 ])
 @pytest.mark.parametrize("beta", [0.0, -0.75])
-@pytest.mark.parametrize("width", [0, 240, 224, 208, 192])
+@pytest.mark.parametrize("width", [0, 240, 224, 208, 192, 128, -128])
 def test_fused_blocks_equal_whole(m, n, k, row_edges, col_edges, beta, width):
     """block launches (all flag combinations, every tile width -- widths below 256 read B rows past the block and, at
-    the plane's end, must not read past the plane) == one whole launch"""
+    the plane's end, must not read past the plane; -128 = the 128 x 128 tile with 64 rows per CTA) == one whole launch"""
     L = oz.lib()
     s, nbits = 9, int(L.ozk_bits_per_int8(k))
     a = to_dev(oracle_lib.gen_matrix("exp_rand-1", m * k, 31))   # op_t A: k x m column-major == rows contiguous
@@ -98,7 +98,7 @@ def test_fused_blocks_equal_whole(m, n, k, row_edges, col_edges, beta, width):
     streams = [torch.cuda.Stream() for _ in range(3)]
     torch.cuda.synchronize()
     i = 0
-    L.ozk_set_cluster_shape(0, width)
+    L.ozk_set_cluster_shape(*((64, 128) if width < 0 else (0, width)))
     for r0, r1 in zip(row_edges[:-1], row_edges[1:]):
         for q0, q1 in zip(col_edges[:-1], col_edges[1:]):
             st = streams[i % 3]   # concurrent launches on several streams, as the host pipeline issues them

@@ -48,12 +48,20 @@ k(const uint8_t *__restrict__ g, uint32_t chunks, uint32_t iters, uint32_t share
       if (it >= kRing && !(remote && rank == 1)) wait_parity(bar, ((it / kRing) - 1) & 1u);
       if (!remote) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kChunk) : "memory");
       else if (rank == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4 * kChunk) : "memory");
-      const uint8_t *sa = g + static_cast<size_t>((grp * 977u + it * 2u) % chunks) * kChunk;
-      const uint8_t *sb = g + static_cast<size_t>((grp * 977u + it * 2u + 1u + 31u * (blockIdx.x % shared)) % chunks) * kChunk;
+      // chunks is a power of two: no division in the issuing thread's loop
+      const uint8_t *sa = g + static_cast<size_t>((grp * 977u + it * 2u) & (chunks - 1u)) * kChunk;
+      const uint8_t *sb = g + static_cast<size_t>((grp * 977u + it * 2u + 1u + 31u * (blockIdx.x & (shared - 1u))) & (chunks - 1u)) * kChunk;
+#ifdef ONECOPY
+      (void)sb;   // one copy of 2 x kChunk contiguous bytes per stage
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(base + slot * 2 * kChunk), "l"(g + static_cast<size_t>((grp * 977u + it * 2u) & (chunks - 2u)) * kChunk),
+                     "r"(2 * kChunk), "r"(tgt) : "memory");
+#else
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(base + slot * 2 * kChunk), "l"(sa), "r"(kChunk), "r"(tgt) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(base + slot * 2 * kChunk + kChunk), "l"(sb), "r"(kChunk), "r"(tgt) : "memory");
+#endif
     }
     if (!(remote && rank == 1))
       for (uint32_t it = (iters > kRing ? iters - kRing : 0); it < iters; it++) wait_parity(bar0 + 8 * (it % kRing), (it / kRing) & 1u);
