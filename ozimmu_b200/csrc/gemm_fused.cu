@@ -347,7 +347,9 @@ oz_gemm_pair_kernel(const FusedParams p) {
       for (uint32_t t = pair_id; t < num_tiles; t += num_pairs) {
         for (uint32_t grp = 0; grp < p.groups; grp++)
         for (PairIter it(p); it.valid(); it.next()) {
-          ptx::mbar_wait_cluster(tempty_bar(buf), bph ^ 1u);
+          // plain wait: the peer's epilogue warps arrive relaxed (nothing to acquire: they only finished READING the
+          // buffer), and an acquire.cluster wait costs an L1 invalidate per product
+          ptx::mbar_wait(tempty_bar(buf), bph ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * Cfg::kBufStride;
           for (uint32_t kb = 0; kb < p.k_blocks; kb++) {

@@ -21,8 +21,12 @@ using namespace oz;
 #ifndef KN
 #define KN 256
 #endif
+#ifndef KM
+#define KM 256   // UMMA M of the pair: 256 (128 rows of A per CTA) or 128 (64 rows per CTA; SS modes only)
+#endif
 constexpr uint32_t kN = KN, kStages = 5, kThreads = 224;   // warps: 0 producer, 1 MMA, 2-5 A stream, 6 relay
-constexpr uint32_t kABytes = 128 * 128, kBBytes = (kN / 2) * 128;
+constexpr uint32_t kM = KM;
+constexpr uint32_t kABytes = (kM / 2) * 128, kBBytes = (kN / 2) * 128;
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kSmem = kStages * kStageBytes + 1024 + 256;
 constexpr uint32_t kAColsTmem = 512 - 64;   // two A buffers of 32 columns at the top of TMEM
@@ -98,7 +102,7 @@ k(const uint8_t *__restrict__ g, uint32_t chunks, uint32_t steps, int mode, unsi
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      constexpr uint32_t idesc = ptx::make_i8_idesc(256, kN);
+      constexpr uint32_t idesc = ptx::make_i8_idesc(kM, kN);
       const bool issuer = ptx::elect_one();
       uint32_t stage = 0, ph = 0;
       for (uint32_t i = 0; i < steps; i++) {
@@ -204,7 +208,7 @@ int main(int argc, char **argv) {
   const int grid = sms / 2 * 2;
   const char *names[] = {"SS, no loads", "SS + ring (A 16 KB + B)", "TS + ring (B only)", "TS + ring (B) + LDG.nc.no_allocate -> STTM (A)",
                          "TS + ring (B) + LDG (L1) -> STTM (A)"};
-  for (int mode = 0; mode < 5; mode++) {
+  for (int mode = 0; mode < (kM == 256 ? 5 : 2); mode++) {
     cudaMemset(out, 0, sizeof(h));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -216,8 +220,8 @@ int main(int argc, char **argv) {
     cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
     double cyc = 0; int n = 0;
     for (int i = 0; i < grid; i += 2) { cyc += static_cast<double>(h[i]); n++; }
-    printf("N=%u mode %d (%s): %s  %.3f ms, %.1f clk per k-step (tensor time %u), %.0f int8 TOP/s\n", kN, mode, names[mode],
-           cudaGetErrorString(err), ms, cyc / n / steps, 2 * kN, 2.0 * 256 * kN * 128 * steps * (grid / 2) / (ms * 1e-3) / 1e12);
+    printf("M=%u N=%u mode %d (%s): %s  %.3f ms, %.1f clk per k-step (tensor time %u), %.0f int8 TOP/s\n", kM, kN, mode, names[mode],
+           cudaGetErrorString(err), ms, cyc / n / steps, kM * kN / 128, 2.0 * kM * kN * 128 * steps * (grid / 2) / (ms * 1e-3) / 1e12);
     fflush(stdout);
     if (err != cudaSuccess) return 1;
   }
