@@ -192,6 +192,13 @@ int ozk_zgemm_combine(size_t m, size_t n, const double *x4, const double alpha[2
  * restores the per-problem choice.  OZIMMU_B200_TILE_N=w forces a width from the environment. */
 int ozk_set_cluster_shape(int cm, int cn);
 
+/* Diagnostic (no GPU needed): the tile the fused kernel would use for an m x n x k problem of `batch` entries --
+ * rows of C per CTA pair (256 or 128) and tile width -- from the measured per-round cost table (persistent launch:
+ * first + (rounds - 1) * next; one_tile_per_pair != 0: SM time of the tiles).  sms <= 0: the current device's SM count
+ * (148 without a device).  Ignores ozk_set_cluster_shape / OZIMMU_B200_TILE_N.  Returns 0, or 1 for a null pointer. */
+int ozk_fused_tile_choice(size_t m, size_t n, size_t k, size_t batch, int one_tile_per_pair, int sms, int *rows,
+                          int *width);
+
 /* Debug/verification launcher: the raw int32 product of ONE slice pair (1-based ids), written
  * column-major with ld = m -- what the reference's cublasGemmEx call produces
  * (src/gemm.cu:315-329).  Same tcgen05 main loop as ozk_gemm_i8_fused. */

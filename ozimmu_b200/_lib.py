@@ -62,6 +62,7 @@ PROTOTYPES = {
                                   c_uint, c_uint, c_double, c_double, c_void_p, c_size_t, c_void_p]),
     "ozk_scale_c": (c_int, [c_size_t, c_size_t, c_double, c_void_p, c_size_t, c_void_p]),
     "ozk_set_cluster_shape": (c_int, [c_int, c_int]),
+    "ozk_fused_tile_choice": (c_int, [c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "ozk_gemm_i8_pair": (c_int, [c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_uint, c_uint, c_uint,
                                  c_void_p, c_void_p]),
     "ozk_mantissa_loss": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_int, c_uint,

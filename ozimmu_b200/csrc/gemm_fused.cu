@@ -826,30 +826,38 @@ int current_device_sms() {
   return cached[dev];
 }
 
+// the tile with the lowest modelled cost: (rows of C per CTA pair, width)
+void choose_tile(uint32_t m, uint32_t n, double k, double batch, bool one_tile_per_pair, int sms, bool allow_half_rows,
+                 int &rows_out, int &width_out) {
+  // A persistent launch costs first + (rounds - 1) x next with rounds = ceil(tiles / resident pairs); a one-tile-per-
+  // pair launch shares the GPU with its neighbours in the block pipelines, so what counts is the SM time of its tiles:
+  // tiles x first / (tiles of the measured round).  (Round 1 / early round 2 used rounds x (55 + width), fitted at k = 8192 only.)
+  const double pairs = static_cast<double>(sms > 1 ? sms / 2 : 1);
+  double best_cost = 1e300;
+  rows_out = 256, width_out = 256;
+  for (const TileCost &t : kTileCosts) {   // ties go to the earlier (wider) entry
+    if (t.rows == 128 && !allow_half_rows) continue;
+    const double tiles = static_cast<double>(ceil_div_u32(m, t.rows)) * ceil_div_u32(n, t.width) * batch;
+    const double rounds = std::ceil(tiles / pairs);
+    const double probe_tiles = t.rows == 128 ? 64.0 : 72.0;   // tiles in the measured round
+    const double cost = one_tile_per_pair ? tiles * interp_k(t.first, k) / probe_tiles
+                                          : interp_k(t.first, k) + (rounds - 1) * interp_k(t.next, k);
+    if (cost < best_cost) {
+      best_cost = cost;
+      rows_out = t.rows;
+      width_out = t.width;
+    }
+  }
+}
+
 int dispatch_fused(const FusedParams &p, cudaStream_t stream) {
   int bn = g_tile_override ? g_tile_override : env_tile_width();
   bool half_rows = g_half_rows_override > 0;
   if (bn == 0 && g_half_rows_override <= 0) {
-    // A persistent launch costs first + (rounds - 1) x next with rounds = ceil(tiles / resident pairs); a one-tile-per-
-    // pair launch shares the GPU with its neighbours in the block pipelines, so what counts is the SM time of its tiles:
-    // tiles x first / (tiles of the measured round).  (Round 1 / early round 2 used rounds x (55 + width), fitted at k = 8192 only.)
-    const int sms = current_device_sms();
-    const double pairs = static_cast<double>(sms > 1 ? sms / 2 : 1);
-    const double batch = p.batch ? p.batch : 1, k = static_cast<double>(p.k_blocks) * BK;
-    double best_cost = 1e300;
-    for (const TileCost &t : kTileCosts) {   // ties go to the earlier (wider) entry
-      if (t.rows == 128 && g_half_rows_override == 0) continue;
-      const double tiles = static_cast<double>(ceil_div_u32(p.m, t.rows)) * ceil_div_u32(p.n, t.width) * batch;
-      const double rounds = std::ceil(tiles / pairs);
-      const double probe_tiles = t.rows == 128 ? 64.0 : 72.0;   // tiles in the measured round
-      const double cost = p.one_tile_per_pair ? tiles * interp_k(t.first, k) / probe_tiles
-                                              : interp_k(t.first, k) + (rounds - 1) * interp_k(t.next, k);
-      if (cost < best_cost) {
-        best_cost = cost;
-        bn = t.width;
-        half_rows = t.rows == 128;
-      }
-    }
+    int rows = 256;
+    choose_tile(p.m, p.n, static_cast<double>(p.k_blocks) * BK, p.batch ? p.batch : 1, p.one_tile_per_pair != 0,
+                current_device_sms(), g_half_rows_override < 0, rows, bn);
+    half_rows = rows == 128;
   }
   if (half_rows) return launch_pair<128, 64>(p, stream);
   switch (bn) {
@@ -886,6 +894,17 @@ FusedParams base_params(size_t m, size_t n, size_t pitch, const int8_t *a_slices
 }  // namespace oz
 
 // Test/tuning hook: force the tile of the fused kernel (see ozimmu_b200.h); anything else restores the per-problem choice.
+extern "C" int ozk_fused_tile_choice(size_t m, size_t n, size_t k, size_t batch, int one_tile_per_pair, int sms, int *rows,
+                                     int *width) {
+  if (rows == nullptr || width == nullptr) return 1;
+  if (sms <= 0) sms = oz::current_device_sms();
+  const size_t pitch = (k + 127) / 128 * 128;
+  oz::choose_tile(static_cast<uint32_t>(m), static_cast<uint32_t>(n), static_cast<double>(pitch),
+                  static_cast<double>(batch ? batch : 1), one_tile_per_pair != 0, sms, true, *rows, *width);
+  cudaGetLastError();   // a process without a device: the SM-count query failed, which is fine here
+  return 0;
+}
+
 extern "C" int ozk_set_cluster_shape(int cm, int cn) {
   oz::g_tile_override = (cm == 0 && oz::tile_width_ok(cn)) ? cn : 0;
   // (64, 128): force the 128 x 128 tile (64 rows per CTA); a forced width excludes it; anything else: per-problem choice

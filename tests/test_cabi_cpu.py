@@ -108,3 +108,28 @@ def test_host_block_edges(extent, want, taper):
         assert sizes[-1] <= sizes[0] and sizes[-2] <= sizes[0]     # the blocks that arrive last are not the big ones
 
 
+
+
+def test_fused_tile_choice():
+    """host logic of the product dispatch (no GPU): the measured cost table picks 256 x 256 tiles for the BASELINE sizes,
+    128 x 128 tiles (64 rows per CTA) where a problem would otherwise leave SMs idle, 128-wide tiles at small k, and the
+    SM-time criterion for the one-tile launches of the block pipelines"""
+    import ctypes as C
+    L = oz.lib()
+
+    def choice(m, n, k, batch=1, one_tile=0, sms=148):
+        rows, width = C.c_int(), C.c_int()
+        assert L.ozk_fused_tile_choice(m, n, k, batch, one_tile, sms, C.addressof(rows), C.addressof(width)) == 0
+        assert (rows.value, width.value) in {(256, w) for w in (256, 240, 224, 208, 192, 128)} | {(128, 128)}
+        return rows.value, width.value
+
+    assert choice(8192, 8192, 8192) == (256, 256)            # headline
+    assert choice(2048, 16384, 16384) == (256, 256)          # config 4, one rank of eight
+    assert choice(16384, 16384, 16384) == (256, 256)
+    assert choice(1024, 1024, 1024) == (128, 128)            # 64 tiles on 128 SMs instead of 32 on 64
+    assert choice(300, 200, 520) == (128, 128)
+    assert choice(1536, 1536, 1536) == (256, 128)            # one round of 72 tiles; small k favours the narrow tile
+    assert choice(2048, 2048, 2048) == (256, 128)
+    assert choice(768, 768, 8192, one_tile=1) == (256, 256)  # block of the host-operand pipeline: SM time per area
+    assert choice(64, 64, 64, batch=4096)[0] == 128          # a big batch of tiny GEMMs: the cheapest single tile
+    assert L.ozk_fused_tile_choice(8, 8, 8, 1, 0, 148, None, None) == 1
