@@ -204,17 +204,6 @@ def max_over_ranks(ms: float, world: int) -> float:
     return float(t.item())
 
 
-def clock_ramp(fn, calls: int = 12) -> None:
-    """Untimed calls before the W warm-up steps of the device-resident loop: a GPU that has been idle sits at its idle
-    clock (120 MHz observed) and needs some tens of milliseconds of load to ramp up; three 17 ms warm-up steps are enough
-    in practice, this makes it independent of W.  A fixed number of calls (a step contains a collective at N > 1: every
-    rank must run the same number).  Used by both arms alike."""
-    import torch
-    for _ in range(calls):
-        fn()
-    torch.cuda.synchronize()
-
-
 def timed_loop(fn, steps: int, warmup: int, world: int, sampler=None) -> float:
     """ms per step: W untimed steps, then exactly K steps between barrier+sync, CUDA events, max over ranks."""
     import torch
@@ -454,7 +443,6 @@ def run_ours(args) -> dict:
                                max_panels=panels) == 0
 
     sampler = ClockSampler(local)
-    clock_ramp(step)
     launches0 = oz.launch_count()
     ms, per_rank = timed_loop_ranks(step, args.steps, args.warmup, world, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
@@ -599,7 +587,6 @@ def run_reference(args) -> dict:
         ref.gemm(0, 0, n, n, n, 1.0, a, n, b, n, 0.0, c, n, s - 1)
 
     sampler = ClockSampler(local)
-    clock_ramp(step)
     ms = timed_loop(step, args.steps, args.warmup, 1, sampler)
     clocks = sampler.stop()
     accuracy = accuracy_vs_cublas(a, b, c, n)
