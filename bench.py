@@ -209,9 +209,9 @@ def timed_loop(fn, steps: int, warmup: int, world: int, sampler=None) -> float:
     import torch
     for _ in range(warmup):
         fn()
-    barrier_sync(world)
     if sampler is not None:
-        sampler.start()
+        sampler.start()      # BEFORE the barrier: see timed_loop_ranks
+    barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -314,9 +314,12 @@ def timed_loop_ranks(fn, steps: int, warmup: int, world: int, sampler=None):
     import torch
     for _ in range(warmup):
         fn()
-    barrier_sync(world)
+    # the clock sampler (NVML initialisation + a thread, tens of milliseconds on rank 0 only) starts BEFORE the barrier:
+    # started after it, rank 0 entered the timed loop late and every other rank's first broadcast -- inside ITS timed
+    # region -- waited for it: 2-5 ms per step on the receiving ranks of a 10-step loop (calls 40 / 42)
     if sampler is not None:
         sampler.start()
+    barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
