@@ -312,6 +312,7 @@ constexpr uint32_t kBandRows = 256;
 struct ColsBands {
   uint32_t bands, p1_per_band, p2_per_band;   // CTAs per band: row-max pass, cut pass
   uint32_t rchunks, rtiles;                   // 256-row chunks (pass 1) and 32-row tiles (pass 2) per full band
+  uint32_t col_chunk;                         // columns per row-max CTA (kColChunk; fewer for small matrices)
   uint32_t *band_done;                        // [batch][bands], zeroed before the launch
 };
 
@@ -347,9 +348,9 @@ split_cols_kernel(int8_t *__restrict__ out_, const size_t pitch, double *__restr
   if (j < cb.p1_per_band) {
     // ---- pass 1: exponent maximum of 256 rows over 64 columns (thread <-> row: coalesced column segments) ----
     const size_t r = row_lo + static_cast<size_t>(j % cb.rchunks) * 256 + threadIdx.x;
-    const uint32_t c0 = (j / cb.rchunks) * kColChunk;
+    const uint32_t c0 = (j / cb.rchunks) * cb.col_chunk;
     if (r < rows && r < row_lo + kBandRows && c0 < len) {
-      const uint32_t c1 = min(len, c0 + kColChunk);
+      const uint32_t c1 = min(len, c0 + cb.col_chunk);
       uint32_t e = 0;
 #pragma unroll 8
       for (uint32_t c = c0; c < c1; c++) e = max(e, exp_field(__ldg(in + (static_cast<size_t>(c) * ld + r) * es)));
@@ -525,7 +526,10 @@ int launch_split(int8_t *out, size_t pitch, size_t plane_rows, double *max_exp, 
     cb.bands = static_cast<uint32_t>((rows + kBandRows - 1) / kBandRows);
     cb.rchunks = kBandRows / 256;
     cb.rtiles = kBandRows / kColsRows;
-    cb.p1_per_band = cb.rchunks * ceil_div_u32(static_cast<uint32_t>(len), kColChunk);
+    // a small matrix (the whole grid fits on the GPU at once) is latency-bound: four times as many row-max CTAs,
+    // each with a quarter of the dependent load batches
+    cb.col_chunk = (rows * len <= (2048u * 2048u)) ? kColChunk / 4 : kColChunk;
+    cb.p1_per_band = cb.rchunks * ceil_div_u32(static_cast<uint32_t>(len), cb.col_chunk);
     cb.p2_per_band = cb.rtiles * static_cast<uint32_t>((pitch + kColsK - 1) / kColsK);
     cb.band_done = band_counters(static_cast<size_t>(cb.bands) * bt.count, stream);
     if (cb.band_done == nullptr) return static_cast<int>(cudaErrorMemoryAllocation);
