@@ -586,18 +586,6 @@ int mtk::ozimmu::gemm_streamed_b(handle_t h, const operation_t op_A, const opera
                                  const double *beta, double *const c_ptr, const std::size_t ldc,
                                  const compute_mode_t compute_mode, const std::size_t num_panels,
                                  const std::size_t *col_edges, const cudaEvent_t *ready) {
-  return oz::host::gemm_streamed_b_impl(h, op_A, op_B, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc,
-                                        compute_mode, num_panels, col_edges, ready, /*one_product=*/false);
-}
-
-// one_product: every panel is SPLIT as it lands, but the products run as ONE ordinary launch after the last panel's
-// split -- the transfer hides the split of B (all but the last panel's) without paying for a cut product
-int oz::host::gemm_streamed_b_impl(handle_t h, const operation_t op_A, const operation_t op_B, const std::size_t m,
-                                   const std::size_t n, const std::size_t k, const double *alpha,
-                                   const double *const a_ptr, const std::size_t lda, const double *const b_ptr,
-                                   const std::size_t ldb, const double *beta, double *const c_ptr, const std::size_t ldc,
-                                   const compute_mode_t compute_mode, const std::size_t num_panels,
-                                   const std::size_t *col_edges, const cudaEvent_t *ready, const bool one_product) {
   int arg_error = 0;
   arg_error |= check_shape(op_A, m, k, lda, "A");
   arg_error |= check_shape(op_B, k, n, ldb, "B");
@@ -655,21 +643,6 @@ int oz::host::gemm_streamed_b_impl(handle_t h, const operation_t op_A, const ope
       num_panels == 1 ? 0u
                       : OZK_FUSED_NO_LOCKSTEP |
                             (H::env_or("OZIMMU_B200_STREAMED_ONE_TILE", "1") != "0" ? OZK_FUSED_ONE_TILE_PER_PAIR : 0u);
-  if (one_product && num_panels > 1) {
-    for (std::size_t p = 0; p < num_panels; p++) {
-      const std::size_t j0 = col_edges[p], nj = col_edges[p + 1] - j0;
-      OZ_CUDA_CHECK(cudaStreamWaitEvent(sb, ready[p], 0));
-      if (nj == 0) continue;
-      const double *src = (op_B == op_n) ? b_ptr + j0 * ldb : b_ptr + j0;
-      OZ_KERNEL_CHECK(ozk_split_int8_block(b_sl, w.pitch, n, j0, bmax + j0, scr_b + j0, nj, k, src, ldb, op_B != op_n,
-                                           num_split, bits, 1, sb));
-    }
-    OZ_CUDA_CHECK(cudaEventRecord(h->ev_join, sb));
-    OZ_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));   // s already holds split(A)
-    OZ_KERNEL_CHECK(ozk_gemm_i8_fused(m, n, k, a_sl, b_sl, w.pitch, amax, bmax, num_split, bits, *alpha, *beta, c_ptr, ldc, s));
-    mark_done(h, s);
-    return 0;
-  }
   for (std::size_t p = 0; p < num_panels; p++) {
     const std::size_t j0 = col_edges[p], nj = col_edges[p + 1] - j0;
     if (nj == 0) continue;

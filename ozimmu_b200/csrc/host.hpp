@@ -78,14 +78,6 @@ void ensure_streams(mtk::ozimmu::handle *h);
 // lazily created copy / split / product streams and per-block events (host_e2e.cu)
 void ensure_pipeline_streams(mtk::ozimmu::handle *h);
 
-// gemm_streamed_b with a choice of what the panels feed: a product launch each (one_product = false) or only their
-// splits, with one ordinary product launch at the end (true); api.cu
-int gemm_streamed_b_impl(mtk::ozimmu::handle *h, mtk::ozimmu::operation_t op_A, mtk::ozimmu::operation_t op_B, std::size_t m,
-                         std::size_t n, std::size_t k, const double *alpha, const double *a_ptr, std::size_t lda,
-                         const double *b_ptr, std::size_t ldb, const double *beta, double *c_ptr, std::size_t ldc,
-                         mtk::ozimmu::compute_mode_t compute_mode, std::size_t num_panels, const std::size_t *col_edges,
-                         const cudaEvent_t *ready, bool one_product);
-
 // compute mode `sgemm` (reference src/cublas_helper.cu:84-134): the GEMM in FP32 through cuBLAS (sgemm_mode.cu).
 // `cublas` = a real cuBLAS handle bound to the handle's stream; alpha / beta: 1 (real) or 2 (complex) doubles.
 void gemm_in_f32(mtk::ozimmu::handle *h, cublasHandle_t cublas, mtk::ozimmu::operation_t op_a,

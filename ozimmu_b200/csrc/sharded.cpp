@@ -196,15 +196,9 @@ int gemm_sharded_impl(handle_t h, H::Comm *c, operation_t op_a, operation_t op_b
   }
   OZ_CUDA_CHECK(cudaEventRecord(c->ev_end, c->stream));
   int rc = 0;
-  // what a landed panel triggers (max_panels > 1): its own product launch (default), or its split only with ONE product
-  // launch after the last panel (OZIMMU_B200_SHARDED_ONE_PRODUCT=1).  Both measured at the config-4 shape on 4 GPUs
-  // (profiles/r2_sharded_probe_4gpu_config4.txt): 1 panel 37.9 ms; 2 / 4 panels with their own products 38.7 / 39.7 ms;
-  // split-only panels 39.2-41.2 / 48.9-50.6 ms (the panel splits queue behind NCCL's broadcast CTAs) -- one panel stays
-  // the default of the callers.
-  const bool one_product = H::env_or("OZIMMU_B200_SHARDED_ONE_PRODUCT", "0") == "1";
   if (m_local != 0)
-    rc = H::gemm_streamed_b_impl(h, op_a, op_b, m_local, n, k, alpha, a, lda, b, ldb, beta, cc, ldc, mode, np, edges.data(),
-                                 ready.data(), one_product);
+    rc = gemm_streamed_b(h, op_a, op_b, m_local, n, k, alpha, a, lda, b, ldb, beta, cc, ldc, mode, np, edges.data(),
+                         ready.data());
   // B must stay untouched until the owner's sends are done / is complete on the receivers when the call's work is
   OZ_CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_end, 0));
   return rc;

@@ -52,13 +52,9 @@ def report(name, per_rank):
 report("product alone (no broadcast)", timed(lambda: oz.gemm(h, 0, 0, rows, n, n, 1.0, a, rows, b, n, 0.0, c, rows, mode)))
 for rep in range(2):
     for panels in panel_list:
-        # what a landed panel triggers: its split only (one product launch at the end) or its own product launch
-        for per_panel in ("0", "1") if panels > 1 else ("0",):
-            os.environ["OZIMMU_B200_SHARDED_ONE_PRODUCT"] = "0" if per_panel == "1" else "1"
-            report(f"sharded_gemm panels={panels} {'product per panel' if per_panel == '1' else 'split per panel, one product'}",
-                   timed(lambda: oz.sharded_gemm(h, comm, 0, 0, rows, n, n, 1.0, a, rows, b, n, 0.0, c, rows, mode, src=0,
-                                                 max_panels=panels)))
-os.environ["OZIMMU_B200_SHARDED_ONE_PRODUCT"] = "0"
+        report(f"sharded_gemm panels={panels}",
+               timed(lambda: oz.sharded_gemm(h, comm, 0, 0, rows, n, n, 1.0, a, rows, b, n, 0.0, c, rows, mode, src=0,
+                                             max_panels=panels)))
 os.environ["OZIMMU_B200_STREAMED_ONE_TILE"] = "1"
 if "nohost" in extra:
     oz.destroy(h); comm.destroy(); dist.destroy_process_group()
