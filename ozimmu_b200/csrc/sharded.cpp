@@ -4,10 +4,11 @@
 //
 // Not in the reference (it has no multi-GPU path); SURVEY 8e / BASELINE.json config 4: row blocks of A and C per GPU,
 // one broadcast of B from its owner, no reduction (K is never split) => every rank's block is bit-identical to the
-// single-GPU result.  B travels in column panels on the communicator's own stream and each panel of C is computed as
-// soon as its columns have landed (gemm_streamed_b): split(A) and the first panels' products hide the rest of the
-// broadcast.  The product launches run one CTA pair per tile at low stream priority, so NCCL's broadcast kernels get
-// their SMs whenever a tile ends instead of waiting for a persistent kernel to drain.
+// single-GPU result.  Default (max_panels <= 1): ONE broadcast on the communicator's own high-priority stream with
+// split(A) running meanwhile, then split(B) and the ordinary persistent product launch.  max_panels > 1: B travels in
+// column panels and each panel of C is computed as soon as its columns have landed (gemm_streamed_b, one CTA pair per
+// tile at low stream priority so that NCCL's kernels get SMs whenever a tile ends) -- measured slower on 2, 4 and 8
+// GPUs, kept as the caller's choice.
 #include <dlfcn.h>
 #include <link.h>
 
